@@ -1,0 +1,128 @@
+/* posetraj_b200 — C ABI of the B200-native PoseTraj denoising hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer: the path is
+ * plain Python (`ControlNetSDVModel.forward`, `UNetSpatioTemporalConditionControlNetModel.forward`,
+ * `EulerDiscreteScheduler.step`, the loop in `StableVideoDiffusionPipelineControlNet.__call__`).
+ * The Python mirror of those classes (posetraj_b200/*.py) lowers every forward onto the entry
+ * points below; INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - Every device buffer (inputs, outputs, workspaces) is owned by the caller; the library never
+ *     allocates or frees device memory and keeps no reference past the call.
+ *   - All launches are stream-ordered on the `stream` argument (a cudaStream_t passed as void*).
+ *   - Return value: 0 on success, otherwise a cudaError_t-compatible code (argument errors return
+ *     cudaErrorInvalidValue = 1); `pt_last_error()` returns a thread-local message.
+ *   - Activations are NHWC / token-major bf16 (`[rows, C]`, row = ((b*F+f)*H + y)*W + x) unless stated.
+ */
+#ifndef POSETRAJ_B200_H_
+#define POSETRAJ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+const char* pt_last_error(void);
+int pt_version(void);
+/* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
+int64_t pt_launch_count(void);
+
+/* 128-byte opaque TMA descriptor (CUtensorMap); must be 64-byte aligned in host memory. */
+typedef struct PtTensorMap {
+  uint64_t opaque[16];
+} PtTensorMap;
+
+/* Encode a bf16 tiled tensor map with SWIZZLE_128B and zero out-of-bounds fill.
+ *   rank 2 or 3; dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
+ *   box[0] must be 64 (one 128-byte swizzle row). */
+int pt_tensormap_encode_bf16(PtTensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box);
+
+/* ------------------------------------------------------------------------------------------ */
+/* P7 + P8: fused CFG combine + v-prediction Euler step + next-step model input               */
+/* replaces pipeline/pipeline_stable_video_diffusion_controlnet.py:532-537,567-572 and        */
+/* utils/scheduling_euler_discrete_karras_fix.py:264-288,418-528                              */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct PtCfgEulerArgs {
+  const void* noise_pred;   /* [2, F, HW, ldp] bf16 token-major (row 0 uncond, row 1 cond), or fp32 NCHW if pred_nchw_f32 */
+  int32_t pred_ld;          /* channel stride of noise_pred rows (token-major mode) */
+  int32_t pred_nchw_f32;    /* 1: noise_pred is [2,F,C,H,W] fp32 contiguous (reference layout) */
+  float* latents;           /* [F, C, H, W] fp32, updated in place (the reference's `latents`, batch 1) */
+  const float* guidance;    /* [F] per-frame guidance scale */
+  const float* sigmas;      /* [steps+1] device Karras sigma table (sigmas[steps] = 0) */
+  const int32_t* step_index;/* device scalar: current step i (read); the kernel does not modify it */
+  int32_t F, C, H, W;
+  /* optional fused producer of the next step's model input:
+   * next_in[b, f, y, x, 0:C] = latents_new / sqrt(sigma_next^2 + 1), next_in[..., C:2C] = image_latents[b,f]
+   * written token-major bf16 in the zero-haloed conv layout (see PtGemmArgs map_mode 1), ld = next_ld */
+  void* next_in;            /* may be NULL */
+  const float* image_latents; /* [2, F, C, H, W] fp32 (NCHW) */
+  int32_t next_ld;
+  int32_t next_padded;      /* 1: rows laid out with one zero column/row per image ((H+1)*(W+1) rows/image) */
+  int32_t mode;             /* 0: full step (update latents, next_in uses sigma[i+1]); 1: only build next_in for sigma[i] */
+} PtCfgEulerArgs;
+int pt_cfg_euler_step(const PtCfgEulerArgs* a, void* stream);
+/* *step_index += 1 (stream-ordered, so a captured CUDA graph of one step can be replayed) */
+int pt_step_advance(int32_t* step_index, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* tcgen05 GEMM / implicit-GEMM convolution                                                   */
+/*   D[m, n] = epilogue( sum_t sum_k A[m + shift_t, k] * Wt[n, t*K + k] )                     */
+/* covers every dense contraction of P2/P3/P5: Linear, 1x1 conv, 3x3 conv (9 row-shifted taps */
+/* over the zero-haloed NHWC layout), temporal (3,1,1) conv (3 taps shifted by H*W rows).     */
+/* ------------------------------------------------------------------------------------------ */
+enum { PT_DT_BF16 = 0, PT_DT_F32 = 1 };
+
+typedef struct PtGemmArgs {
+  const PtTensorMap* tmap_a0; /* rank-3 {K0, rows_per_batch, batches}, box {64,128,1} */
+  const PtTensorMap* tmap_a1; /* optional second K-range (channel concat); NULL if unused */
+  const PtTensorMap* tmap_b;  /* rank-2 {num_taps*(K0+K1), N_rows}, box {64, b_box_rows} */
+  int32_t rows_per_batch;     /* A/accumulator row space per batch */
+  int32_t batches;
+  int32_t n_out;              /* number of output columns (GEGLU: the gated width, = half of W rows) */
+  int32_t k0_chunks;          /* K0 / 64 */
+  int32_t k1_chunks;          /* K1 / 64 (0 if no second source) */
+  int32_t num_taps;           /* 1, 3 or 9 */
+  int32_t tap_shift[9];       /* row shift of each tap in the A row space */
+  int32_t block_n;            /* accumulator tile width: multiple of 32, 32..256 (GEGLU: 64/128/192/256) */
+  int32_t geglu;              /* 1: tile = [block_n/2 value rows | block_n/2 gate rows], out = v*gelu(g) */
+  int32_t gate_row_offset;    /* row offset of the gate half inside Wt / bias (GEGLU only) */
+  /* epilogue: val = acc_scale*(acc + bias[n] + rowvec[g(m), n]) + res1_scale*res1[m,n] + res2_scale*res2[m,n] */
+  const float* bias;          /* [>= n rows of Wt] fp32 or NULL */
+  const float* rowvec;        /* fp32 [groups, rowvec_ld] or NULL */
+  int32_t rowvec_ld;
+  int32_t rowvec_mode;        /* 0 none; 1: g = orow / rv_a; 2: g = ((orow / rv_a) * rv_b + orow % rv_b) % rv_c */
+  int32_t rv_a, rv_b, rv_c;
+  float acc_scale;
+  const void* res1;           /* bf16 [out rows, res_ld] or NULL */
+  const void* res2;
+  float res1_scale, res2_scale;
+  int32_t res_ld;
+  /* output */
+  void* out;
+  int32_t out_ld;
+  int32_t out_dtype;          /* PT_DT_BF16 / PT_DT_F32 */
+  /* optional second output: out2[m,n] = val + aux_scale * aux[m,n]  (ControlNet residual injected into the
+   * UNet skip tensor, models/unet_spatio_temporal_condition_controlnet.py:451-459) */
+  void* out2;
+  const void* aux;
+  float aux_scale;
+  /* row mapping accumulator row -> output row:
+   *   0: identity (orow = batch*rows_per_batch + r)
+   *   1: zero-haloed image space -> compact: r = img*(pH1*pW1) + y*pW1 + x, valid iff y < pH1-1, x < pW1-1,
+   *      y % ostride == 0, x % ostride == 0; orow = (img*oH + y/ostride)*oW + x/ostride */
+  int32_t map_mode;
+  int32_t pW1, pH1, ostride, oW, oH;
+} PtGemmArgs;
+int pt_gemm(const PtGemmArgs* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSETRAJ_B200_H_ */
