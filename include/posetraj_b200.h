@@ -32,6 +32,8 @@ const char* pt_last_error(void);
 int pt_version(void);
 /* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
 int64_t pt_launch_count(void);
+/* sizeof() of a struct declared in this header, by name (-1 if unknown): ABI self-check for bindings */
+int pt_sizeof(const char* name);
 
 /* 128-byte opaque TMA descriptor (CUtensorMap); must be 64-byte aligned in host memory. */
 typedef struct PtTensorMap {

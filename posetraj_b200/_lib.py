@@ -1,0 +1,144 @@
+"""ctypes binding of libposetraj_b200.so (include/posetraj_b200.h).
+
+There is exactly one compute backend: the hand-written sm_100a library.  If it is missing or a call
+fails, this module raises — there is no eager/CPU fallback anywhere in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libposetraj_b200.so"
+
+
+class PtTensorMap(C.Structure):
+    _fields_ = [("opaque", C.c_uint64 * 16)]
+
+
+class PtCfgEulerArgs(C.Structure):
+    _fields_ = [
+        ("noise_pred", C.c_void_p),
+        ("pred_ld", C.c_int32),
+        ("pred_nchw_f32", C.c_int32),
+        ("latents", C.c_void_p),
+        ("guidance", C.c_void_p),
+        ("sigmas", C.c_void_p),
+        ("step_index", C.c_void_p),
+        ("F", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("next_in", C.c_void_p),
+        ("image_latents", C.c_void_p),
+        ("next_ld", C.c_int32),
+        ("next_padded", C.c_int32),
+        ("mode", C.c_int32),
+    ]
+
+
+class PtGemmArgs(C.Structure):
+    _fields_ = [
+        ("tmap_a0", C.c_void_p),
+        ("tmap_a1", C.c_void_p),
+        ("tmap_b", C.c_void_p),
+        ("rows_per_batch", C.c_int32),
+        ("batches", C.c_int32),
+        ("n_out", C.c_int32),
+        ("k0_chunks", C.c_int32),
+        ("k1_chunks", C.c_int32),
+        ("num_taps", C.c_int32),
+        ("tap_shift", C.c_int32 * 9),
+        ("block_n", C.c_int32),
+        ("geglu", C.c_int32),
+        ("gate_row_offset", C.c_int32),
+        ("bias", C.c_void_p),
+        ("rowvec", C.c_void_p),
+        ("rowvec_ld", C.c_int32),
+        ("rowvec_mode", C.c_int32),
+        ("rv_a", C.c_int32), ("rv_b", C.c_int32), ("rv_c", C.c_int32),
+        ("acc_scale", C.c_float),
+        ("res1", C.c_void_p),
+        ("res2", C.c_void_p),
+        ("res1_scale", C.c_float), ("res2_scale", C.c_float),
+        ("res_ld", C.c_int32),
+        ("out", C.c_void_p),
+        ("out_ld", C.c_int32),
+        ("out_dtype", C.c_int32),
+        ("out2", C.c_void_p),
+        ("aux", C.c_void_p),
+        ("aux_scale", C.c_float),
+        ("map_mode", C.c_int32),
+        ("pW1", C.c_int32), ("pH1", C.c_int32), ("ostride", C.c_int32), ("oW", C.c_int32), ("oH", C.c_int32),
+    ]
+
+
+PT_DT_BF16 = 0
+PT_DT_F32 = 1
+
+# every symbol include/posetraj_b200.h declares: name -> (restype, argtypes)
+_SIGNATURES = {
+    "pt_last_error": (C.c_char_p, []),
+    "pt_version": (C.c_int, []),
+    "pt_launch_count": (C.c_int64, []),
+    "pt_sizeof": (C.c_int, [C.c_char_p]),
+    "pt_tensormap_encode_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64),
+                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "pt_cfg_euler_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_gemm": (C.c_int, [C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class PoseTrajLibError(RuntimeError):
+    pass
+
+
+def exported_symbols() -> list[str]:
+    return list(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library (once). Raises loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise PoseTrajLibError(
+                f"{LIB_PATH} is missing: build it with `python -m posetraj_b200.build` "
+                "(there is no fallback path)")
+        handle = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else 0)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().pt_last_error().decode(errors="replace")
+        if code == 1:
+            raise ValueError(f"{what}: {msg}")
+        raise PoseTrajLibError(f"{what}: CUDA error {code}: {msg}")
+
+
+def aligned_tensormap() -> PtTensorMap:
+    """A 64-byte aligned PtTensorMap (ctypes only guarantees 8)."""
+    raw = (C.c_uint8 * (128 + 64))()
+    addr = C.addressof(raw)
+    off = (-addr) % 64
+    tm = PtTensorMap.from_buffer(raw, off)
+    tm._keepalive = raw
+    return tm
+
+
+def encode_tensormap(base_ptr: int, dims: list[int], strides_bytes: list[int], box: list[int]) -> PtTensorMap:
+    rank = len(dims)
+    tm = aligned_tensormap()
+    d = (C.c_uint64 * rank)(*dims)
+    s = (C.c_uint64 * max(1, rank - 1))(*strides_bytes)
+    b = (C.c_uint32 * rank)(*box)
+    check(lib().pt_tensormap_encode_bf16(C.addressof(tm), C.c_void_p(base_ptr), rank, d, s, b),
+          "pt_tensormap_encode_bf16")
+    return tm

@@ -90,3 +90,12 @@ extern "C" int pt_tensormap_encode_bf16(PtTensorMap* out, const void* base, int 
   }
   return 0;
 }
+
+// ABI self-check: lets the Python binding assert that its ctypes mirrors match the C structs.
+extern "C" int pt_sizeof(const char* name) {
+  if (name == nullptr) return -1;
+  if (!strcmp(name, "PtTensorMap")) return (int)sizeof(PtTensorMap);
+  if (!strcmp(name, "PtCfgEulerArgs")) return (int)sizeof(PtCfgEulerArgs);
+  if (!strcmp(name, "PtGemmArgs")) return (int)sizeof(PtGemmArgs);
+  return -1;
+}

@@ -1,0 +1,207 @@
+"""Launch descriptors for the sm_100a kernels (host side of the C ABI).
+
+Each class pre-builds the C argument struct once (pointers into caller-owned torch buffers, TMA
+descriptors) so that running it is a single ctypes call; the engine keeps lists of them per model
+and replays them every denoise step.  Tensors are only used for their device pointers, shapes and
+strides — the math is in csrc/*.cu.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import PT_DT_BF16, PT_DT_F32
+
+NUM_SMS = 148
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(stream=None) -> int:
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return stream.cuda_stream
+
+
+def pick_block_n(m_tiles: int, n_out: int, geglu: bool = False, k_iters: int = 8) -> int:
+    """Tile-width heuristic: minimise (waves x per-tile cost) over the legal accumulator widths."""
+    best = None
+    cands = [256, 192, 128, 64] if geglu else [256, 224, 192, 160, 128, 96, 64, 32]
+    for bn in cands:
+        per_tile_n = bn // 2 if geglu else bn
+        if per_tile_n > max(32, ((n_out + 31) // 32) * 32):
+            continue
+        n_tiles = math.ceil(n_out / per_tile_n)
+        tiles = m_tiles * n_tiles
+        waves = math.ceil(tiles / NUM_SMS)
+        # MMA time ~ bn per k-iteration; the epilogue (~bn columns of TMEM traffic) overlaps unless K is tiny;
+        # a fixed per-tile overhead covers pipeline fill/drain.
+        cost = waves * (k_iters * max(bn, 128) * 0.5 + 1.5 * bn + 200)
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, bn)
+    assert best is not None
+    return best[1]
+
+
+class Gemm:
+    """D = epilogue(sum_taps A[m + shift] @ W_tap^T) — see PtGemmArgs in include/posetraj_b200.h."""
+
+    def __init__(self, a0: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *,
+                 a1: Optional[torch.Tensor] = None, batches: int = 1, taps: Sequence[int] = (0,),
+                 n_out: Optional[int] = None, block_n: Optional[int] = None, geglu: bool = False,
+                 bias: Optional[torch.Tensor] = None,
+                 rowvec: Optional[torch.Tensor] = None, rowvec_mode: int = 0, rv=(1, 1, 1),
+                 acc_scale: float = 1.0,
+                 res1: Optional[torch.Tensor] = None, res1_scale: float = 1.0,
+                 res2: Optional[torch.Tensor] = None, res2_scale: float = 1.0,
+                 out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_scale: float = 0.0,
+                 halo: Optional[tuple] = None, ostride: int = 1, name: str = "gemm"):
+        assert a0.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+        assert a0.dim() == 2 and w.dim() == 2 and a0.stride(1) == 1 and w.stride(1) == 1
+        self.name = name
+        rows_total, k0 = a0.shape
+        assert rows_total % batches == 0
+        rpb = rows_total // batches
+        k1 = 0
+        if a1 is not None:
+            assert a1.dtype == torch.bfloat16 and a1.shape[0] == rows_total and a1.stride(1) == 1
+            k1 = a1.shape[1]
+        if k0 % 64 or k1 % 64:
+            raise ValueError("Gemm: K must be a multiple of 64")
+        ntaps = len(taps)
+        if w.shape[1] != ntaps * (k0 + k1):
+            raise ValueError(f"Gemm {name}: weight K {w.shape[1]} != taps*(K0+K1) {ntaps * (k0 + k1)}")
+        if geglu:
+            gate_off = w.shape[0] // 2
+            n_out = gate_off if n_out is None else n_out
+        else:
+            gate_off = 0
+            n_out = w.shape[0] if n_out is None else n_out
+        m_tiles = batches * math.ceil(rpb / 128)
+        if block_n is None:
+            block_n = pick_block_n(m_tiles, n_out, geglu, ntaps * (k0 + k1) // 64)
+        self.block_n = block_n
+        b_box_rows = block_n // 2 if geglu else block_n
+
+        self.tm_a0 = _lib.encode_tensormap(a0.data_ptr(), [k0, rpb, batches],
+                                           [a0.stride(0) * 2, a0.stride(0) * 2 * rpb], [64, 128, 1])
+        self.tm_a1 = None
+        if a1 is not None:
+            self.tm_a1 = _lib.encode_tensormap(a1.data_ptr(), [k1, rpb, batches],
+                                               [a1.stride(0) * 2, a1.stride(0) * 2 * rpb], [64, 128, 1])
+        self.tm_b = _lib.encode_tensormap(w.data_ptr(), [w.shape[1], w.shape[0]], [w.stride(0) * 2],
+                                          [64, b_box_rows])
+        a = _lib.PtGemmArgs()
+        a.tmap_a0 = C.addressof(self.tm_a0)
+        a.tmap_a1 = C.addressof(self.tm_a1) if self.tm_a1 is not None else None
+        a.tmap_b = C.addressof(self.tm_b)
+        a.rows_per_batch = rpb
+        a.batches = batches
+        a.n_out = n_out
+        a.k0_chunks = k0 // 64
+        a.k1_chunks = k1 // 64
+        a.num_taps = ntaps
+        for i, s in enumerate(taps):
+            a.tap_shift[i] = int(s)
+        a.block_n = block_n
+        a.geglu = 1 if geglu else 0
+        a.gate_row_offset = gate_off
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.is_contiguous()
+        a.bias = _ptr(bias)
+        if rowvec is not None:
+            assert rowvec.dtype == torch.float32 and rowvec.stride(-1) == 1
+            a.rowvec = _ptr(rowvec)
+            a.rowvec_ld = rowvec.stride(0) if rowvec.dim() == 2 else rowvec.numel()
+            a.rowvec_mode = rowvec_mode if rowvec_mode else 1
+            a.rv_a, a.rv_b, a.rv_c = (int(v) for v in rv)
+        a.acc_scale = acc_scale
+        out_rows = out.shape[0]
+        for r in (res1, res2):
+            if r is not None:
+                assert r.dtype == torch.bfloat16 and r.stride(1) == 1 and r.shape[0] == out_rows
+        if res1 is not None and res2 is not None:
+            assert res1.stride(0) == res2.stride(0)
+        a.res1 = _ptr(res1)
+        a.res2 = _ptr(res2)
+        a.res1_scale = res1_scale
+        a.res2_scale = res2_scale
+        a.res_ld = res1.stride(0) if res1 is not None else (res2.stride(0) if res2 is not None else 0)
+        assert out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+        a.out = out.data_ptr()
+        a.out_ld = out.stride(0)
+        a.out_dtype = PT_DT_BF16 if out.dtype == torch.bfloat16 else PT_DT_F32
+        if out2 is not None:
+            assert aux is not None and out2.dtype == out.dtype and out2.stride(0) == out.stride(0)
+            assert aux.dtype == torch.bfloat16 and aux.stride(0) == out.stride(0)
+            a.out2 = out2.data_ptr()
+            a.aux = aux.data_ptr()
+            a.aux_scale = aux_scale
+        if halo is not None:
+            h, w_ = halo  # unpadded image height/width of the A row space
+            a.map_mode = 1
+            a.pW1 = w_ + 1
+            a.pH1 = h + 1
+            a.ostride = ostride
+            a.oH = (h + ostride - 1) // ostride
+            a.oW = (w_ + ostride - 1) // ostride
+            n_img = rows_total // ((h + 1) * (w_ + 1))
+            assert n_img * (h + 1) * (w_ + 1) == rows_total
+            assert out_rows == n_img * a.oH * a.oW, (out_rows, n_img, a.oH, a.oW)
+        else:
+            a.map_mode = 0
+            assert out_rows == rows_total
+        self.args = a
+        self._keep = (a0, a1, w, out, bias, rowvec, res1, res2, out2, aux)
+        self._argp = C.addressof(a)
+
+    def launch(self, stream_ptr: int) -> None:
+        _lib.check(_lib.lib().pt_gemm(self._argp, stream_ptr), self.name)
+
+
+def conv3x3_taps(w_img: int) -> list[int]:
+    """Row shifts of the 9 taps (ky, kx row-major) in the zero-haloed image space of width w_img + 1."""
+    return [dy * (w_img + 1) + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+
+class CfgEuler:
+    def __init__(self, *, noise_pred: Optional[torch.Tensor], latents: torch.Tensor, guidance: torch.Tensor,
+                 sigmas: torch.Tensor, step_index: torch.Tensor, next_in: Optional[torch.Tensor] = None,
+                 image_latents: Optional[torch.Tensor] = None, next_padded: bool = True, mode: int = 0,
+                 pred_nchw_f32: bool = False):
+        F_, Cc, H, W = latents.shape[-4:]
+        assert latents.dtype == torch.float32 and latents.is_contiguous()
+        assert guidance.dtype == torch.float32 and sigmas.dtype == torch.float32 and step_index.dtype == torch.int32
+        a = _lib.PtCfgEulerArgs()
+        a.noise_pred = _ptr(noise_pred)
+        if noise_pred is not None and not pred_nchw_f32:
+            assert noise_pred.dtype == torch.bfloat16 and noise_pred.dim() == 2
+            a.pred_ld = noise_pred.stride(0)
+        if pred_nchw_f32:
+            assert noise_pred.dtype == torch.float32 and noise_pred.is_contiguous()
+        a.pred_nchw_f32 = 1 if pred_nchw_f32 else 0
+        a.latents = latents.data_ptr()
+        a.guidance = guidance.data_ptr()
+        a.sigmas = sigmas.data_ptr()
+        a.step_index = step_index.data_ptr()
+        a.F, a.C, a.H, a.W = F_, Cc, H, W
+        if next_in is not None:
+            assert next_in.dtype == torch.bfloat16 and next_in.dim() == 2
+            assert image_latents is not None and image_latents.dtype == torch.float32 and image_latents.is_contiguous()
+            a.next_in = next_in.data_ptr()
+            a.image_latents = image_latents.data_ptr()
+            a.next_ld = next_in.stride(0)
+            a.next_padded = 1 if next_padded else 0
+        a.mode = mode
+        self.args = a
+        self._keep = (noise_pred, latents, guidance, sigmas, step_index, next_in, image_latents)
+        self._argp = C.addressof(a)
+
+    def launch(self, stream_ptr: int) -> None:
+        _lib.check(_lib.lib().pt_cfg_euler_step(self._argp, stream_ptr), "pt_cfg_euler_step")
