@@ -12,7 +12,7 @@
 // Structure (per CTA, one CTA per SM, tiles 128 x block_n, K step 64):
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> SWIZZLE_128B smem ring, mbarrier expect_tx)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma kind::f16, accumulators in TMEM, 2 accumulator stages)
-//   warps 2..5    : epilogue       (tcgen05.ld -> bias / row-vector / residual / blend / GEGLU -> global)
+//   warps 2..9    : epilogue       (tcgen05.ld -> bias / row-vector / residual / blend / GEGLU -> global)
 // The three pipelines (smem full/empty, TMEM full/empty, static persistent tile schedule) follow the
 // canonical Blackwell GEMM anatomy; block_n, stage count and tap table are runtime values so the single
 // instantiation covers all shapes.
@@ -24,11 +24,11 @@ namespace pt {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr uint32_t kTmemCols = 512;             // 2 accumulator stages x 256 fp32 columns
 constexpr int kMaxStages = 8;
-constexpr int kSmemCtl = 1024;                  // barriers + tmem pointer live in the first KiB
+constexpr int kSmemCtl = 3072;                  // barriers + tmem pointer (256 B) + staged bias (2 KiB)
 
 struct GemmParams {
   int rows_per_batch, batches, n_out;
@@ -57,8 +57,8 @@ struct alignas(64) TmapParam {
   uint64_t opaque[16];
 };
 
-PT_DEVICE void store8(const GemmParams& p, void* base, size_t off, const float (&v)[8], int nvalid) {
-  if (p.out_dtype == PT_DT_BF16) {
+PT_DEVICE void store8(int out_dtype, void* base, size_t off, const float* v, int nvalid) {
+  if (out_dtype == PT_DT_BF16) {
     bf16* o = reinterpret_cast<bf16*>(base) + off;
     if (nvalid == 8) {
       uint4 u;
@@ -81,53 +81,79 @@ PT_DEVICE void store8(const GemmParams& p, void* base, size_t off, const float (
   }
 }
 
-PT_DEVICE void load8_bf16(const bf16* src, float (&v)[8], int nvalid) {
-  if (nvalid == 8) {
-    uint4 u = ldg_u4(src);
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+// 8 bf16 of a residual-like operand -> raw registers (zero when absent); vector path needs 16-byte alignment,
+// which holds whenever ld % 8 == 0 and n % 8 == 0 (checked on the host for the vector case).
+PT_DEVICE uint4 load8_raw(const bf16* src, int nvalid) {
+  if (nvalid == 8) return ldg_u4(src);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  for (int j = 0; j < nvalid; ++j) {
+    const uint32_t b = (uint32_t)__bfloat16_as_ushort(src[j]);
+    w[j >> 1] |= (j & 1) ? (b << 16) : b;
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+PT_DEVICE void fma8(float* v, uint4 u, float s) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = fmaf(s, a.x, v[0]); v[1] = fmaf(s, a.y, v[1]); v[2] = fmaf(s, b.x, v[2]); v[3] = fmaf(s, b.y, v[3]);
+  v[4] = fmaf(s, c.x, v[4]); v[5] = fmaf(s, c.y, v[5]); v[6] = fmaf(s, d.x, v[6]); v[7] = fmaf(s, d.y, v[7]);
+}
+
+// Operands of one 32-column chunk of one accumulator row, fetched BEFORE the TMEM wait so that their
+// global-load latency overlaps the tcgen05.ld and is paid once per chunk rather than once per 8 columns.
+struct ChunkOperands {
+  uint4 r1[4], r2[4], ax[4];
+  float rv[32];
+};
+
+PT_DEVICE void prefetch_chunk(const GemmParams& p, ChunkOperands& o, int n, long long orow, int grp, bool valid) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    const int nn = n + g8 * 8;
+    const int nvalid = valid ? max(0, min(8, p.n_out - nn)) : 0;
+    o.r1[g8] = (p.res1 != nullptr && nvalid > 0) ? load8_raw(p.res1 + (size_t)orow * p.res_ld + nn, nvalid) : make_uint4(0, 0, 0, 0);
+    o.r2[g8] = (p.res2 != nullptr && nvalid > 0) ? load8_raw(p.res2 + (size_t)orow * p.res_ld + nn, nvalid) : make_uint4(0, 0, 0, 0);
+    o.ax[g8] = (p.out2 != nullptr && nvalid > 0) ? load8_raw(p.aux + (size_t)orow * p.out_ld + nn, nvalid) : make_uint4(0, 0, 0, 0);
+  }
+  if (p.rowvec_mode != 0 && valid) {
+    const float* rv = p.rowvec + (size_t)grp * p.rowvec_ld + n;
+    if (n + 32 <= p.n_out) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(rv) + j);
+        o.rv[4 * j] = t.x; o.rv[4 * j + 1] = t.y; o.rv[4 * j + 2] = t.z; o.rv[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o.rv[j] = (n + j < p.n_out) ? __ldg(rv + j) : 0.f;
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (j < nvalid) ? __bfloat162float(src[j]) : 0.f;
+    for (int j = 0; j < 32; ++j) o.rv[j] = 0.f;
   }
 }
 
-// Finish 8 consecutive output columns [n, n+8) of one accumulator row and write them.
-PT_DEVICE void epilogue8(const GemmParams& p, float (&v)[8], int n, long long orow, int grp) {
-  const int nvalid = min(8, p.n_out - n);
-  if (nvalid <= 0) return;
-  if (p.rowvec_mode != 0) {
-    const float* rv = p.rowvec + (size_t)grp * p.rowvec_ld + n;
+// f[32] already holds acc (+bias, GEGLU applied); finish and store the chunk.
+PT_DEVICE void finish_chunk(const GemmParams& p, float* f, const ChunkOperands& o, int n, long long orow) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nvalid) v[j] += rv[j];
-  }
-  if (p.acc_scale != 1.0f) {
+  for (int g8 = 0; g8 < 4; ++g8) {
+    const int nn = n + g8 * 8;
+    const int nvalid = min(8, p.n_out - nn);
+    if (nvalid <= 0) break;
+    float* v = f + g8 * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= p.acc_scale;
-  }
-  if (p.res1 != nullptr) {
-    float r[8];
-    load8_bf16(p.res1 + (size_t)orow * p.res_ld + n, r, nvalid);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(p.res1_scale, r[j], v[j]);
-  }
-  if (p.res2 != nullptr) {
-    float r[8];
-    load8_bf16(p.res2 + (size_t)orow * p.res_ld + n, r, nvalid);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(p.res2_scale, r[j], v[j]);
-  }
-  store8(p, p.out, (size_t)orow * p.out_ld + n, v, nvalid);
-  if (p.out2 != nullptr) {
-    float r[8];
-    load8_bf16(p.aux + (size_t)orow * p.out_ld + n, r, nvalid);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(p.aux_scale, r[j], v[j]);
-    store8(p, p.out2, (size_t)orow * p.out_ld + n, v, nvalid);
+    for (int j = 0; j < 8; ++j) v[j] = (v[j] + o.rv[g8 * 8 + j]) * p.acc_scale;
+    if (p.res1 != nullptr) fma8(v, o.r1[g8], p.res1_scale);
+    if (p.res2 != nullptr) fma8(v, o.r2[g8], p.res2_scale);
+    store8(p.out_dtype, p.out, (size_t)orow * p.out_ld + nn, v, nvalid);
+    if (p.out2 != nullptr) {
+      fma8(v, o.ax[g8], p.aux_scale);
+      store8(p.out_dtype, p.out2, (size_t)orow * p.out_ld + nn, v, nvalid);
+    }
   }
 }
 
+template <bool kGeglu>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_constant__ TmapParam tmap_a1,
                     const __grid_constant__ TmapParam tmap_b, const __grid_constant__ GemmParams p) {
@@ -141,6 +167,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
   uint64_t* tfull_bar = empty_bar + kMaxStages;            // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                    // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(smem + 256);     // [2][256] bias of the tile, per accumulator stage
   uint8_t* tiles = smem + kSmemCtl;
 
   const int warp = threadIdx.x >> 5;
@@ -160,7 +187,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_mbar_init();
   }
@@ -183,7 +210,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         const int batch = m_tile / p.tiles_per_batch;
         const int r0 = (m_tile - batch * p.tiles_per_batch) * kBlockM;
         const int half = p.block_n >> 1;
-        const int n0 = p.geglu ? n_tile * half : n_tile * p.block_n;
+        const int n0 = kGeglu ? n_tile * half : n_tile * p.block_n;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int arow = r0 + p.tap_shift[tap];
           for (int kc = 0; kc < k_chunks; ++kc) {
@@ -197,7 +224,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
               tma_load_3d(sA, &tmap_a1, &full_bar[stage], (kc - p.k0_chunks) * kBlockK, arow, batch);
             }
             const int kcol = (tap * k_chunks + kc) * kBlockK;
-            if (p.geglu) {
+            if constexpr (kGeglu) {
               tma_load_2d(sB, &tmap_b, &full_bar[stage], kcol, n0);
               tma_load_2d(sB + (size_t)half * kBlockK * 2, &tmap_b, &full_bar[stage], kcol,
                           p.gate_row_offset + n0);
@@ -248,7 +275,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
     }
   } else {
     // ------------------------------ epilogue warps ----------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 warps: warp % 4 selects the TMEM lane quarter (hardware restriction), (warp - 2) / 4 the chunk parity.
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;  // 0..255
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -275,71 +305,77 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
       } else if (p.rowvec_mode == 2) {
         grp = (int)(((orow / p.rv_a) * p.rv_b + orow % p.rv_b) % p.rv_c);
       }
+      if (!valid) { orow = 0; grp = 0; }
+
+      // stage this tile's bias in smem, indexed like the accumulator columns
+      const int half = p.block_n >> 1;
+      const int n0 = kGeglu ? n_tile * half : n_tile * p.block_n;
+      float* sb = sbias + acc * 256;
+      if (etid < p.block_n) {
+        float bv = 0.f;
+        if (p.bias != nullptr) {
+          if constexpr (kGeglu) {
+            const int nn = n0 + (etid < half ? etid : etid - half);
+            if (nn < p.n_out) bv = __ldg(p.bias + (etid < half ? nn : p.gate_row_offset + nn));
+          } else if (n0 + etid < p.n_out) {
+            bv = __ldg(p.bias + n0 + etid);
+          }
+        }
+        sb[etid] = bv;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-
-      if (!p.geglu) {
-        const int n0 = n_tile * p.block_n;
-        const int chunks = p.block_n >> 5;
-        for (int c = 0; c < chunks; ++c) {
+      const int chunks = (kGeglu ? half : p.block_n) >> 5;
+      if (hsel >= chunks) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      for (int c = hsel; c < chunks; c += 2) {
+        const int n = n0 + c * 32;
+        float f[32];
+        if constexpr (kGeglu) {
+          // GEGLU tiles carry bias only (host-checked): out = (x + bx) * gelu(g + bg)
           uint32_t v[32];
-          tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
-          tmem_wait_ld();
-          if (c == chunks - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-          }
-          if (valid) {
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const int n = n0 + c * 32 + g8 * 8;
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g8 * 8 + j]);
-              if (p.bias != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (n + j < p.n_out) f[j] += __ldg(p.bias + n + j);
-              }
-              epilogue8(p, f, n, orow, grp);
-            }
-          }
-        }
-      } else {
-        const int half = p.block_n >> 1;
-        const int n0 = n_tile * half;
-        const int chunks = half >> 5;
-        for (int c = 0; c < chunks; ++c) {
-          uint32_t v[32], g[32];
+          uint32_t g[32];
           tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
           tmem_ld_32x32(t_acc + (uint32_t)(half + c * 32), g);
           tmem_wait_ld();
-          if (c == chunks - 1) {
+          if (c + 2 >= chunks) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float xv = __uint_as_float(v[j]) + sb[c * 32 + j];
+            const float gv = __uint_as_float(g[j]) + sb[half + c * 32 + j];
+            f[j] = xv * gelu_erf_f(gv);
+          }
           if (valid) {
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
-              const int n = n0 + c * 32 + g8 * 8;
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float xv = __uint_as_float(v[g8 * 8 + j]);
-                float gv = __uint_as_float(g[g8 * 8 + j]);
-                if (p.bias != nullptr && n + j < p.n_out) {
-                  xv += __ldg(p.bias + n + j);
-                  gv += __ldg(p.bias + p.gate_row_offset + n + j);
-                }
-                f[j] = xv * gelu_erf_f(gv);
-              }
-              epilogue8(p, f, n, orow, grp);
+              const int nvalid = min(8, p.n_out - (n + g8 * 8));
+              if (nvalid > 0) store8(p.out_dtype, p.out, (size_t)orow * p.out_ld + n + g8 * 8, f + g8 * 8, nvalid);
             }
           }
+        } else {
+          uint32_t v[32];
+          tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
+          ChunkOperands ops;
+          prefetch_chunk(p, ops, n, orow, grp, valid);
+          tmem_wait_ld();
+          if (c + 2 >= chunks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + sb[c * 32 + j];
+          if (valid) finish_chunk(p, f, ops, n, orow);
         }
       }
     }
@@ -378,6 +414,8 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: rowvec_mode without rowvec");
   if (a->out2 != nullptr && a->aux == nullptr)
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: out2 without aux");
+  if (a->geglu && (a->rowvec_mode != 0 || a->res1 != nullptr || a->res2 != nullptr || a->out2 != nullptr || a->acc_scale != 1.0f))
+    return pt_fail(cudaErrorInvalidValue, "pt_gemm: GEGLU tiles support a bias-only epilogue");
 
   GemmParams p;
   p.rows_per_batch = a->rows_per_batch;
@@ -428,7 +466,9 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   const size_t smem_bytes = (size_t)kSmemCtl + (size_t)p.stages * p.stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
@@ -440,6 +480,9 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   memcpy(&ta0, a->tmap_a0, sizeof(TmapParam));
   memcpy(&ta1, a->tmap_a1 ? a->tmap_a1 : a->tmap_a0, sizeof(TmapParam));
   memcpy(&tb, a->tmap_b, sizeof(TmapParam));
-  gemm_tcgen05_kernel<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
+  if (p.geglu)
+    gemm_tcgen05_kernel<true><<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
+  else
+    gemm_tcgen05_kernel<false><<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
   return pt_launched("pt_gemm");
 }
