@@ -118,11 +118,145 @@ typedef struct PtGemmArgs {
   /* row mapping accumulator row -> output row:
    *   0: identity (orow = batch*rows_per_batch + r)
    *   1: zero-haloed image space -> compact: r = img*(pH1*pW1) + y*pW1 + x, valid iff y < pH1-1, x < pW1-1,
-   *      y % ostride == 0, x % ostride == 0; orow = (img*oH + y/ostride)*oW + x/ostride */
+   *      y % ostride == 0, x % ostride == 0; orow = (img*oH + y/ostride)*oW + x/ostride (see out_halo) */
   int32_t map_mode;
   int32_t pW1, pH1, ostride, oW, oH;
+  int32_t out_halo;           /* map_mode 1 only: write the zero-haloed layout of the (strided) output image instead
+                               * of the compact one: orow = (img*(oH+1) + y/ostride)*(oW+1) + x/ostride; halo rows
+                               * are never written (the caller zeroes the buffer once) */
+  int32_t act_silu;           /* apply SiLU after acc_scale and before the residual terms (cond-embedding convs,
+                               * models/controlnet_sdv.py:103-109) */
 } PtGemmArgs;
 int pt_gemm(const PtGemmArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* GroupNorm(32) (+SiLU): diffusers ResnetBlock2D.norm1/2, TemporalResnetBlock.norm1/2 (5-D    */
+/* statistics), TransformerSpatioTemporalModel.norm, conv_norm_out                             */
+/* (models/unet_spatio_temporal_condition_controlnet.py:237-238,494-495)    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct PtGroupNormArgs {
+  const void* x0;           /* bf16 [rows, ld0], channels [0, c0) */
+  const void* x1;           /* optional bf16 [rows, ld1], channels [c0, c0+c1): the un-materialised torch.cat */
+  int32_t c0, c1, ld0, ld1;
+  int32_t rows_per_stat;    /* rows sharing statistics: H*W (per frame) or F*H*W (TemporalResnetBlock) */
+  int32_t num_stat;         /* number of statistics groups: B*F or B */
+  void* stats;              /* workspace: double [num_stat, 32, 2] */
+  const float* gamma;       /* [c0+c1] */
+  const float* beta;
+  float eps;
+  int32_t silu;
+  void* out;                /* bf16 [out rows, out_ld] */
+  int32_t out_ld;
+  int32_t halo;             /* 1: write the zero-haloed image layout ((H+1)*(W+1) rows per image, pads zeroed) */
+  int32_t H, W;
+} PtGroupNormArgs;
+int pt_groupnorm(const PtGroupNormArgs* a, void* stream);
+
+/* LayerNorm (BasicTransformerBlock / TemporalBasicTransformerBlock norms, eps 1e-5).  Optional fused
+ * `hidden_states + emb` of models/modified_svd.py:196-197: addvec[frame] is added first and the sum is also
+ * written to sum_out. */
+typedef struct PtLayerNormArgs {
+  const void* x;            /* bf16 [rows, ld] */
+  int32_t ld;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  void* out;                /* bf16 [rows, out_ld] */
+  int32_t out_ld;
+  int32_t rows, C;
+  const float* addvec;      /* optional fp32 [F, C]; frame = (row / hw) % F */
+  int32_t hw, F;
+  void* sum_out;            /* optional bf16 [rows, out_ld] = x + addvec */
+} PtLayerNormArgs;
+int pt_layernorm(const PtLayerNormArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* attention                                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+/* Spatial self-attention (BasicTransformerBlock.attn1): per image, S = H*W tokens, head_dim 64, non-causal,
+ * scale 64^-0.5.  qkv is the fused projection [n_img*S, 3C] = (Q | K | V); tmap_qkv is a rank-3 tensor map
+ * {3C, S, n_img} with box {64, 128, 1} over it. */
+typedef struct PtAttnSpatialArgs {
+  const PtTensorMap* tmap_qkv;
+  void* out;                /* bf16 [n_img*S, out_ld] */
+  int32_t out_ld;
+  int32_t S, heads, C, n_img;
+} PtAttnSpatialArgs;
+int pt_attention_spatial(const PtAttnSpatialArgs* a, void* stream);
+
+/* Temporal self-attention (TemporalBasicTransformerBlock.attn1, models/modified_svd.py:64-81): for each
+ * (batch, pixel, head) attention over the F frames; rows are (b*F + f)*HW + s. */
+typedef struct PtAttnTemporalArgs {
+  const void* qkv;          /* bf16 [B*F*HW, ld] = (Q | K | V) */
+  int32_t ld;
+  void* out;                /* bf16 [B*F*HW, out_ld] */
+  int32_t out_ld;
+  int32_t B, F, HW, heads, C;
+} PtAttnTemporalArgs;
+int pt_attention_temporal(const PtAttnTemporalArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* small / layout kernels                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+/* out[m, n] (+)= act_out( sum_k act_in(in[m, k]) * W[n, k] + bias[n] ), fp32 in/out, bf16 weights (tiny M):
+ * TimestepEmbedding MLPs, time_emb_proj(silu(emb)), 1-token cross-attention to_v/to_out, cc_projection camera columns */
+typedef struct PtSmallLinearArgs {
+  const float* in;
+  int32_t in_ld;
+  const void* w;            /* bf16 [N, w_ld] */
+  int32_t w_ld;
+  const float* bias;
+  float* out;
+  int32_t out_ld;
+  int32_t M, N, K;
+  int32_t act_in_silu, act_out_silu, accumulate;
+} PtSmallLinearArgs;
+int pt_small_linear(const PtSmallLinearArgs* a, void* stream);
+
+/* Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[m] = [cos(t_m f_k) | sin(t_m f_k)].
+ * If t is NULL every row uses t = 0.25*ln(sigmas[*step_index]) (utils/scheduling_euler_discrete_karras_fix.py:344-347) */
+typedef struct PtSinCosArgs {
+  const float* t;
+  const float* sigmas;
+  const int32_t* step_index;
+  float* out;
+  int32_t out_ld;
+  int32_t M, dim;
+} PtSinCosArgs;
+int pt_timestep_sincos(const PtSinCosArgs* a, void* stream);
+
+/* nearest-neighbour 2x (diffusers Upsample2D) from compact [n,H,W,C] to [n,2H,2W,C], optionally zero-haloed */
+typedef struct PtUpsampleArgs {
+  const void* x;
+  int32_t ld;
+  void* out;
+  int32_t out_ld;
+  int32_t n, H, W, C, halo;
+} PtUpsampleArgs;
+int pt_upsample2x(const PtUpsampleArgs* a, void* stream);
+
+/* direct 3x3 conv (+SiLU), pad 1, stride 1|2, Cin <= 32, Cout in {16, 32}: the narrow head of
+ * ControlNetConditioningEmbeddingSVD (models/controlnet_sdv.py:84-109) */
+typedef struct PtConvDirectArgs {
+  const void* x;            /* fp32 NCHW [n,Cin,H,W] if in_nchw_f32 else bf16 NHWC compact [n*H*W, in_ld] */
+  int32_t in_nchw_f32, in_ld;
+  const float* w;           /* fp32 [3][3][Cin][Cout] */
+  const float* bias;
+  void* out;                /* bf16 NHWC [rows, out_ld], compact or zero-haloed (halo never written) */
+  int32_t out_ld, out_halo;
+  int32_t n, H, W, Cin, Cout, stride, silu;
+} PtConvDirectArgs;
+int pt_conv3x3_direct(const PtConvDirectArgs* a, void* stream);
+
+/* reference tensors are NCHW ([B*F, C, H, W], fp32 or bf16); the kernels work on token-major bf16 */
+typedef struct PtLayoutArgs {
+  const void* nchw_const_unused; /* reserved (keeps the struct layout stable) */
+  void* nchw;               /* NCHW side (source of pt_nchw_to_tokens, destination of pt_tokens_to_nchw) */
+  void* tokens;             /* bf16 [rows, ld] side */
+  int32_t n, C, H, W, ld, halo, nchw_f32;
+} PtLayoutArgs;
+int pt_nchw_to_tokens(const PtLayoutArgs* a, void* stream);
+int pt_tokens_to_nchw(const PtLayoutArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

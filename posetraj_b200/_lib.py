@@ -68,7 +68,52 @@ class PtGemmArgs(C.Structure):
         ("aux_scale", C.c_float),
         ("map_mode", C.c_int32),
         ("pW1", C.c_int32), ("pH1", C.c_int32), ("ostride", C.c_int32), ("oW", C.c_int32), ("oH", C.c_int32),
+        ("out_halo", C.c_int32), ("act_silu", C.c_int32),
     ]
+
+
+
+def _st(name, fields):
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+i32, f32, vp = C.c_int32, C.c_float, C.c_void_p
+
+PtGroupNormArgs = _st("PtGroupNormArgs", [
+    ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32),
+    ("rows_per_stat", i32), ("num_stat", i32), ("stats", vp), ("gamma", vp), ("beta", vp),
+    ("eps", f32), ("silu", i32), ("out", vp), ("out_ld", i32), ("halo", i32), ("H", i32), ("W", i32)])
+
+PtLayerNormArgs = _st("PtLayerNormArgs", [
+    ("x", vp), ("ld", i32), ("gamma", vp), ("beta", vp), ("eps", f32), ("out", vp), ("out_ld", i32),
+    ("rows", i32), ("C", i32), ("addvec", vp), ("hw", i32), ("F", i32), ("sum_out", vp)])
+
+PtAttnSpatialArgs = _st("PtAttnSpatialArgs", [
+    ("tmap_qkv", vp), ("out", vp), ("out_ld", i32), ("S", i32), ("heads", i32), ("C", i32), ("n_img", i32)])
+
+PtAttnTemporalArgs = _st("PtAttnTemporalArgs", [
+    ("qkv", vp), ("ld", i32), ("out", vp), ("out_ld", i32),
+    ("B", i32), ("F", i32), ("HW", i32), ("heads", i32), ("C", i32)])
+
+PtSmallLinearArgs = _st("PtSmallLinearArgs", [
+    ("in_", vp), ("in_ld", i32), ("w", vp), ("w_ld", i32), ("bias", vp), ("out", vp), ("out_ld", i32),
+    ("M", i32), ("N", i32), ("K", i32), ("act_in_silu", i32), ("act_out_silu", i32), ("accumulate", i32)])
+
+PtSinCosArgs = _st("PtSinCosArgs", [
+    ("t", vp), ("sigmas", vp), ("step_index", vp), ("out", vp), ("out_ld", i32), ("M", i32), ("dim", i32)])
+
+PtUpsampleArgs = _st("PtUpsampleArgs", [
+    ("x", vp), ("ld", i32), ("out", vp), ("out_ld", i32),
+    ("n", i32), ("H", i32), ("W", i32), ("C", i32), ("halo", i32)])
+
+PtConvDirectArgs = _st("PtConvDirectArgs", [
+    ("x", vp), ("in_nchw_f32", i32), ("in_ld", i32), ("w", vp), ("bias", vp), ("out", vp),
+    ("out_ld", i32), ("out_halo", i32),
+    ("n", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32), ("stride", i32), ("silu", i32)])
+
+PtLayoutArgs = _st("PtLayoutArgs", [
+    ("nchw_const_unused", vp), ("nchw", vp), ("tokens", vp),
+    ("n", i32), ("C", i32), ("H", i32), ("W", i32), ("ld", i32), ("halo", i32), ("nchw_f32", i32)])
 
 
 PT_DT_BF16 = 0
@@ -85,6 +130,16 @@ _SIGNATURES = {
     "pt_cfg_euler_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_gemm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_layernorm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_attention_spatial": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_attention_temporal": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_small_linear": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_timestep_sincos": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_conv3x3_direct": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_nchw_to_tokens": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_tokens_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

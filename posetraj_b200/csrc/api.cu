@@ -97,5 +97,14 @@ extern "C" int pt_sizeof(const char* name) {
   if (!strcmp(name, "PtTensorMap")) return (int)sizeof(PtTensorMap);
   if (!strcmp(name, "PtCfgEulerArgs")) return (int)sizeof(PtCfgEulerArgs);
   if (!strcmp(name, "PtGemmArgs")) return (int)sizeof(PtGemmArgs);
+  if (!strcmp(name, "PtGroupNormArgs")) return (int)sizeof(PtGroupNormArgs);
+  if (!strcmp(name, "PtLayerNormArgs")) return (int)sizeof(PtLayerNormArgs);
+  if (!strcmp(name, "PtAttnSpatialArgs")) return (int)sizeof(PtAttnSpatialArgs);
+  if (!strcmp(name, "PtAttnTemporalArgs")) return (int)sizeof(PtAttnTemporalArgs);
+  if (!strcmp(name, "PtSmallLinearArgs")) return (int)sizeof(PtSmallLinearArgs);
+  if (!strcmp(name, "PtSinCosArgs")) return (int)sizeof(PtSinCosArgs);
+  if (!strcmp(name, "PtUpsampleArgs")) return (int)sizeof(PtUpsampleArgs);
+  if (!strcmp(name, "PtConvDirectArgs")) return (int)sizeof(PtConvDirectArgs);
+  if (!strcmp(name, "PtLayoutArgs")) return (int)sizeof(PtLayoutArgs);
   return -1;
 }

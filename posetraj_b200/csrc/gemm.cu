@@ -50,7 +50,7 @@ struct GemmParams {
   void* out2;
   const bf16* aux;
   float aux_scale;
-  int map_mode, pW1, pH1, ostride, oW, oH;
+  int map_mode, pW1, pH1, ostride, oW, oH, out_halo, act_silu;
 };
 
 struct alignas(64) TmapParam {
@@ -143,6 +143,10 @@ PT_DEVICE void finish_chunk(const GemmParams& p, float* f, const ChunkOperands& 
     float* v = f + g8 * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (v[j] + o.rv[g8 * 8 + j]) * p.acc_scale;
+    if (p.act_silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    }
     if (p.res1 != nullptr) fma8(v, o.r1[g8], p.res1_scale);
     if (p.res2 != nullptr) fma8(v, o.r2[g8], p.res2_scale);
     store8(p.out_dtype, p.out, (size_t)orow * p.out_ld + nn, v, nvalid);
@@ -296,8 +300,11 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         const int y = rem / p.pW1;
         const int x = rem - y * p.pW1;
         valid = valid && (y < p.pH1 - 1) && (x < p.pW1 - 1) && (y % p.ostride == 0) && (x % p.ostride == 0);
-        orow = ((long long)(batch * (p.rows_per_batch / per_img) + img) * p.oH + y / p.ostride) * p.oW +
-               x / p.ostride;
+        const long long oimg = (long long)batch * (p.rows_per_batch / per_img) + img;
+        if (p.out_halo)
+          orow = (oimg * (p.oH + 1) + y / p.ostride) * (p.oW + 1) + x / p.ostride;
+        else
+          orow = (oimg * p.oH + y / p.ostride) * p.oW + x / p.ostride;
       }
       int grp = 0;
       if (p.rowvec_mode == 1) {
@@ -462,6 +469,8 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.ostride = a->ostride > 0 ? a->ostride : 1;
   p.oW = a->oW;
   p.oH = a->oH;
+  p.out_halo = a->out_halo;
+  p.act_silu = a->act_silu;
 
   const size_t smem_bytes = (size_t)kSmemCtl + (size_t)p.stages * p.stage_bytes + 1024;
   static bool attr_set = false;

@@ -1,0 +1,376 @@
+// posetraj_b200 — small latency-bound / layout kernels around the GEMM core.
+//
+//   pt_small_linear      tiny-M linear layers (time / aug / frame-position embeddings, the batched time_emb_proj of
+//                        all resnets, the degenerate 1-token cross-attention vectors, the camera columns of
+//                        cc_projection): weight-bandwidth bound GEMV, one warp per output feature.
+//   pt_timestep_sincos   Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0), optionally
+//                        reading t = 0.25*ln(sigma[step]) from the device sigma table so a captured step replays.
+//   pt_upsample2x        nearest 2x (Upsample2D) written straight into the zero-haloed conv input layout.
+//   pt_conv3x3_direct    3x3 conv (+SiLU) for the <= 32-channel head of the ControlNet conditioning embedding
+//                        (models/controlnet_sdv.py:84-109): bandwidth-bound, kept off the tensor cores.
+//   pt_nchw_to_tokens / pt_tokens_to_nchw   boundary layout conversion (reference tensors are NCHW).
+#include "common.cuh"
+#include "launch.h"
+#include "../../include/posetraj_b200.h"
+
+namespace pt {
+
+// ---------------------------------------------------------------------------------------------------------
+struct SmallLinearParams {
+  const float* in;   // [M, K] fp32
+  int in_ld;
+  const bf16* w;     // [N, K] bf16 (row stride w_ld)
+  int w_ld;
+  const float* bias; // [N] or null
+  float* out;        // [M, N] fp32 (row stride out_ld)
+  int out_ld;
+  int M, N, K;
+  int act_in_silu, act_out_silu, accumulate;
+};
+
+__global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearParams p) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= p.N) return;
+  const bf16* wr = p.w + (size_t)n * p.w_ld;
+  for (int m0 = 0; m0 < p.M; m0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if ((p.K & 7) == 0 && (p.w_ld & 7) == 0) {
+      for (int k = lane * 8; k < p.K; k += 256) {
+        const uint4 u = ldg_u4(wr + k);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        const float wv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (m0 + i < p.M) {
+            const float* xr = p.in + (size_t)(m0 + i) * p.in_ld + k;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = xr[j];
+              if (p.act_in_silu) x = silu_f(x);
+              acc[i] = fmaf(x, wv[j], acc[i]);
+            }
+          }
+        }
+      }
+    } else {
+      for (int k = lane; k < p.K; k += 32) {
+        const float wv = __bfloat162float(wr[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (m0 + i < p.M) {
+            float x = p.in[(size_t)(m0 + i) * p.in_ld + k];
+            if (p.act_in_silu) x = silu_f(x);
+            acc[i] = fmaf(x, wv, acc[i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (m0 + i < p.M) {
+          float v = acc[i] + (p.bias != nullptr ? p.bias[n] : 0.f);
+          if (p.act_out_silu) v = silu_f(v);
+          float* o = p.out + (size_t)(m0 + i) * p.out_ld + n;
+          *o = p.accumulate ? (*o + v) : v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct SinCosParams {
+  const float* t;       // [M] or null
+  const float* sigmas;  // used when t is null: t = 0.25 * ln(sigmas[*step_index]) for every row
+  const int* step_index;
+  float* out;           // [M, dim]
+  int out_ld;
+  int M, dim;
+};
+
+__global__ void sincos_kernel(const SinCosParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = p.dim >> 1;
+  if (idx >= p.M * half) return;
+  const int m = idx / half;
+  const int k = idx - m * half;
+  float t;
+  if (p.t != nullptr) {
+    t = p.t[m];
+  } else {
+    t = 0.25f * logf(p.sigmas[*p.step_index]);
+  }
+  const float freq = expf(-logf(10000.0f) * (float)k / (float)half);
+  const float arg = t * freq;
+  p.out[(size_t)m * p.out_ld + k] = cosf(arg);         // flip_sin_to_cos: cos first
+  p.out[(size_t)m * p.out_ld + half + k] = sinf(arg);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct UpsampleParams {
+  const bf16* x;  // compact [n, H, W, C]
+  int ld;
+  bf16* out;      // haloed [n, 2H+1, 2W+1, C] (or compact [n, 2H, 2W, C])
+  int out_ld;
+  int n, H, W, C, halo;
+};
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p) {
+  const int cvec = p.C >> 3;
+  const int oW = 2 * p.W + (p.halo ? 1 : 0), oH = 2 * p.H + (p.halo ? 1 : 0);
+  const long long total = (long long)p.n * oH * oW * cvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvec);
+    const long long orow = idx / cvec;
+    const int ox = (int)(orow % oW);
+    const long long t2 = orow / oW;
+    const int oy = (int)(t2 % oH);
+    const int img = (int)(t2 / oH);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (oy < 2 * p.H && ox < 2 * p.W) {
+      const size_t irow = ((size_t)img * p.H + (oy >> 1)) * p.W + (ox >> 1);
+      v = ldg_u4(p.x + irow * p.ld + cv * 8);
+    }
+    stg_u4(p.out + (size_t)orow * p.out_ld + cv * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct ConvDirectParams {
+  const void* x;     // NCHW fp32 [n, Cin, H, W] (in_nchw_f32) or NHWC bf16 compact [n, H, W, ld]
+  int in_nchw_f32, in_ld;
+  const float* w;    // [3][3][Cin][Cout] fp32
+  const float* bias; // [Cout]
+  bf16* out;         // NHWC bf16, compact or haloed, row stride out_ld
+  int out_ld, out_halo;
+  int n, H, W, Cin, Cout, stride, silu;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(128) conv3x3_direct_kernel(const ConvDirectParams p) {
+  extern __shared__ float s_w[];  // 9*Cin*COUT + COUT
+  const int wcount = 9 * p.Cin * COUT;
+  for (int i = threadIdx.x; i < wcount; i += blockDim.x) s_w[i] = p.w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_w[wcount + i] = p.bias[i];
+  __syncthreads();
+  const int oH = (p.H + p.stride - 1) / p.stride, oW = (p.W + p.stride - 1) / p.stride;
+  const long long total = (long long)p.n * oH * oW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % oW);
+    const long long t2 = idx / oW;
+    const int oy = (int)(t2 % oH);
+    const int img = (int)(t2 / oH);
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = s_w[wcount + co];
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * p.stride + ky - 1;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * p.stride + kx - 1;
+        if (ix < 0 || ix >= p.W) continue;
+        const float* wt = s_w + (size_t)(ky * 3 + kx) * p.Cin * COUT;
+        for (int ci = 0; ci < p.Cin; ++ci) {
+          float xv;
+          if (p.in_nchw_f32) {
+            xv = reinterpret_cast<const float*>(p.x)[(((size_t)img * p.Cin + ci) * p.H + iy) * p.W + ix];
+          } else {
+            xv = __bfloat162float(reinterpret_cast<const bf16*>(p.x)[(((size_t)img * p.H + iy) * p.W + ix) * p.in_ld + ci]);
+          }
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, wt[ci * COUT + co], acc[co]);
+        }
+      }
+    }
+    size_t orow;
+    if (p.out_halo)
+      orow = ((size_t)img * (oH + 1) + oy) * (oW + 1) + ox;
+    else
+      orow = ((size_t)img * oH + oy) * oW + ox;
+    bf16* o = p.out + orow * p.out_ld;
+#pragma unroll
+    for (int co = 0; co < COUT; co += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = p.silu ? silu_f(acc[co + j]) : acc[co + j];
+      uint4 u;
+      u.x = pack_bf16x2(v[0], v[1]);
+      u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]);
+      u.w = pack_bf16x2(v[6], v[7]);
+      stg_u4(o + co, u);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct LayoutParams {
+  const void* src;
+  void* dst;
+  int n, C, H, W;
+  int ld;        // token row stride (elements)
+  int halo;      // token side uses the zero-haloed layout
+  int f32;       // NCHW side is fp32 (else bf16)
+};
+
+// 32 pixels x 32 channels transposed through smem; block (32, 8)
+__global__ void nchw_to_tokens_kernel(const LayoutParams p) {
+  __shared__ float tile[32][33];
+  const int HW = p.H * p.W;
+  const int img = blockIdx.z;
+  const int pix0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, pix = pix0 + threadIdx.x;
+    float v = 0.f;
+    if (c < p.C && pix < HW) {
+      const size_t si = ((size_t)img * p.C + c) * HW + pix;
+      v = p.f32 ? reinterpret_cast<const float*>(p.src)[si] : __bfloat162float(reinterpret_cast<const bf16*>(p.src)[si]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int pix = pix0 + i, c = c0 + threadIdx.x;
+    if (c < p.C && pix < HW) {
+      size_t row;
+      if (p.halo) {
+        const int y = pix / p.W, x = pix - y * p.W;
+        row = ((size_t)img * (p.H + 1) + y) * (p.W + 1) + x;
+      } else {
+        row = (size_t)img * HW + pix;
+      }
+      reinterpret_cast<bf16*>(p.dst)[row * p.ld + c] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+__global__ void tokens_to_nchw_kernel(const LayoutParams p) {
+  __shared__ float tile[32][33];
+  const int HW = p.H * p.W;
+  const int img = blockIdx.z;
+  const int pix0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int pix = pix0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (c < p.C && pix < HW) {
+      size_t row;
+      if (p.halo) {
+        const int y = pix / p.W, x = pix - y * p.W;
+        row = ((size_t)img * (p.H + 1) + y) * (p.W + 1) + x;
+      } else {
+        row = (size_t)img * HW + pix;
+      }
+      v = __bfloat162float(reinterpret_cast<const bf16*>(p.src)[row * p.ld + c]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, pix = pix0 + threadIdx.x;
+    if (c < p.C && pix < HW) {
+      const size_t di = ((size_t)img * p.C + c) * HW + pix;
+      const float v = tile[threadIdx.x][i];
+      if (p.f32)
+        reinterpret_cast<float*>(p.dst)[di] = v;
+      else
+        reinterpret_cast<bf16*>(p.dst)[di] = __float2bfloat16(v);
+    }
+  }
+}
+
+}  // namespace pt
+
+using namespace pt;
+
+extern "C" int pt_small_linear(const PtSmallLinearArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->in && a->w && a->out, "pt_small_linear: null argument");
+  PT_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "pt_small_linear: empty problem");
+  SmallLinearParams p;
+  p.in = a->in; p.in_ld = a->in_ld;
+  p.w = reinterpret_cast<const bf16*>(a->w); p.w_ld = a->w_ld;
+  p.bias = a->bias;
+  p.out = a->out; p.out_ld = a->out_ld;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.act_in_silu = a->act_in_silu; p.act_out_silu = a->act_out_silu; p.accumulate = a->accumulate;
+  const int blocks = (a->N + 7) / 8;
+  small_linear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return pt_launched("pt_small_linear");
+}
+
+extern "C" int pt_timestep_sincos(const PtSinCosArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->out != nullptr, "pt_timestep_sincos: null argument");
+  PT_CHECK_ARG(a->t != nullptr || (a->sigmas != nullptr && a->step_index != nullptr), "pt_timestep_sincos: need t or (sigmas, step_index)");
+  PT_CHECK_ARG(a->M > 0 && a->dim > 0 && a->dim % 2 == 0, "pt_timestep_sincos: dim must be even");
+  SinCosParams p;
+  p.t = a->t; p.sigmas = a->sigmas; p.step_index = a->step_index;
+  p.out = a->out; p.out_ld = a->out_ld; p.M = a->M; p.dim = a->dim;
+  const int total = a->M * (a->dim / 2);
+  sincos_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  return pt_launched("pt_timestep_sincos");
+}
+
+extern "C" int pt_upsample2x(const PtUpsampleArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->x && a->out, "pt_upsample2x: null argument");
+  PT_CHECK_ARG(a->n > 0 && a->H > 0 && a->W > 0 && a->C > 0 && a->C % 8 == 0, "pt_upsample2x: C must be a multiple of 8");
+  UpsampleParams p;
+  p.x = reinterpret_cast<const bf16*>(a->x); p.ld = a->ld;
+  p.out = reinterpret_cast<bf16*>(a->out); p.out_ld = a->out_ld;
+  p.n = a->n; p.H = a->H; p.W = a->W; p.C = a->C; p.halo = a->halo;
+  const long long total = (long long)a->n * (2 * a->H + 1) * (2 * a->W + 1) * (a->C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)pt_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  upsample2x_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return pt_launched("pt_upsample2x");
+}
+
+extern "C" int pt_conv3x3_direct(const PtConvDirectArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->x && a->w && a->bias && a->out, "pt_conv3x3_direct: null argument");
+  PT_CHECK_ARG(a->Cout == 16 || a->Cout == 32, "pt_conv3x3_direct: Cout must be 16 or 32");
+  PT_CHECK_ARG(a->Cin >= 1 && a->Cin <= 32 && (a->stride == 1 || a->stride == 2), "pt_conv3x3_direct: Cin <= 32, stride 1|2");
+  PT_CHECK_ARG(a->n > 0 && a->H > 0 && a->W > 0, "pt_conv3x3_direct: empty problem");
+  ConvDirectParams p;
+  p.x = a->x; p.in_nchw_f32 = a->in_nchw_f32; p.in_ld = a->in_ld;
+  p.w = a->w; p.bias = a->bias;
+  p.out = reinterpret_cast<bf16*>(a->out); p.out_ld = a->out_ld; p.out_halo = a->out_halo;
+  p.n = a->n; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout; p.stride = a->stride; p.silu = a->silu;
+  const int oH = (a->H + a->stride - 1) / a->stride, oW = (a->W + a->stride - 1) / a->stride;
+  const long long total = (long long)a->n * oH * oW;
+  long long blocks = (total + 127) / 128;
+  const long long cap = (long long)pt_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = sizeof(float) * (9 * (size_t)a->Cin * a->Cout + a->Cout);
+  if (a->Cout == 16)
+    conv3x3_direct_kernel<16><<<(int)blocks, 128, smem, (cudaStream_t)stream>>>(p);
+  else
+    conv3x3_direct_kernel<32><<<(int)blocks, 128, smem, (cudaStream_t)stream>>>(p);
+  return pt_launched("pt_conv3x3_direct");
+}
+
+static int layout_common(const PtLayoutArgs* a, void* stream, bool to_tokens) {
+  PT_CHECK_ARG(a != nullptr && a->nchw && a->tokens, "pt layout: null argument");
+  PT_CHECK_ARG(a->n > 0 && a->C > 0 && a->H > 0 && a->W > 0 && a->ld >= a->C, "pt layout: bad shape");
+  PT_CHECK_ARG(a->n <= 65535 && (a->C + 31) / 32 <= 65535, "pt layout: too many images/channels");
+  LayoutParams p;
+  p.src = to_tokens ? a->nchw : a->tokens;
+  p.dst = to_tokens ? a->tokens : a->nchw;
+  p.n = a->n; p.C = a->C; p.H = a->H; p.W = a->W; p.ld = a->ld; p.halo = a->halo; p.f32 = a->nchw_f32;
+  dim3 grid((a->H * a->W + 31) / 32, (a->C + 31) / 32, a->n);
+  dim3 block(32, 8);
+  if (to_tokens)
+    nchw_to_tokens_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p);
+  else
+    tokens_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p);
+  return pt_launched(to_tokens ? "pt_nchw_to_tokens" : "pt_tokens_to_nchw");
+}
+
+extern "C" int pt_nchw_to_tokens(const PtLayoutArgs* a, void* stream) { return layout_common(a, stream, true); }
+extern "C" int pt_tokens_to_nchw(const PtLayoutArgs* a, void* stream) { return layout_common(a, stream, false); }

@@ -1,0 +1,359 @@
+// posetraj_b200 — GroupNorm(32)(+SiLU) and LayerNorm on token-major (NHWC) bf16 activations.
+//
+// HBM-bound glue of SURVEY.md §8a/§2.2: 152 GroupNorm and 161 LayerNorm calls per denoise step.
+//   * GroupNorm statistics are per (image, group) for the spatial blocks (ResnetBlock2D, transformer `norm`,
+//     conv_norm_out) and per (batch, group) across all F frames for TemporalResnetBlock (5-D input) — the same
+//     kernels with a different "rows per statistics group".
+//   * The apply kernel can read a channel concat of two tensors (up-block `cat([h, skip], 1)` is never
+//     materialised) and can write the zero-haloed image layout the implicit-GEMM 3x3 conv consumes.
+//   * LayerNorm optionally adds the per-frame position embedding first and also emits that sum
+//     (`hidden_states_mix = hidden_states + emb`, models/modified_svd.py:196-197).
+// Algorithmic bytes: GN stats pass reads numel*2 B, apply pass reads numel*2 B and writes numel*2 B (the second
+// read normally hits the 126 MB L2); LayerNorm reads and writes numel*2 B.
+#include "common.cuh"
+#include "launch.h"
+#include "../../include/posetraj_b200.h"
+
+namespace pt {
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm statistics: sum / sum of squares per (stat group s, norm group g) accumulated in fp64 atomics
+// ---------------------------------------------------------------------------------------------------------
+struct GnStatsParams {
+  const bf16* x0;
+  const bf16* x1;
+  int c0, c1, ld0, ld1;
+  int rows_per_stat;  // rows sharing statistics (H*W, or F*H*W for the temporal 5-D norm)
+  int num_stat;       // number of statistics groups (B*F or B)
+  int splits;         // CTAs per statistics group
+  double* stats;      // [num_stat, 32, 2], zeroed by the launcher
+};
+
+__global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
+  __shared__ float s_sum[32], s_sq[32];
+  const int C = p.c0 + p.c1;
+  const int cvec = C >> 3;            // threads along channels (8 channels each)
+  const int rpar = blockDim.x / cvec; // row lanes
+  const int tc = threadIdx.x % cvec;
+  const int tr = threadIdx.x / cvec;
+  const int stat = blockIdx.x / p.splits;
+  const int split = blockIdx.x - stat * p.splits;
+  if (threadIdx.x < 32) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int c = tc * 8;
+  const bf16* src;
+  int ld;
+  if (c < p.c0) {
+    src = p.x0 + c;
+    ld = p.ld0;
+  } else {
+    src = p.x1 + (c - p.c0);
+    ld = p.ld1;
+  }
+  const int rows_per_split = (p.rows_per_stat + p.splits - 1) / p.splits;
+  const int r_begin = split * rows_per_split;
+  const int r_end = min(p.rows_per_stat, r_begin + rows_per_split);
+  float sum[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  if (tr < rpar) {
+    const size_t base = (size_t)stat * p.rows_per_stat;
+    for (int r = r_begin + tr; r < r_end; r += rpar) {
+      const uint4 u = ldg_nc_u4(src + (base + r) * ld);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sum[j] += v[j];
+        sq[j] = fmaf(v[j], v[j], sq[j]);
+      }
+    }
+    const int cg = C >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cg;
+      atomicAdd(&s_sum[g], sum[j]);
+      atomicAdd(&s_sq[g], sq[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    atomicAdd(&p.stats[((size_t)stat * 32 + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
+    atomicAdd(&p.stats[((size_t)stat * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm apply (+SiLU), optional concat input, optional zero-haloed output
+// ---------------------------------------------------------------------------------------------------------
+struct GnApplyParams {
+  const bf16* x0;
+  const bf16* x1;
+  int c0, c1, ld0, ld1;
+  int rows_per_stat, num_stat, splits;
+  const double* stats;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int silu;
+  bf16* out;
+  int out_ld;
+  int halo;  // 1: out rows are the zero-haloed image space; an image is H x W with H*W dividing rows_per_stat
+  int H, W;
+};
+
+__global__ void __launch_bounds__(512) gn_apply_kernel(const GnApplyParams p) {
+  extern __shared__ float s_ab[];  // [C] scale, [C] shift
+  const int C = p.c0 + p.c1;
+  float* s_scale = s_ab;
+  float* s_shift = s_ab + C;
+  const int stat = blockIdx.x / p.splits;
+  const int split = blockIdx.x - stat * p.splits;
+  const int cg = C >> 5;
+  const double cnt = (double)p.rows_per_stat * cg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cg;
+    const double m = p.stats[((size_t)stat * 32 + g) * 2] / cnt;
+    double var = p.stats[((size_t)stat * 32 + g) * 2 + 1] / cnt - m * m;
+    if (var < 0) var = 0;
+    const float rstd = rsqrtf((float)var + p.eps);
+    const float ga = p.gamma[c] * rstd;
+    s_scale[c] = ga;
+    s_shift[c] = p.beta[c] - (float)m * ga;
+  }
+  __syncthreads();
+
+  const int cvec = C >> 3;
+  const int rpar = blockDim.x / cvec;
+  const int tc = threadIdx.x % cvec;
+  const int tr = threadIdx.x / cvec;
+  if (tr >= rpar) return;
+  const int c = tc * 8;
+  const bf16* src;
+  int ld;
+  if (c < p.c0) {
+    src = p.x0 + c;
+    ld = p.ld0;
+  } else {
+    src = p.x1 + (c - p.c0);
+    ld = p.ld1;
+  }
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s_scale[c + j];
+    sh[j] = s_shift[c + j];
+  }
+  // iterate over OUTPUT rows of this statistics group (haloed space if requested)
+  const int HW = p.H * p.W;
+  const int imgs_per_stat = p.halo ? p.rows_per_stat / HW : 1;
+  const int P = (p.H + 1) * (p.W + 1);
+  const int out_rows = p.halo ? imgs_per_stat * P : p.rows_per_stat;
+  const int rows_per_split = (out_rows + p.splits - 1) / p.splits;
+  const int r_begin = split * rows_per_split;
+  const int r_end = min(out_rows, r_begin + rows_per_split);
+  const size_t in_base = (size_t)stat * p.rows_per_stat;
+  const size_t out_base = (size_t)stat * out_rows;
+  for (int r = r_begin + tr; r < r_end; r += rpar) {
+    long long in_row = r;
+    bool pad = false;
+    if (p.halo) {
+      const int img = r / P;
+      const int rem = r - img * P;
+      const int y = rem / (p.W + 1);
+      const int x = rem - y * (p.W + 1);
+      pad = (y == p.H) || (x == p.W);
+      in_row = (long long)img * HW + y * p.W + x;
+    }
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (!pad) {
+      const uint4 u = ldg_nc_u4(src + (in_base + in_row) * ld);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (p.silu) v[j] = silu_f(v[j]);
+      }
+      o.x = pack_bf16x2(v[0], v[1]);
+      o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]);
+      o.w = pack_bf16x2(v[6], v[7]);
+    }
+    stg_u4(p.out + (out_base + r) * p.out_ld + c, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row kept in registers (C <= 2048)
+// ---------------------------------------------------------------------------------------------------------
+struct LnParams {
+  const bf16* x;
+  int ld;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  bf16* out;
+  int out_ld;
+  int rows, C;
+  const float* addvec;  // optional [F, C] fp32 added before normalising: frame = (row / hw) % F
+  int hw, F;
+  bf16* sum_out;        // optional: x + addvec (bf16), same ld as out
+};
+
+constexpr int kLnMaxVec = 8;  // 8 vectors x 8 channels x 32 lanes = 2048 channels
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.rows) return;
+  const int nvec = p.C >> 3;
+  const bf16* src = p.x + (size_t)warp * p.ld;
+  const float* av = nullptr;
+  if (p.addvec != nullptr) av = p.addvec + (size_t)((warp / p.hw) % p.F) * p.C;
+  float v[kLnMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 u = ldg_nc_u4(src + vi * 8);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
+      v[i][4] = c.x; v[i][5] = c.y; v[i][6] = d.x; v[i][7] = d.y;
+      if (av != nullptr) {
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
+        const float4 e1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8) + 1);
+        v[i][0] += e0.x; v[i][1] += e0.y; v[i][2] += e0.z; v[i][3] += e0.w;
+        v[i][4] += e1.x; v[i][5] += e1.y; v[i][6] += e1.z; v[i][7] += e1.w;
+        if (p.sum_out != nullptr) {
+          uint4 o;
+          o.x = pack_bf16x2(v[i][0], v[i][1]);
+          o.y = pack_bf16x2(v[i][2], v[i][3]);
+          o.z = pack_bf16x2(v[i][4], v[i][5]);
+          o.w = pack_bf16x2(v[i][6], v[i][7]);
+          stg_u4(p.sum_out + (size_t)warp * p.out_ld + vi * 8, o);
+          // normalise exactly what the consumer of sum_out will see (bf16-rounded), like the reference does
+          const float2 ra = unpack_bf16x2(o.x), rb = unpack_bf16x2(o.y), rc = unpack_bf16x2(o.z), rd = unpack_bf16x2(o.w);
+          v[i][0] = ra.x; v[i][1] = ra.y; v[i][2] = rb.x; v[i][3] = rb.y;
+          v[i][4] = rc.x; v[i][5] = rc.y; v[i][6] = rd.x; v[i][7] = rd.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)p.C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)p.C + p.eps);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gg[j], bb[j]);
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]);
+      u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]);
+      u.w = pack_bf16x2(o[6], o[7]);
+      stg_u4(p.out + (size_t)warp * p.out_ld + vi * 8, u);
+    }
+  }
+}
+
+}  // namespace pt
+
+using namespace pt;
+
+static int gn_block_threads(int C) {
+  const int cvec = C / 8;
+  int rpar = 256 / cvec;
+  if (rpar < 1) rpar = 1;
+  return cvec * rpar;
+}
+
+extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->x0 != nullptr && a->out != nullptr && a->stats != nullptr && a->gamma && a->beta,
+               "pt_groupnorm: null argument");
+  const int C = a->c0 + a->c1;
+  PT_CHECK_ARG(a->c0 > 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0 && C % 32 == 0 && C / 8 <= 512,
+               "pt_groupnorm: channels must be multiples of 8 (sources) and 32 (total), <= 4096");
+  PT_CHECK_ARG(a->c1 == 0 || a->x1 != nullptr, "pt_groupnorm: c1 > 0 without x1");
+  PT_CHECK_ARG(a->rows_per_stat > 0 && a->num_stat > 0, "pt_groupnorm: empty problem");
+  PT_CHECK_ARG(!a->halo || (a->H > 0 && a->W > 0 && a->rows_per_stat % (a->H * a->W) == 0),
+               "pt_groupnorm: halo output needs H*W dividing rows_per_stat");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(a->stats, 0, sizeof(double) * 64 * (size_t)a->num_stat, st);
+  if (e != cudaSuccess) return pt_fail(e, "pt_groupnorm: memset");
+  const int threads = gn_block_threads(C);
+  int splits = (pt_num_sms() * 4 + a->num_stat - 1) / a->num_stat;
+  const int rpar = threads / (C / 8);
+  const int max_splits = (a->rows_per_stat + rpar * 4 - 1) / (rpar * 4);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+
+  GnStatsParams s;
+  s.x0 = reinterpret_cast<const bf16*>(a->x0);
+  s.x1 = reinterpret_cast<const bf16*>(a->x1);
+  s.c0 = a->c0; s.c1 = a->c1; s.ld0 = a->ld0; s.ld1 = a->ld1;
+  s.rows_per_stat = a->rows_per_stat;
+  s.num_stat = a->num_stat;
+  s.splits = splits;
+  s.stats = reinterpret_cast<double*>(a->stats);
+  gn_stats_kernel<<<a->num_stat * splits, threads, 0, st>>>(s);
+  int rc = pt_launched("pt_groupnorm(stats)");
+  if (rc) return rc;
+
+  GnApplyParams p;
+  p.x0 = s.x0; p.x1 = s.x1; p.c0 = a->c0; p.c1 = a->c1; p.ld0 = a->ld0; p.ld1 = a->ld1;
+  p.rows_per_stat = a->rows_per_stat; p.num_stat = a->num_stat; p.splits = splits;
+  p.stats = s.stats;
+  p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
+  p.out = reinterpret_cast<bf16*>(a->out);
+  p.out_ld = a->out_ld;
+  p.halo = a->halo; p.H = a->H > 0 ? a->H : 1; p.W = a->W > 0 ? a->W : 1;
+  gn_apply_kernel<<<a->num_stat * splits, threads, sizeof(float) * 2 * C, st>>>(p);
+  return pt_launched("pt_groupnorm(apply)");
+}
+
+extern "C" int pt_layernorm(const PtLayerNormArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->x && a->out && a->gamma && a->beta, "pt_layernorm: null argument");
+  PT_CHECK_ARG(a->C % 8 == 0 && a->C >= 8 && a->C <= kLnMaxVec * 256, "pt_layernorm: C must be a multiple of 8, <= 2048");
+  PT_CHECK_ARG(a->rows > 0, "pt_layernorm: empty problem");
+  PT_CHECK_ARG(a->addvec == nullptr || (a->hw > 0 && a->F > 0), "pt_layernorm: addvec needs hw and F");
+  LnParams p;
+  p.x = reinterpret_cast<const bf16*>(a->x);
+  p.ld = a->ld;
+  p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps;
+  p.out = reinterpret_cast<bf16*>(a->out);
+  p.out_ld = a->out_ld;
+  p.rows = a->rows; p.C = a->C;
+  p.addvec = a->addvec; p.hw = a->hw > 0 ? a->hw : 1; p.F = a->F > 0 ? a->F : 1;
+  p.sum_out = reinterpret_cast<bf16*>(a->sum_out);
+  const int warps_per_block = 8;
+  const int blocks = (a->rows + warps_per_block - 1) / warps_per_block;
+  layernorm_kernel<<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(p);
+  return pt_launched("pt_layernorm");
+}

@@ -61,7 +61,8 @@ class Gemm:
                  res1: Optional[torch.Tensor] = None, res1_scale: float = 1.0,
                  res2: Optional[torch.Tensor] = None, res2_scale: float = 1.0,
                  out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_scale: float = 0.0,
-                 halo: Optional[tuple] = None, ostride: int = 1, name: str = "gemm"):
+                 halo: Optional[tuple] = None, ostride: int = 1, out_halo: bool = False,
+                 act_silu: bool = False, name: str = "gemm"):
         assert a0.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
         assert a0.dim() == 2 and w.dim() == 2 and a0.stride(1) == 1 and w.stride(1) == 1
         self.name = name
@@ -153,10 +154,15 @@ class Gemm:
             a.oW = (w_ + ostride - 1) // ostride
             n_img = rows_total // ((h + 1) * (w_ + 1))
             assert n_img * (h + 1) * (w_ + 1) == rows_total
-            assert out_rows == n_img * a.oH * a.oW, (out_rows, n_img, a.oH, a.oW)
+            a.out_halo = 1 if out_halo else 0
+            if out_halo:
+                assert out_rows == n_img * (a.oH + 1) * (a.oW + 1), (out_rows, n_img, a.oH, a.oW)
+            else:
+                assert out_rows == n_img * a.oH * a.oW, (out_rows, n_img, a.oH, a.oW)
         else:
             a.map_mode = 0
             assert out_rows == rows_total
+        a.act_silu = 1 if act_silu else 0
         self.args = a
         self._keep = (a0, a1, w, out, bias, rowvec, res1, res2, out2, aux)
         self._argp = C.addressof(a)
@@ -205,3 +211,184 @@ class CfgEuler:
 
     def launch(self, stream_ptr: int) -> None:
         _lib.check(_lib.lib().pt_cfg_euler_step(self._argp, stream_ptr), "pt_cfg_euler_step")
+
+
+class _Op:
+    """Base: holds a ctypes args struct + the C entry point; launch() is one ctypes call."""
+    fn_name = ""
+
+    def _finish(self, args, keep, name=None):
+        self.args = args
+        self._keep = keep
+        self._argp = C.addressof(args)
+        self._fn = getattr(_lib.lib(), self.fn_name)
+        self.name = name or self.fn_name
+
+    def launch(self, stream_ptr: int) -> None:
+        _lib.check(self._fn(self._argp, stream_ptr), self.name)
+
+
+class GroupNorm(_Op):
+    fn_name = "pt_groupnorm"
+
+    def __init__(self, x0, out, gamma, beta, stats, *, rows_per_stat, eps, silu=True, x1=None,
+                 halo: Optional[tuple] = None, name=None):
+        a = _lib.PtGroupNormArgs()
+        assert x0.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and stats.dtype == torch.float64
+        assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+        rows = x0.shape[0]
+        assert rows % rows_per_stat == 0
+        a.x0 = x0.data_ptr()
+        a.c0, a.ld0 = x0.shape[1], x0.stride(0)
+        if x1 is not None:
+            assert x1.dtype == torch.bfloat16 and x1.shape[0] == rows
+            a.x1 = x1.data_ptr()
+            a.c1, a.ld1 = x1.shape[1], x1.stride(0)
+        assert gamma.numel() == a.c0 + a.c1
+        a.rows_per_stat = rows_per_stat
+        a.num_stat = rows // rows_per_stat
+        assert stats.numel() >= a.num_stat * 64
+        a.stats = stats.data_ptr()
+        a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+        a.eps = eps
+        a.silu = 1 if silu else 0
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        if halo is not None:
+            a.halo, a.H, a.W = 1, halo[0], halo[1]
+            n_img = rows // (halo[0] * halo[1])
+            assert out.shape[0] == n_img * (halo[0] + 1) * (halo[1] + 1)
+        else:
+            assert out.shape[0] == rows
+        self._finish(a, (x0, x1, out, gamma, beta, stats), name)
+
+
+class LayerNorm(_Op):
+    fn_name = "pt_layernorm"
+
+    def __init__(self, x, out, gamma, beta, *, eps=1e-5, addvec=None, hw=1, frames=1, sum_out=None, name=None):
+        a = _lib.PtLayerNormArgs()
+        assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+        a.x, a.ld = x.data_ptr(), x.stride(0)
+        a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), eps
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        a.rows, a.C = x.shape
+        if addvec is not None:
+            assert addvec.dtype == torch.float32 and addvec.is_contiguous() and addvec.shape == (frames, x.shape[1])
+            a.addvec, a.hw, a.F = addvec.data_ptr(), hw, frames
+            if sum_out is not None:
+                assert sum_out.stride(0) == out.stride(0) and sum_out.dtype == torch.bfloat16
+                a.sum_out = sum_out.data_ptr()
+        self._finish(a, (x, out, gamma, beta, addvec, sum_out), name)
+
+
+class AttnSpatial(_Op):
+    fn_name = "pt_attention_spatial"
+
+    def __init__(self, qkv, out, *, n_img, heads, name=None):
+        rows, c3 = qkv.shape
+        Cc = c3 // 3
+        S = rows // n_img
+        assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and S * n_img == rows
+        self.tm = _lib.encode_tensormap(qkv.data_ptr(), [c3, S, n_img], [qkv.stride(0) * 2, qkv.stride(0) * 2 * S],
+                                        [64, 128, 1])
+        a = _lib.PtAttnSpatialArgs()
+        a.tmap_qkv = C.addressof(self.tm)
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        a.S, a.heads, a.C, a.n_img = S, heads, Cc, n_img
+        self._finish(a, (qkv, out), name)
+
+
+class AttnTemporal(_Op):
+    fn_name = "pt_attention_temporal"
+
+    def __init__(self, qkv, out, *, batch, frames, hw, heads, name=None):
+        a = _lib.PtAttnTemporalArgs()
+        assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+        assert qkv.shape[0] == batch * frames * hw
+        a.qkv, a.ld = qkv.data_ptr(), qkv.stride(0)
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        a.B, a.F, a.HW, a.heads, a.C = batch, frames, hw, heads, qkv.shape[1] // 3
+        self._finish(a, (qkv, out), name)
+
+
+class SmallLinear(_Op):
+    fn_name = "pt_small_linear"
+
+    def __init__(self, x, w, out, bias=None, *, act_in_silu=False, act_out_silu=False, accumulate=False, name=None):
+        a = _lib.PtSmallLinearArgs()
+        assert x.dtype == torch.float32 and out.dtype == torch.float32 and w.dtype == torch.bfloat16
+        assert x.dim() == 2 and out.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
+        a.in_, a.in_ld = x.data_ptr(), x.stride(0)
+        a.w, a.w_ld = w.data_ptr(), w.stride(0)
+        a.bias = _ptr(bias)
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        a.M, a.K = x.shape
+        a.N = w.shape[0]
+        assert w.shape[1] == a.K and out.shape == (a.M, a.N)
+        a.act_in_silu, a.act_out_silu, a.accumulate = int(act_in_silu), int(act_out_silu), int(accumulate)
+        self._finish(a, (x, w, out, bias), name)
+
+
+class SinCos(_Op):
+    fn_name = "pt_timestep_sincos"
+
+    def __init__(self, out, *, t=None, sigmas=None, step_index=None, name=None):
+        a = _lib.PtSinCosArgs()
+        assert out.dtype == torch.float32 and out.dim() == 2
+        a.t, a.sigmas, a.step_index = _ptr(t), _ptr(sigmas), _ptr(step_index)
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        a.M, a.dim = out.shape
+        if t is not None:
+            assert t.dtype == torch.float32 and t.numel() == a.M
+        self._finish(a, (out, t, sigmas, step_index), name)
+
+
+class Upsample2x(_Op):
+    fn_name = "pt_upsample2x"
+
+    def __init__(self, x, out, *, n, H, W, halo=True, name=None):
+        a = _lib.PtUpsampleArgs()
+        assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and x.shape[0] == n * H * W
+        a.x, a.ld = x.data_ptr(), x.stride(0)
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        a.n, a.H, a.W, a.C, a.halo = n, H, W, x.shape[1], int(halo)
+        exp_rows = n * (2 * H + 1) * (2 * W + 1) if halo else n * 4 * H * W
+        assert out.shape[0] == exp_rows
+        self._finish(a, (x, out), name)
+
+
+class ConvDirect(_Op):
+    fn_name = "pt_conv3x3_direct"
+
+    def __init__(self, x, w, bias, out, *, n, H, W, cin, cout, stride=1, silu=True, in_nchw_f32=False,
+                 out_halo=False, name=None):
+        a = _lib.PtConvDirectArgs()
+        assert w.dtype == torch.float32 and w.is_contiguous() and w.numel() == 9 * cin * cout
+        assert bias.dtype == torch.float32 and out.dtype == torch.bfloat16
+        a.x = x.data_ptr()
+        a.in_nchw_f32 = int(in_nchw_f32)
+        if in_nchw_f32:
+            assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == n * cin * H * W
+        else:
+            assert x.dtype == torch.bfloat16 and x.shape[0] == n * H * W
+            a.in_ld = x.stride(0)
+        a.w, a.bias = w.data_ptr(), bias.data_ptr()
+        a.out, a.out_ld, a.out_halo = out.data_ptr(), out.stride(0), int(out_halo)
+        a.n, a.H, a.W, a.Cin, a.Cout, a.stride, a.silu = n, H, W, cin, cout, stride, int(silu)
+        self._finish(a, (x, w, bias, out), name)
+
+
+class Layout(_Op):
+    """NCHW (fp32|bf16) <-> token-major bf16."""
+
+    def __init__(self, nchw, tokens, *, to_tokens: bool, halo=False, name=None):
+        self.fn_name = "pt_nchw_to_tokens" if to_tokens else "pt_tokens_to_nchw"
+        a = _lib.PtLayoutArgs()
+        assert nchw.is_contiguous() and nchw.dim() == 4 and nchw.dtype in (torch.float32, torch.bfloat16)
+        assert tokens.dtype == torch.bfloat16 and tokens.dim() == 2
+        a.nchw, a.tokens = nchw.data_ptr(), tokens.data_ptr()
+        a.n, a.C, a.H, a.W = nchw.shape
+        a.ld, a.halo, a.nchw_f32 = tokens.stride(0), int(halo), int(nchw.dtype == torch.float32)
+        rows = a.n * ((a.H + 1) * (a.W + 1) if halo else a.H * a.W)
+        assert tokens.shape[0] == rows and tokens.shape[1] >= a.C
+        self._finish(a, (nchw, tokens), name)

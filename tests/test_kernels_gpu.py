@@ -1,0 +1,193 @@
+"""Kernel-level numerics of the non-GEMM kernels against plain torch fp32 on the same (bf16-rounded) inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def sp():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rnd(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("n_img,H,W,c0,c1,frames_per_stat,halo,silu", [
+    (6, 10, 18, 320, 0, 1, True, True), (4, 5, 9, 1280, 640, 1, True, True), (6, 8, 12, 64, 0, 3, False, True),
+    (28, 20, 36, 640, 0, 1, False, False), (4, 10, 18, 1280, 1280, 1, True, True), (2, 40, 72, 320, 0, 1, True, True)])
+def test_groupnorm(cuda_dev, n_img, H, W, c0, c1, frames_per_stat, halo, silu):
+    from posetraj_b200.ops import GroupNorm
+    torch.manual_seed(0)
+    Cc = c0 + c1
+    x0 = rnd(n_img * H * W, c0) + 0.5
+    x1 = rnd(n_img * H * W, c1, scale=2.0) if c1 else None
+    gamma = torch.randn(Cc, device="cuda")
+    beta = torch.randn(Cc, device="cuda")
+    stats = torch.zeros(n_img * 64, device="cuda", dtype=torch.float64)
+    out_rows = n_img * (H + 1) * (W + 1) if halo else n_img * H * W
+    out = torch.full((out_rows, Cc), 7.0, device="cuda", dtype=torch.bfloat16)
+    GroupNorm(x0, out, gamma, beta, stats, rows_per_stat=frames_per_stat * H * W, eps=1e-6, silu=silu, x1=x1,
+              halo=(H, W) if halo else None).launch(sp())
+    torch.cuda.synchronize()
+    x = x0.float() if x1 is None else torch.cat([x0, x1], 1).float()
+    ns = n_img // frames_per_stat
+    xr = x.view(ns, frames_per_stat * H * W, Cc).permute(0, 2, 1)  # [ns, C, L]
+    ref = F.group_norm(xr, 32, gamma, beta, eps=1e-6)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(n_img, H, W, Cc)
+    if halo:
+        o = out.view(n_img, H + 1, W + 1, Cc)
+        assert o[:, H].abs().max() == 0 and o[:, :, W].abs().max() == 0
+        got = o[:, :H, :W]
+    else:
+        got = out.view(n_img, H, W, Cc)
+    assert rel_l2(got, ref) < 6e-3
+
+
+@pytest.mark.parametrize("rows,Cc", [(1000, 320), (333, 640), (77, 1280)])
+def test_layernorm(cuda_dev, rows, Cc):
+    from posetraj_b200.ops import LayerNorm
+    torch.manual_seed(1)
+    x = rnd(rows, Cc) + 0.3
+    g, b = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    out = torch.empty_like(x)
+    LayerNorm(x, out, g, b).launch(sp())
+    torch.cuda.synchronize()
+    assert rel_l2(out, F.layer_norm(x.float(), (Cc,), g, b, 1e-5)) < 5e-3
+
+
+def test_layernorm_addvec(cuda_dev):
+    from posetraj_b200.ops import LayerNorm
+    torch.manual_seed(2)
+    B, Fr, HW, Cc = 2, 3, 20, 320
+    x = rnd(B * Fr * HW, Cc)
+    emb = torch.randn(Fr, Cc, device="cuda")
+    g, b = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    out, s = torch.empty_like(x), torch.empty_like(x)
+    LayerNorm(x, out, g, b, addvec=emb, hw=HW, frames=Fr, sum_out=s).launch(sp())
+    torch.cuda.synchronize()
+    xs = (x.float().view(B, Fr, HW, Cc) + emb.view(1, Fr, 1, Cc)).reshape(-1, Cc)
+    assert rel_l2(s, xs) < 4e-3
+    assert rel_l2(out, F.layer_norm(xs.to(torch.bfloat16).float(), (Cc,), g, b, 1e-5)) < 5e-3
+
+
+@pytest.mark.parametrize("n_img,S,heads", [(3, 45, 20), (4, 180, 20), (2, 720, 10), (2, 2880, 5), (1, 128, 1), (2, 300, 2)])
+def test_attention_spatial(cuda_dev, n_img, S, heads):
+    from posetraj_b200.ops import AttnSpatial
+    torch.manual_seed(3)
+    Cc = heads * 64
+    qkv = rnd(n_img * S, 3 * Cc)
+    out = torch.zeros(n_img * S, Cc, device="cuda", dtype=torch.bfloat16)
+    AttnSpatial(qkv, out, n_img=n_img, heads=heads).launch(sp())
+    torch.cuda.synchronize()
+    q, k, v = (t.view(n_img, S, heads, 64).transpose(1, 2) for t in qkv.float().chunk(3, dim=1))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n_img * S, Cc)
+    assert rel_l2(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,Fr,HW,heads", [(2, 14, 45, 20), (2, 14, 180, 5), (1, 25, 50, 10), (2, 1, 30, 5), (2, 16, 33, 5)])
+def test_attention_temporal(cuda_dev, B, Fr, HW, heads):
+    from posetraj_b200.ops import AttnTemporal
+    torch.manual_seed(4)
+    Cc = heads * 64
+    qkv = rnd(B * Fr * HW, 3 * Cc)
+    out = torch.zeros(B * Fr * HW, Cc, device="cuda", dtype=torch.bfloat16)
+    AttnTemporal(qkv, out, batch=B, frames=Fr, hw=HW, heads=heads).launch(sp())
+    torch.cuda.synchronize()
+    t = qkv.float().view(B, Fr, HW, 3, heads, 64).permute(3, 0, 2, 4, 1, 5)  # [3, B, HW, heads, F, 64]
+    ref = F.scaled_dot_product_attention(t[0], t[1], t[2])  # [B, HW, heads, F, 64]
+    ref = ref.permute(0, 3, 1, 2, 4).reshape(B * Fr * HW, Cc)
+    assert rel_l2(out, ref) < 1e-2
+
+
+def test_small_linear_and_sincos(cuda_dev):
+    from posetraj_b200.ops import SinCos, SmallLinear
+    torch.manual_seed(5)
+    for (M, K, N) in [(2, 320, 1280), (14, 1280, 640), (28, 12, 256), (3, 768, 1280)]:
+        x = torch.randn(M, K, device="cuda")
+        w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+        b = torch.randn(N, device="cuda")
+        out = torch.zeros(M, N, device="cuda")
+        SmallLinear(x, w, out, b, act_in_silu=True, act_out_silu=True).launch(sp())
+        torch.cuda.synchronize()
+        ref = F.silu(F.silu(x) @ w.float().t() + b)
+        assert rel_l2(out, ref) < 1e-4
+        SmallLinear(x, w, out, None, accumulate=True).launch(sp())
+        torch.cuda.synchronize()
+        assert rel_l2(out, ref + x @ w.float().t()) < 1e-4
+    t = torch.tensor([1.63777, -1.553652, 0.0, 13.0], device="cuda")
+    out = torch.zeros(4, 320, device="cuda")
+    SinCos(out, t=t).launch(sp())
+    torch.cuda.synchronize()
+    half = 160
+    freq = torch.exp(-math.log(10000.0) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    arg = t[:, None] * freq[None]
+    assert rel_l2(out, torch.cat([arg.cos(), arg.sin()], 1)) < 1e-4
+    sig = torch.tensor([700.0, 10.0, 0.002, 0.0], device="cuda")
+    si = torch.tensor([1], device="cuda", dtype=torch.int32)
+    out2 = torch.zeros(2, 320, device="cuda")
+    SinCos(out2, sigmas=sig, step_index=si).launch(sp())
+    torch.cuda.synchronize()
+    arg = (0.25 * math.log(10.0)) * freq
+    assert rel_l2(out2[1], torch.cat([arg.cos(), arg.sin()])) < 1e-4
+
+
+def test_upsample_and_layout(cuda_dev):
+    from posetraj_b200.ops import Layout, Upsample2x
+    torch.manual_seed(6)
+    n, H, W, Cc = 3, 5, 9, 64
+    x = rnd(n * H * W, Cc)
+    out = torch.full((n * (2 * H + 1) * (2 * W + 1), Cc), 3.0, device="cuda", dtype=torch.bfloat16)
+    Upsample2x(x, out, n=n, H=H, W=W).launch(sp())
+    torch.cuda.synchronize()
+    o = out.view(n, 2 * H + 1, 2 * W + 1, Cc)
+    ref = F.interpolate(x.float().view(n, H, W, Cc).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(o[:, :2 * H, :2 * W].float(), ref)
+    assert o[:, 2 * H].abs().max() == 0 and o[:, :, 2 * W].abs().max() == 0
+    for dt in (torch.float32, torch.bfloat16):
+        for halo in (False, True):
+            src = torch.randn(4, 40, 7, 11, device="cuda").to(dt).contiguous()
+            rows = 4 * (8 * 12 if halo else 77)
+            tok = torch.zeros(rows, 64, device="cuda", dtype=torch.bfloat16)
+            Layout(src, tok, to_tokens=True, halo=halo).launch(sp())
+            back = torch.zeros_like(src)
+            Layout(back, tok, to_tokens=False, halo=halo).launch(sp())
+            torch.cuda.synchronize()
+            assert torch.equal(back.float(), src.to(torch.bfloat16).float())
+            if not halo:
+                assert torch.equal(tok[:, :40].float().view(4, 7, 11, 40), src.to(torch.bfloat16).float().permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("cin,cout,stride,nchw", [(3, 16, 1, True), (16, 16, 1, False), (16, 32, 2, False)])
+def test_conv_direct(cuda_dev, cin, cout, stride, nchw):
+    from posetraj_b200.ops import ConvDirect
+    torch.manual_seed(7)
+    n, H, W = 2, 32, 48
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") / math.sqrt(9 * cin)
+    bias = torch.randn(cout, device="cuda")
+    if nchw:
+        x = torch.randn(n, cin, H, W, device="cuda").contiguous()
+        xr = x
+    else:
+        xb = rnd(n * H * W, cin)
+        x = xb
+        xr = xb.float().view(n, H, W, cin).permute(0, 3, 1, 2)
+    oH, oW = H // stride, W // stride
+    out = torch.zeros(n * (oH + 1) * (oW + 1), 64, device="cuda", dtype=torch.bfloat16)
+    ConvDirect(x, wt.permute(2, 3, 1, 0).contiguous(), bias, out, n=n, H=H, W=W, cin=cin, cout=cout, stride=stride,
+               silu=True, in_nchw_f32=nchw, out_halo=True).launch(sp())
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(xr, wt, bias, stride=stride, padding=1)).permute(0, 2, 3, 1)
+    o = out.view(n, oH + 1, oW + 1, 64)
+    assert rel_l2(o[:, :oH, :oW, :cout], ref) < 4e-3
+    assert o[..., cout:].abs().max() == 0 and o[:, oH].abs().max() == 0
