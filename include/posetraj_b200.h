@@ -68,6 +68,7 @@ typedef struct PtCfgEulerArgs {
   int32_t next_ld;
   int32_t next_padded;      /* 1: rows laid out with one zero column/row per image ((H+1)*(W+1) rows/image) */
   int32_t mode;             /* 0: full step (update latents, next_in uses sigma[i+1]); 1: only build next_in for sigma[i] */
+  int32_t single_pred;      /* 1: noise_pred holds ONE already-combined prediction [F,...] (plain scheduler.step) */
 } PtCfgEulerArgs;
 int pt_cfg_euler_step(const PtCfgEulerArgs* a, void* stream);
 /* *step_index += 1 (stream-ordered, so a captured CUDA graph of one step can be replayed) */
@@ -225,13 +226,15 @@ typedef struct PtSinCosArgs {
 } PtSinCosArgs;
 int pt_timestep_sincos(const PtSinCosArgs* a, void* stream);
 
-/* nearest-neighbour 2x (diffusers Upsample2D) from compact [n,H,W,C] to [n,2H,2W,C], optionally zero-haloed */
+/* nearest-neighbour 2x (diffusers Upsample2D) from compact [n,H,W,C] to [n,2H,2W,C], optionally zero-haloed;
+ * scale == 1 is a plain copy into the zero-haloed layout (input of the stride-2 Downsample2D conv) */
 typedef struct PtUpsampleArgs {
   const void* x;
   int32_t ld;
   void* out;
   int32_t out_ld;
   int32_t n, H, W, C, halo;
+  int32_t scale;            /* 1 or 2 (0 means 2) */
 } PtUpsampleArgs;
 int pt_upsample2x(const PtUpsampleArgs* a, void* stream);
 

@@ -32,6 +32,7 @@ class PtCfgEulerArgs(C.Structure):
         ("next_ld", C.c_int32),
         ("next_padded", C.c_int32),
         ("mode", C.c_int32),
+        ("single_pred", C.c_int32),
     ]
 
 
@@ -104,7 +105,7 @@ PtSinCosArgs = _st("PtSinCosArgs", [
 
 PtUpsampleArgs = _st("PtUpsampleArgs", [
     ("x", vp), ("ld", i32), ("out", vp), ("out_ld", i32),
-    ("n", i32), ("H", i32), ("W", i32), ("C", i32), ("halo", i32)])
+    ("n", i32), ("H", i32), ("W", i32), ("C", i32), ("halo", i32), ("scale", i32)])
 
 PtConvDirectArgs = _st("PtConvDirectArgs", [
     ("x", vp), ("in_nchw_f32", i32), ("in_ld", i32), ("w", vp), ("bias", vp), ("out", vp),

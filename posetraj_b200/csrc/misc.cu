@@ -118,12 +118,13 @@ struct UpsampleParams {
   int ld;
   bf16* out;      // haloed [n, 2H+1, 2W+1, C] (or compact [n, 2H, 2W, C])
   int out_ld;
-  int n, H, W, C, halo;
+  int n, H, W, C, halo, scale;
 };
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p) {
   const int cvec = p.C >> 3;
-  const int oW = 2 * p.W + (p.halo ? 1 : 0), oH = 2 * p.H + (p.halo ? 1 : 0);
+  const int sc = p.scale;
+  const int oW = sc * p.W + (p.halo ? 1 : 0), oH = sc * p.H + (p.halo ? 1 : 0);
   const long long total = (long long)p.n * oH * oW * cvec;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p)
     const int oy = (int)(t2 % oH);
     const int img = (int)(t2 / oH);
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (oy < 2 * p.H && ox < 2 * p.W) {
-      const size_t irow = ((size_t)img * p.H + (oy >> 1)) * p.W + (ox >> 1);
+    if (oy < sc * p.H && ox < sc * p.W) {
+      const size_t irow = ((size_t)img * p.H + (oy / sc)) * p.W + (ox / sc);
       v = ldg_u4(p.x + irow * p.ld + cv * 8);
     }
     stg_u4(p.out + (size_t)orow * p.out_ld + cv * 8, v);
@@ -324,6 +325,7 @@ extern "C" int pt_upsample2x(const PtUpsampleArgs* a, void* stream) {
   p.x = reinterpret_cast<const bf16*>(a->x); p.ld = a->ld;
   p.out = reinterpret_cast<bf16*>(a->out); p.out_ld = a->out_ld;
   p.n = a->n; p.H = a->H; p.W = a->W; p.C = a->C; p.halo = a->halo;
+  p.scale = (a->scale == 1) ? 1 : 2;
   const long long total = (long long)a->n * (2 * a->H + 1) * (2 * a->W + 1) * (a->C / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)pt_num_sms() * 16;

@@ -22,7 +22,7 @@ struct CfgEulerParams {
   int F, C, H, W;
   bf16* next_in;
   const float* image_latents;
-  int next_ld, next_padded, mode;
+  int next_ld, next_padded, mode, single_pred;
 };
 
 // one thread per (f, y, x); C (= 4) channels handled in a short loop
@@ -47,11 +47,11 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const CfgEulerParams p) 
       if (p.pred_nchw_f32) {
         const float* pr = reinterpret_cast<const float*>(p.pred);
         u = pr[li];
-        cnd = pr[(size_t)p.F * p.C * HW + li];
+        cnd = p.single_pred ? u : pr[(size_t)p.F * p.C * HW + li];
       } else {
         const bf16* pr = reinterpret_cast<const bf16*>(p.pred);
         u = __bfloat162float(pr[(size_t)idx * p.pred_ld + c]);
-        cnd = __bfloat162float(pr[((size_t)total + idx) * p.pred_ld + c]);
+        cnd = p.single_pred ? u : __bfloat162float(pr[((size_t)total + idx) * p.pred_ld + c]);
       }
       // same operation order as the reference scheduler (fp32)
       const float v = u + g * (cnd - u);
@@ -115,6 +115,7 @@ extern "C" int pt_cfg_euler_step(const PtCfgEulerArgs* a, void* stream) {
   p.next_ld = a->next_ld;
   p.next_padded = a->next_padded;
   p.mode = a->mode;
+  p.single_pred = a->single_pred;
   const int total = a->F * a->H * a->W;
   cfg_euler_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
   return pt_launched("pt_cfg_euler_step");

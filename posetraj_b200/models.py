@@ -1,0 +1,286 @@
+"""Drop-in mirrors of the reference's two network classes, running on the sm_100a kernel library.
+
+  ControlNetSDVModel.forward                          /root/reference/models/controlnet_sdv.py:516-650
+      cam variant (`camera_cond`)                     /root/reference/models/controlnet_sdv_cam_infer.py:84,96-122,537
+      bbox variant (`controlnet_bbox`)                /root/reference/models/controlnet_sdv_bbox.py:109-138,551
+  UNetSpatioTemporalConditionControlNetModel.forward  /root/reference/models/unet_spatio_temporal_condition_controlnet.py:356-504
+
+Same argument names, shapes and return structure as the reference.  Tensors come in and go out in the reference's
+layouts ([B, F, C, H, W]); inside, everything is token-major bf16 and every arithmetic op is a kernel of
+libposetraj_b200.so (no eager fallback: a CPU tensor or a missing library raises).  The ControlNet returns its 13
+residuals as channels-last views of the buffers the UNet plan reads, so feeding them to the UNet is zero-copy.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import asdict, dataclass
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+
+from . import ops
+from .config import SVDConfig, controlnet_param_shapes, unet_param_shapes
+from .engine import BF16, F32, NetPlan, WeightStore
+
+
+@dataclass
+class ControlNetOutput:
+    down_block_res_samples: Tuple[torch.Tensor]
+    mid_block_res_sample: torch.Tensor
+
+
+@dataclass
+class UNetSpatioTemporalConditionOutput:
+    sample: torch.FloatTensor = None
+
+
+def random_state_dict(shapes: Dict[str, tuple], device, seed: int = 0, zero_keys: Tuple[str, ...] = ()) -> Dict[str, torch.Tensor]:
+    """Random-init weights with torch's default statistics (kaiming-uniform(a=sqrt(5)) conv/linear weights and
+    biases ~ U(+-1/sqrt(fan_in)), norm scale 1 / shift 0, mix_factor 0.5), generated directly on `device`.
+    Keys starting with an entry of `zero_keys` are zero (the reference's `zero_module`)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        if any(k.startswith(z) for z in zero_keys):
+            sd[k] = torch.zeros(shp, device=device, dtype=BF16)
+        elif k.endswith("mix_factor"):
+            sd[k] = torch.full(shp, 0.5, device=device, dtype=F32)
+        elif ".norm" in k or k.startswith("conv_norm_out") or ".norm." in k:
+            sd[k] = (torch.ones if k.endswith("weight") else torch.zeros)(shp, device=device, dtype=F32)
+        else:
+            wk = k[: -len("bias")] + "weight" if k.endswith("bias") else k
+            fan_in = int(math.prod(shapes[wk][1:])) if len(shapes[wk]) > 1 else shapes[wk][0]
+            bound = 1.0 / math.sqrt(fan_in)
+            sd[k] = ((torch.rand(shp, device=device, generator=g, dtype=F32) * 2 - 1) * bound).to(BF16 if len(shp) > 1 else F32)
+    return sd
+
+
+class _NetBase(torch.nn.Module):
+    kind = ""
+
+    def __init__(self, cfg: SVDConfig, state_dict: Dict[str, torch.Tensor], device=None, **flags):
+        super().__init__()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if device is None or torch.device(device).type != "cuda":
+            raise RuntimeError("posetraj_b200 runs on CUDA sm_100a only; there is no CPU path")
+        self.cfg = cfg
+        self.flags = flags
+        self._device = torch.device(device)
+        self._sd = dict(state_dict)
+        self._check_keys()
+        self.weights = WeightStore(self._sd, self._device)
+        self._plans: Dict[tuple, NetPlan] = {}
+        self.config = SimpleNamespace(**asdict(cfg))
+        self.add_embedding = SimpleNamespace(
+            linear_1=SimpleNamespace(in_features=cfg.projection_class_embeddings_input_dim))
+        self.dtype = BF16
+
+    # -- reference-compatible odds and ends ------------------------------------------------------
+    @property
+    def device(self):
+        return self._device
+
+    def expected_shapes(self) -> Dict[str, tuple]:
+        raise NotImplementedError
+
+    def _check_keys(self):
+        exp = self.expected_shapes()
+        missing = [k for k in exp if k not in self._sd]
+        if missing:
+            raise KeyError(f"{type(self).__name__}: state dict misses {len(missing)} keys, e.g. {missing[:3]}")
+        for k, shp in exp.items():
+            if tuple(self._sd[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: expected shape {shp}, got {tuple(self._sd[k].shape)}")
+
+    def state_dict(self, *a, **k):
+        return dict(self._sd)
+
+    def num_parameters(self) -> int:
+        return sum(int(math.prod(s)) for s in self.expected_shapes().values())
+
+    def plan_for(self, batch, frames, h, w, **kw) -> NetPlan:
+        key = (batch, frames, h, w) + tuple(sorted((k, id(v) if torch.is_tensor(v) or isinstance(v, list) else v)
+                                                   for k, v in kw.items()))
+        if key not in self._plans:
+            self._plans[key] = NetPlan(self.kind, self.cfg, self.weights, batch=batch, frames=frames, height=h, width=w,
+                                       device=self._device, **self.flags, **kw)
+        return self._plans[key]
+
+    # -- shared input staging -------------------------------------------------------------------
+    def _stage_common(self, plan: NetPlan, sample, timestep, encoder_hidden_states, added_time_ids, sp):
+        B, Fr, Cin, H, W = sample.shape
+        if sample.device.type != "cuda":
+            raise RuntimeError("posetraj_b200: inputs must be CUDA tensors (no CPU fallback)")
+        x = sample.reshape(B * Fr, Cin, H, W)
+        if x.dtype not in (F32, BF16):
+            x = x.to(F32)
+        ops.Layout(x.contiguous(), plan.x_in, to_tokens=True, halo=True).launch(sp)
+        if torch.is_tensor(timestep):
+            plan.t_buf.copy_(timestep.detach().reshape(-1).to(F32).expand(B) if timestep.numel() == 1
+                             else timestep.detach().to(F32).reshape(B))
+        else:
+            plan.t_buf.fill_(float(timestep))
+        ehs = encoder_hidden_states
+        if ehs.shape[0] != B or ehs.shape[1] != 1:
+            raise ValueError("encoder_hidden_states must be [batch, 1, cross_attention_dim] on this path")
+        key = (ehs.data_ptr(), ehs._version, added_time_ids.data_ptr(), added_time_ids._version)
+        plan.time_ids.copy_(added_time_ids.detach().to(F32).reshape(-1))
+        if getattr(plan, "_embed_key", None) != key:
+            plan.ehs.copy_(ehs.detach()[:, 0, :].to(F32))
+            NetPlan.run(plan.embed_ops, sp)
+            plan._embed_key = key
+
+    @staticmethod
+    def _as_nchw_view(tokens: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+        """[n*h*w, C] token buffer -> logical [n, C, h, w] tensor in channels-last memory (no copy)."""
+        return tokens.view(n, h, w, tokens.shape[1]).permute(0, 3, 1, 2)
+
+
+class ControlNetSDVModel(_NetBase):
+    """Mirror of models/controlnet_sdv*.py `ControlNetSDVModel` (flags: cam=True for the `_cam`/`_cam_infer`
+    variants, bbox=True for `_bbox`)."""
+    kind = "controlnet"
+
+    def __init__(self, cfg: SVDConfig, state_dict, device=None, cam: bool = False, bbox: bool = False):
+        super().__init__(cfg, state_dict, device, cam=cam, bbox=bbox)
+
+    def expected_shapes(self):
+        return controlnet_param_shapes(self.cfg, cam=self.flags["cam"], bbox=self.flags["bbox"])
+
+    @classmethod
+    def from_random(cls, cfg: SVDConfig = SVDConfig(), device=None, seed: int = 0, cam=False, bbox=False,
+                    faithful_zero_init: bool = True):
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        zero = ("controlnet_down_blocks", "controlnet_mid_block", "controlnet_cond_embedding.conv_out") if faithful_zero_init else ()
+        sd = random_state_dict(controlnet_param_shapes(cfg, cam, bbox), device, seed + 1, zero_keys=zero)
+        return cls(cfg, sd, device, cam=cam, bbox=bbox)
+
+    @classmethod
+    def from_unet(cls, unet: "UNetSpatioTemporalConditionControlNetModel", controlnet_conditioning_channel_order="rgb",
+                  conditioning_embedding_out_channels=(16, 32, 96, 256), load_weights_from_unet: bool = True,
+                  conditioning_channels: int = 3, seed: int = 0):
+        """controlnet_sdv.py:653-709: copies conv_in, time_embedding, down_blocks, mid_block (NOT add_embedding)."""
+        cfg = SVDConfig(**{**asdict(unet.cfg), "conditioning_channels": conditioning_channels,
+                           "conditioning_embedding_out_channels": tuple(conditioning_embedding_out_channels)})
+        shapes = controlnet_param_shapes(cfg)
+        sd = random_state_dict(shapes, unet.device, seed + 1,
+                               zero_keys=("controlnet_down_blocks", "controlnet_mid_block", "controlnet_cond_embedding.conv_out"))
+        if load_weights_from_unet:
+            usd = unet.state_dict()
+            for k in sd:
+                if k.startswith(("conv_in.", "time_embedding.", "down_blocks.", "mid_block.")):
+                    sd[k] = usd[k]
+        return cls(cfg, sd, unet.device)
+
+    def forward(self, sample, timestep, encoder_hidden_states, added_time_ids, controlnet_cond=None,
+                camera_cond=None, controlnet_bbox=None, image_only_indicator=None, return_dict: bool = True,
+                guess_mode: bool = False, conditioning_scale: float = 1.0, _plan_kwargs=None):
+        B, Fr, _, H, W = sample.shape
+        sp = torch.cuda.current_stream().cuda_stream
+        cond_hw = tuple(controlnet_cond.shape[-2:]) if controlnet_cond is not None else (H * 8, W * 8)
+        plan = self.plan_for(B, Fr, H, W, cond_hw=cond_hw, **(_plan_kwargs or {}))
+        self._stage_common(plan, sample, timestep, encoder_hidden_states, added_time_ids, sp)
+        self.stage_condition(plan, controlnet_cond, camera_cond, controlnet_bbox, sp)
+        plan.set_conditioning_scale(conditioning_scale)
+        NetPlan.run(plan.step_ops, sp)
+        down = [self._as_nchw_view(t, B * Fr, *self._hw_of(plan, i)) for i, t in enumerate(plan.res[:-1])]
+        mid = self._as_nchw_view(plan.res[-1], B * Fr, *plan.level_hw[-1])
+        if not return_dict:
+            return (down, mid)
+        return ControlNetOutput(down_block_res_samples=down, mid_block_res_sample=mid)
+
+    @staticmethod
+    def _hw_of(plan: NetPlan, i: int):
+        rows = plan.res_shapes[i][0] // plan.n
+        for hw in plan.level_hw:
+            if hw[0] * hw[1] == rows:
+                return hw
+        raise AssertionError
+
+    def stage_condition(self, plan: NetPlan, controlnet_cond, camera_cond, controlnet_bbox, sp) -> None:
+        """Runs the (step-invariant) conditioning embedding when its inputs changed (controlnet_sdv.py:596-599)."""
+        if controlnet_cond is None:
+            if getattr(plan, "_cond_key", None) != "none":
+                plan.cond_emb.zero_()
+                plan._cond_key = "none"
+            return
+        key = (controlnet_cond.data_ptr(), controlnet_cond._version,
+               None if camera_cond is None else (camera_cond.data_ptr(), camera_cond._version),
+               None if controlnet_bbox is None else (controlnet_bbox.data_ptr(), controlnet_bbox._version))
+        if getattr(plan, "_cond_key", None) == key:
+            return
+        plan.cond_in.copy_(controlnet_cond.detach().reshape(plan.cond_in.shape).to(F32))
+        if camera_cond is not None:
+            if not plan.cam:
+                raise ValueError("camera_cond given but this ControlNet was built without cc_projection (cam=False)")
+            plan.cam_in.copy_(camera_cond.detach().reshape(plan.n, 12).to(F32))
+        if controlnet_bbox is not None and plan.bbox:
+            plan.cond_in2.copy_(controlnet_bbox.detach().reshape(plan.cond_in2.shape).to(F32))
+        NetPlan.run(plan.cond_op_list(camera_cond is not None, controlnet_bbox is not None), sp)
+        plan._cond_key = key
+
+
+class UNetSpatioTemporalConditionControlNetModel(_NetBase):
+    kind = "unet"
+
+    def expected_shapes(self):
+        return unet_param_shapes(self.cfg)
+
+    @classmethod
+    def from_random(cls, cfg: SVDConfig = SVDConfig(), device=None, seed: int = 0):
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        return cls(cfg, random_state_dict(unet_param_shapes(cfg), device, seed), device)
+
+    def forward(self, sample, timestep, encoder_hidden_states, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, return_dict: bool = True, added_time_ids=None, _plan_kwargs=None):
+        B, Fr, _, H, W = sample.shape
+        sp = torch.cuda.current_stream().cuda_stream
+        plan = self._plan_matching(B, Fr, H, W, down_block_additional_residuals, _plan_kwargs)
+        self._stage_common(plan, sample, timestep, encoder_hidden_states, added_time_ids, sp)
+        self._stage_residuals(plan, down_block_additional_residuals, mid_block_additional_residual)
+        NetPlan.run(plan.step_ops, sp)
+        out = torch.empty(B * Fr, self.cfg.out_channels, H, W, device=self._device,
+                          dtype=sample.dtype if sample.dtype in (F32, BF16) else F32)
+        ops.Layout(out, plan.noise_pred, to_tokens=False).launch(sp)
+        out = out.view(B, Fr, self.cfg.out_channels, H, W)
+        if not return_dict:
+            return (out,)
+        return UNetSpatioTemporalConditionOutput(sample=out)
+
+    def _plan_matching(self, B, Fr, H, W, residuals, plan_kwargs):
+        """Prefer a plan whose residual buffers ARE the tensors handed in (zero-copy hand-off from the ControlNet)."""
+        if residuals is not None and len(residuals) > 0:
+            ptr = residuals[0].data_ptr()
+            for p in self._plans.values():
+                if (p.B, p.F, p.H, p.W) == (B, Fr, H, W) and p.res[0].data_ptr() == ptr:
+                    return p
+        return self.plan_for(B, Fr, H, W, **(plan_kwargs or {}))
+
+    def adopt_residual_buffers(self, controlnet_plan: NetPlan) -> NetPlan:
+        """Build (once) a plan that reads the ControlNet plan's residual buffers in place."""
+        p = controlnet_plan
+        return self.plan_for(p.B, p.F, p.H, p.W, residual_bufs=p.res)
+
+    def _stage_residuals(self, plan: NetPlan, down, mid) -> None:
+        if down is None:
+            for t in plan.res[:-1]:
+                t.zero_()
+        else:
+            if len(down) != len(plan.res) - 1:
+                raise ValueError(f"expected {len(plan.res) - 1} down_block_additional_residuals, got {len(down)}")
+            for dst, src in zip(plan.res[:-1], down):
+                self._copy_residual(dst, src, plan.n)
+        if mid is None:
+            plan.res[-1].zero_()
+        else:
+            self._copy_residual(plan.res[-1], mid, plan.n)
+
+    @staticmethod
+    def _copy_residual(dst: torch.Tensor, src: torch.Tensor, n: int) -> None:
+        if src.data_ptr() == dst.data_ptr():
+            return
+        Cc = dst.shape[1]
+        h, w = src.shape[-2:]
+        dst.view(n, h, w, Cc).copy_(src.detach().permute(0, 2, 3, 1))

@@ -180,7 +180,7 @@ class CfgEuler:
     def __init__(self, *, noise_pred: Optional[torch.Tensor], latents: torch.Tensor, guidance: torch.Tensor,
                  sigmas: torch.Tensor, step_index: torch.Tensor, next_in: Optional[torch.Tensor] = None,
                  image_latents: Optional[torch.Tensor] = None, next_padded: bool = True, mode: int = 0,
-                 pred_nchw_f32: bool = False):
+                 pred_nchw_f32: bool = False, single_pred: bool = False):
         F_, Cc, H, W = latents.shape[-4:]
         assert latents.dtype == torch.float32 and latents.is_contiguous()
         assert guidance.dtype == torch.float32 and sigmas.dtype == torch.float32 and step_index.dtype == torch.int32
@@ -205,6 +205,7 @@ class CfgEuler:
             a.next_ld = next_in.stride(0)
             a.next_padded = 1 if next_padded else 0
         a.mode = mode
+        a.single_pred = 1 if single_pred else 0
         self.args = a
         self._keep = (noise_pred, latents, guidance, sigmas, step_index, next_in, image_latents)
         self._argp = C.addressof(a)
@@ -346,13 +347,13 @@ class SinCos(_Op):
 class Upsample2x(_Op):
     fn_name = "pt_upsample2x"
 
-    def __init__(self, x, out, *, n, H, W, halo=True, name=None):
+    def __init__(self, x, out, *, n, H, W, halo=True, scale=2, name=None):
         a = _lib.PtUpsampleArgs()
         assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and x.shape[0] == n * H * W
         a.x, a.ld = x.data_ptr(), x.stride(0)
         a.out, a.out_ld = out.data_ptr(), out.stride(0)
-        a.n, a.H, a.W, a.C, a.halo = n, H, W, x.shape[1], int(halo)
-        exp_rows = n * (2 * H + 1) * (2 * W + 1) if halo else n * 4 * H * W
+        a.n, a.H, a.W, a.C, a.halo, a.scale = n, H, W, x.shape[1], int(halo), scale
+        exp_rows = n * (scale * H + 1) * (scale * W + 1) if halo else n * scale * scale * H * W
         assert out.shape[0] == exp_rows
         self._finish(a, (x, out), name)
 
@@ -392,3 +393,13 @@ class Layout(_Op):
         rows = a.n * ((a.H + 1) * (a.W + 1) if halo else a.H * a.W)
         assert tokens.shape[0] == rows and tokens.shape[1] >= a.C
         self._finish(a, (nchw, tokens), name)
+
+
+class StepAdvance:
+    def __init__(self, step_index: torch.Tensor):
+        assert step_index.dtype == torch.int32
+        self.step_index = step_index
+        self.name = "pt_step_advance"
+
+    def launch(self, stream_ptr: int) -> None:
+        _lib.check(_lib.lib().pt_step_advance(self.step_index.data_ptr(), stream_ptr), self.name)

@@ -1,0 +1,265 @@
+"""Mirror of `StableVideoDiffusionPipelineControlNet` with the denoise loop on the sm_100a kernels.
+
+Reference: /root/reference/pipeline/pipeline_stable_video_diffusion_controlnet.py
+  __call__ :317-340 (signature kept verbatim), prepare_latents :267-299, added_time_ids override :513-523,
+  guidance scale :506-509, denoise loop :526-583; the `_cam` variant
+  (/root/reference/pipeline/pipeline_stable_video_diffusion_controlnet_cam.py:321,506-509,549) adds `camera_cond`.
+
+What runs where
+  * per step: ControlNet plan -> UNet plan -> fused CFG + Euler + next-input kernel -> device step counter.  The
+    per-step kernel sequence is captured into a CUDA graph (same kernels, replayed) unless a step-end callback
+    needs host control between steps.
+  * once per call: Karras sigma table (host float64, like the reference), ControlNet conditioning embedding,
+    the 1-token cross-attention vectors.
+  * CLIP image encoding and the VAE are outside the hot path: pass `image_encoder` /
+    `vae` modules to use them, or hand the pipeline `image_embeddings=` / `image_latents=` directly
+    (then `image` may be None and only output_type="latent" is available).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Union
+
+import torch
+
+from . import ops
+from .engine import BF16, F32, NetPlan
+from .models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+from .scheduler import EulerDiscreteScheduler
+
+
+@dataclass
+class StableVideoDiffusionPipelineOutput:
+    frames: Union[List, torch.Tensor]
+
+
+def _get_add_time_ids(noise_aug_strength, dtype, batch_size, fps=4, motion_bucket_id=128, unet=None):
+    """pipeline...controlnet.py:37-59 (module-level helper used for the hard override at :513-523)."""
+    add_time_ids = [fps, motion_bucket_id, noise_aug_strength]
+    passed = unet.config.addition_time_embed_dim * len(add_time_ids)
+    expected = unet.add_embedding.linear_1.in_features
+    if expected != passed:
+        raise ValueError(f"Model expects an added time embedding vector of length {expected}, but a vector of "
+                         f"{passed} was created. The model has an incorrect config.")
+    return torch.tensor([add_time_ids], dtype=dtype)
+
+
+class DenoiseEngine:
+    """One video's denoise loop: both network plans wired to shared buffers + the fused scheduler kernel."""
+
+    def __init__(self, unet: UNetSpatioTemporalConditionControlNetModel, controlnet: ControlNetSDVModel,
+                 scheduler: EulerDiscreteScheduler, *, frames: int, h: int, w: int, cond_hw: tuple, device):
+        self.unet, self.controlnet, self.scheduler = unet, controlnet, scheduler
+        self.F, self.h, self.w, self.device = frames, h, w, device
+        cfg = unet.cfg
+        self.latents = torch.zeros(frames, cfg.out_channels, h, w, device=device, dtype=F32)
+        self.image_latents = torch.zeros(2, frames, cfg.out_channels, h, w, device=device, dtype=F32)
+        self.guidance = torch.ones(frames, device=device, dtype=F32)
+        self.step_index = torch.zeros(1, device=device, dtype=torch.int32)
+        self.sigmas = torch.zeros(1024, device=device, dtype=F32)
+        kw = dict(sigmas=self.sigmas, step_index=self.step_index)
+        self.cplan: NetPlan = controlnet.plan_for(2, frames, h, w, cond_hw=cond_hw, **kw)
+        self.uplan: NetPlan = unet.plan_for(2, frames, h, w, x_in=self.cplan.x_in, residual_bufs=self.cplan.res, **kw)
+        common = dict(latents=self.latents, guidance=self.guidance, sigmas=self.sigmas, step_index=self.step_index,
+                      next_in=self.cplan.x_in, image_latents=self.image_latents, next_padded=True)
+        self.prepare_op = ops.CfgEuler(noise_pred=None, mode=1, **common)
+        self.update_op = ops.CfgEuler(noise_pred=self.uplan.noise_pred, mode=0, **common)
+        self.step_ops = self.cplan.step_ops + self.uplan.step_ops + [self.update_op, ops.StepAdvance(self.step_index)]
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = len(self.step_ops) + sum(1 for o in self.step_ops if isinstance(o, ops.GroupNorm))
+
+    def load(self, *, latents, image_latents, image_embeddings, added_time_ids, guidance, sigmas,
+             controlnet_condition, camera_cond=None, cond_scale: float = 1.0) -> None:
+        """Stage one video's inputs (host->device copies happen here) and run the step-invariant prologue."""
+        sp = torch.cuda.current_stream().cuda_stream
+        self.latents.copy_(latents.reshape(self.latents.shape))
+        self.image_latents.copy_(image_latents.reshape(self.image_latents.shape))
+        self.guidance.copy_(guidance.reshape(-1))
+        n = sigmas.numel()
+        self.sigmas[:n].copy_(sigmas)
+        self.step_index.zero_()
+        for plan in (self.cplan, self.uplan):
+            plan.ehs.copy_(image_embeddings[:, 0, :])
+            plan.time_ids.copy_(added_time_ids.reshape(-1))
+            NetPlan.run(plan.embed_ops, sp)
+        self.controlnet.stage_condition(self.cplan, controlnet_condition, camera_cond, None, sp)
+        self.cplan.set_conditioning_scale(cond_scale)
+        self.prepare_op.launch(sp)
+
+    def step(self) -> None:
+        """One denoise step (all kernels of ControlNet + UNet + CFG/Euler)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            NetPlan.run(self.step_ops, torch.cuda.current_stream().cuda_stream)
+
+    def capture(self) -> None:
+        """Capture the per-step kernel sequence into a CUDA graph (call after at least one eager step)."""
+        if self.graph is not None:
+            return
+        saved = self.step_index.clone(), self.latents.clone(), self.cplan.x_in.clone()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                NetPlan.run(self.step_ops, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.current_stream().wait_stream(s)
+        # capture does not execute, but keep state exactly as before anyway
+        self.step_index.copy_(saved[0]); self.latents.copy_(saved[1]); self.cplan.x_in.copy_(saved[2])
+        self.graph = g
+
+
+class StableVideoDiffusionPipelineControlNet:
+    """Same constructor components and `__call__` signature as the reference pipeline."""
+
+    def __init__(self, vae=None, image_encoder=None, unet: UNetSpatioTemporalConditionControlNetModel = None,
+                 controlnet: ControlNetSDVModel = None, scheduler: EulerDiscreteScheduler = None,
+                 feature_extractor=None):
+        self.vae, self.image_encoder, self.unet, self.controlnet = vae, image_encoder, unet, controlnet
+        self.scheduler = scheduler or EulerDiscreteScheduler()
+        self.feature_extractor = feature_extractor
+        self.vae_scale_factor = 8
+        self._engines: Dict[tuple, DenoiseEngine] = {}
+        self._guidance_scale = None
+        self._num_timesteps = 0
+        self.use_cuda_graph = True
+
+    @property
+    def guidance_scale(self):
+        return self._guidance_scale
+
+    @property
+    def num_timesteps(self):
+        return self._num_timesteps
+
+    @property
+    def _execution_device(self):
+        return self.unet.device
+
+    def check_inputs(self, image, height, width):
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+
+    def prepare_latents(self, batch_size, num_frames, num_channels_latents, height, width, dtype, device, generator,
+                        latents=None):
+        shape = (batch_size, num_frames, num_channels_latents // 2, height // self.vae_scale_factor,
+                 width // self.vae_scale_factor)
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective"
+                             f" batch size of {batch_size}. Make sure the batch size matches the length of the generators.")
+        if latents is None:
+            gdev = generator.device if isinstance(generator, torch.Generator) else device
+            latents = torch.randn(shape, generator=generator, device=gdev, dtype=dtype).to(device)
+        else:
+            latents = latents.to(device)
+        return latents * self.scheduler.init_noise_sigma
+
+    def engine_for(self, frames, h, w, cond_hw) -> DenoiseEngine:
+        key = (frames, h, w, tuple(cond_hw))
+        if key not in self._engines:
+            self._engines[key] = DenoiseEngine(self.unet, self.controlnet, self.scheduler, frames=frames, h=h, w=w,
+                                               cond_hw=cond_hw, device=self._execution_device)
+        return self._engines[key]
+
+    @torch.no_grad()
+    def __call__(self, image=None, controlnet_condition=None, camera_cond=None, height: int = 576, width: int = 1024,
+                 num_frames: Optional[int] = None, num_inference_steps: int = 25, min_guidance_scale: float = 1.0,
+                 max_guidance_scale: float = 3.0, fps: int = 7, motion_bucket_id: int = 127,
+                 noise_aug_strength: float = 0.02, decode_chunk_size: Optional[int] = None,
+                 num_videos_per_prompt: Optional[int] = 1, generator=None, latents: Optional[torch.Tensor] = None,
+                 output_type: Optional[str] = "pil", callback_on_step_end: Optional[Callable] = None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
+                 controlnet_cond_scale=1.0, batch_size=1, image_embeddings: Optional[torch.Tensor] = None,
+                 image_latents: Optional[torch.Tensor] = None):
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
+        self.check_inputs(image, height, width)
+        device = self._execution_device
+        if batch_size * num_videos_per_prompt != 1:
+            # the reference scripts call the pipeline once per video; batching videos into one call would change
+            # results through the temporal cross-attention interleave
+            raise ValueError("posetraj_b200: one video per call (batch_size * num_videos_per_prompt must be 1)")
+        if max_guidance_scale <= 1.0:
+            raise ValueError("posetraj_b200: the path is built for classifier-free guidance (max_guidance_scale > 1)")
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+
+        # 3./4. image conditioning (outside the hot path)
+        if image_embeddings is None or image_latents is None:
+            if self.image_encoder is None or self.vae is None:
+                raise ValueError("pass image_embeddings= and image_latents= (or construct the pipeline with "
+                                 "image_encoder and vae modules)")
+            image_embeddings, image_latents = self._encode_conditioning(image, height, width, noise_aug_strength,
+                                                                        generator, device)
+        image_embeddings = image_embeddings.to(device=device, dtype=F32)
+        image_latents = image_latents.to(device=device, dtype=F32)
+        if image_latents.dim() == 4:  # [2, C, h, w] -> repeat per frame (:466)
+            image_latents = image_latents.unsqueeze(1).repeat(1, num_frames, 1, 1, 1)
+
+        # 4. timesteps, 5. latents
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        timesteps = self.scheduler.timesteps
+        latents = self.prepare_latents(1, num_frames, self.unet.config.in_channels, height, width, F32, device,
+                                       generator, latents)
+        # controlnet condition: [F, 3, H, W] in [-1, 1] -> duplicated for the CFG pair (:500-503)
+        cond = controlnet_condition
+        if cond is None:
+            raise ValueError("controlnet_condition is required")
+        cond = cond.to(device=device, dtype=F32)
+        if cond.dim() == 4:
+            cond = cond.unsqueeze(0)
+        if cond.shape[0] == 1:
+            cond = torch.cat([cond] * 2)
+        cam = None
+        if camera_cond is not None:
+            cam = torch.as_tensor(camera_cond).to(device=device, dtype=F32)
+            if cam.dim() == 2:
+                cam = cam.unsqueeze(0)
+            if cam.shape[0] == 1:
+                cam = torch.cat([cam] * 2)  # ..._cam.py:506-509
+        # 7. guidance scale per frame (:506-509)
+        guidance = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames, device=device, dtype=F32)
+        self._guidance_scale = guidance.view(1, num_frames, 1, 1, 1)
+        # added_time_ids hard override [6, 128, 0.02] x2 (:513-523): the caller's fps / motion_bucket_id are ignored
+        added_time_ids = _get_add_time_ids(0.02, F32, 1, 6, 128, unet=self.unet)
+        added_time_ids = torch.cat([added_time_ids] * 2).to(device)
+
+        # 8. denoising loop
+        eng = self.engine_for(num_frames, h, w, tuple(cond.shape[-2:]))
+        eng.load(latents=latents, image_latents=image_latents, image_embeddings=image_embeddings,
+                 added_time_ids=added_time_ids, guidance=guidance, sigmas=self.scheduler.sigmas,
+                 controlnet_condition=cond, camera_cond=cam, cond_scale=float(controlnet_cond_scale))
+        self._num_timesteps = len(timesteps)
+        use_graph = self.use_cuda_graph and callback_on_step_end is None
+        for i, t in enumerate(timesteps):
+            if use_graph and i == 1:
+                eng.capture()
+            if use_graph and i >= 1:
+                eng.graph.replay()
+            else:
+                NetPlan.run(eng.step_ops, torch.cuda.current_stream().cuda_stream)
+            if callback_on_step_end is not None:
+                cb_latents = eng.latents.view(1, num_frames, -1, h, w)
+                out = callback_on_step_end(self, i, t, {"latents": cb_latents})
+                new = out.pop("latents", cb_latents) if isinstance(out, dict) else cb_latents
+                if new.data_ptr() != eng.latents.data_ptr():
+                    eng.latents.copy_(new.reshape(eng.latents.shape))
+        latents = eng.latents.view(1, num_frames, -1, h, w).clone()
+
+        if output_type != "latent":
+            if self.vae is None:
+                raise ValueError("output_type other than 'latent' needs a VAE (SURVEY.md §8f row 2)")
+            frames = self.decode_latents(latents, num_frames, decode_chunk_size or num_frames)
+        else:
+            frames = latents
+        if not return_dict:
+            return frames
+        return StableVideoDiffusionPipelineOutput(frames=frames)
+
+    # ---- outside the hot path: thin adapters over user-supplied HF modules ------------------------------
+    def _encode_conditioning(self, image, height, width, noise_aug_strength, generator, device):
+        raise NotImplementedError("CLIP / VAE encoding is next-scope (SURVEY.md §8f): pass image_embeddings/image_latents")
+
+    def decode_latents(self, latents, num_frames, decode_chunk_size):
+        raise NotImplementedError("VAE decoding is next-scope (SURVEY.md §8f): use output_type='latent'")

@@ -1,0 +1,121 @@
+"""Parity of the CUDA path against the oracle on identical weights and inputs (GPU tests, through the
+reference-shaped module API which lowers onto the C ABI).
+
+Tolerance (north_star): per-step noise prediction relative L2 <= 1e-2 in bf16; ControlNet residuals the same.
+"""
+import pytest
+import torch
+
+from parity_util import make_small_inputs, oracle_pair, rel_l2, small_cfg
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def to_dev(d, dev):
+    return {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+@pytest.fixture(scope="module")
+def small_setup(cuda_dev):
+    from posetraj_b200.models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+    cfg = small_cfg()
+    o_unet, o_cnet = oracle_pair(cfg, seed=0, cam=True)
+    unet = UNetSpatioTemporalConditionControlNetModel(cfg, o_unet.state_dict(), cuda_dev)
+    cnet = ControlNetSDVModel(cfg, o_cnet.state_dict(), cuda_dev, cam=True)
+    return cfg, o_unet, o_cnet, unet, cnet
+
+
+def model_input(inp, sigma):
+    x = torch.cat([inp["latents"]] * 2) / (sigma ** 2 + 1) ** 0.5
+    return torch.cat([x, inp["image_latents"]], dim=2)
+
+
+@pytest.mark.parametrize("sigma,use_cam", [(700.0, False), (10.0, True), (0.05, False)])
+def test_single_step_parity(small_setup, cuda_dev, sigma, use_cam):
+    cfg, o_unet, o_cnet, unet, cnet = small_setup
+    inp = make_small_inputs(cfg)
+    x = model_input(inp, sigma)
+    t = torch.tensor(0.25 * torch.log(torch.tensor(sigma)))
+    cam = inp["camera_cond"] if use_cam else None
+    with torch.no_grad():
+        o_down, o_mid = o_cnet(x, t, inp["image_embeddings"], inp["added_time_ids"], controlnet_cond=inp["controlnet_condition"],
+                               camera_cond=cam, conditioning_scale=0.8)
+        o_pred = o_unet(x, t, inp["image_embeddings"], down_block_additional_residuals=o_down,
+                        mid_block_additional_residual=o_mid, added_time_ids=inp["added_time_ids"])
+    d = to_dev(inp, cuda_dev)
+    xd = x.to(cuda_dev)
+    down, mid = cnet(xd, t.to(cuda_dev), d["image_embeddings"], d["added_time_ids"], controlnet_cond=d["controlnet_condition"],
+                     camera_cond=None if cam is None else d["camera_cond"], conditioning_scale=0.8, return_dict=False)
+    torch.cuda.synchronize()
+    errs = [rel_l2(a, b) for a, b in zip(down + [mid], o_down + [o_mid])]
+    assert max(errs) < TOL, errs
+    assert all(a.shape == b.shape for a, b in zip(down + [mid], o_down + [o_mid]))
+    pred = unet(xd, t.to(cuda_dev), d["image_embeddings"], down_block_additional_residuals=down,
+                mid_block_additional_residual=mid, added_time_ids=d["added_time_ids"], return_dict=False)[0]
+    torch.cuda.synchronize()
+    assert pred.shape == o_pred.shape
+    e = rel_l2(pred, o_pred)
+    assert e < TOL, e
+
+
+def test_external_residual_tensors(small_setup, cuda_dev):
+    """UNet fed ordinary NCHW tensors (not the ControlNet's own buffers): same result as the oracle."""
+    cfg, o_unet, o_cnet, unet, cnet = small_setup
+    inp = make_small_inputs(cfg, seed=77)
+    x = model_input(inp, 3.0)
+    t = torch.tensor(0.25 * torch.log(torch.tensor(3.0)))
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        o_down, o_mid = o_cnet(x, t, inp["image_embeddings"], inp["added_time_ids"], controlnet_cond=inp["controlnet_condition"])
+        o_down = [torch.randn(r.shape, generator=g) * 0.3 for r in o_down]
+        o_mid = torch.randn(o_mid.shape, generator=g) * 0.3
+        o_pred = o_unet(x, t, inp["image_embeddings"], down_block_additional_residuals=o_down,
+                        mid_block_additional_residual=o_mid, added_time_ids=inp["added_time_ids"])
+    d = to_dev(inp, cuda_dev)
+    pred = unet(x.to(cuda_dev), t.to(cuda_dev), d["image_embeddings"],
+                down_block_additional_residuals=[r.to(cuda_dev) for r in o_down],
+                mid_block_additional_residual=o_mid.to(cuda_dev), added_time_ids=d["added_time_ids"]).sample
+    torch.cuda.synchronize()
+    assert rel_l2(pred, o_pred) < TOL
+
+
+def test_zero_init_controlnet_gives_zero_residuals(cuda_dev):
+    """Invariant (SURVEY.md §4 i): a faithfully initialised ControlNet (zero_module convs) outputs exact zeros."""
+    from posetraj_b200.models import ControlNetSDVModel
+    cfg = small_cfg()
+    cnet = ControlNetSDVModel.from_random(cfg, cuda_dev, seed=3)
+    inp = to_dev(make_small_inputs(cfg), cuda_dev)
+    x = model_input(inp, 50.0)
+    down, mid = cnet(x, 0.9, inp["image_embeddings"], inp["added_time_ids"], controlnet_cond=inp["controlnet_condition"],
+                     return_dict=False)
+    torch.cuda.synchronize()
+    assert all(float(r.abs().max()) == 0.0 for r in down + [mid])
+
+
+def test_pipeline_three_steps(small_setup, cuda_dev):
+    """Fused loop (ControlNet -> UNet -> CFG+Euler kernel, CUDA-graph replay) vs the oracle's loop."""
+    from oracle.pipeline import denoise
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    cfg, o_unet, o_cnet, unet, cnet = small_setup
+    inp = make_small_inputs(cfg, seed=99)
+    steps = 4
+    with torch.no_grad():
+        want = denoise(o_unet, o_cnet, inp["latents"], inp["image_latents"], inp["image_embeddings"],
+                       inp["controlnet_condition"], inp["added_time_ids"], inp["guidance"], num_inference_steps=steps)
+    pipe = StableVideoDiffusionPipelineControlNet(unet=unet, controlnet=cnet)
+    h, w = inp["latents"].shape[-2:]
+    init_sigma = (700.0 ** 2 + 1) ** 0.5
+    got = pipe(None, inp["controlnet_condition"][0].to(cuda_dev), height=h * 8, width=w * 8, num_frames=cfg.num_frames,
+               num_inference_steps=steps, latents=(inp["latents"] / init_sigma).to(cuda_dev), output_type="latent",
+               image_embeddings=inp["image_embeddings"].to(cuda_dev), image_latents=inp["image_latents"].to(cuda_dev)).frames
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    assert rel_l2(got, want) < TOL
+    # eager replay (callback path) must agree with the graph path
+    got2 = pipe(None, inp["controlnet_condition"][0].to(cuda_dev), height=h * 8, width=w * 8, num_frames=cfg.num_frames,
+                num_inference_steps=steps, latents=(inp["latents"] / init_sigma).to(cuda_dev), output_type="latent",
+                image_embeddings=inp["image_embeddings"].to(cuda_dev), image_latents=inp["image_latents"].to(cuda_dev),
+                callback_on_step_end=lambda p, i, t, kw: kw).frames
+    torch.cuda.synchronize()
+    assert rel_l2(got2, got) < 1e-6
