@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — PoseTraj denoising hot path on B200 (BASELINE.json metric: UNet+ControlNet denoise steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is ONE denoise step of the reference loop
+(/root/reference/pipeline/pipeline_stable_video_diffusion_controlnet.py:530-572): ControlNetSDV forward + UNet forward
+on the CFG pair (2 x 14 frames x 8 ch x 40x72 latent, 320x576 px), CFG combine and the Euler-Karras update — the
+workload of BASELINE.json configs[1] (25-step sampling, bf16 storage / fp32 accumulate, random-init SVD-shaped
+weights, synthetic inputs).
+
+  value      steps/s with the video's inputs resident in HBM (CUDA-graph replay of the per-step kernel list), whole job
+             over N GPUs; N > 1 = one independent video per rank (video-batch sharding, weak scaling, no collective
+             on the data path: SURVEY.md §8e).
+  e2e        the same metric through the public API, `StableVideoDiffusionPipelineControlNet.__call__`, fed HOST
+             (pinned) tensors, with the host->device copies of the conditioning and the device->host read of the
+             final latents inside the timed region.
+  roofline   the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): algorithmic FLOPs / CUDA-event time of its
+             launches inside one step, against MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference   the oracle (CPU restatement of the reference; the reference itself needs
+             diffusers==0.24.0 which does not exist in this image) on all host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoise_steps_per_sec"
+UNIT = "steps/s"
+FRAMES, LAT_H, LAT_W, SAMPLING_STEPS = 14, 40, 72, 25
+WORKLOAD = "configs[1]: 25-step Euler-Karras SVD-img2vid, CFG pair x 14 frames x 320x576 (latent 40x72), 1 trajectory"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe) during the timed region
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores (cpu_baseline of the own arm, and `--impl reference`)
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_sample_plan(budget_s_per_step: float):
+    """Pick a bounded sample of the workload: (frames, h, w).  ~7 s per frame at 40x72 on 8 cores (measured)."""
+    import torch
+    cores = torch.get_num_threads()
+    per_frame = 7.0 * 8 / max(cores, 1)
+    if budget_s_per_step >= 2 * per_frame:
+        return 2, LAT_H, LAT_W
+    if budget_s_per_step >= per_frame:
+        return 1, LAT_H, LAT_W
+    return 1, 24, 40  # quarter-ish resolution: still every layer of both networks
+
+
+def cpu_oracle_steps_per_sec(steps: int, warmup: int, budget_s: float = 150.0):
+    """Times the oracle (fp32, all host threads) on a bounded sample and extrapolates by algorithmic FLOPs."""
+    import torch
+    from oracle.models import build_models
+    from oracle.pipeline import denoise_step, make_inputs
+    from oracle.scheduler import EulerKarrasOracle
+    from posetraj_b200.config import SVDConfig
+    from posetraj_b200.roofline import step_flops
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    f, h, w = _cpu_sample_plan(budget_s / max(1, steps + warmup))
+    unet, cnet = build_models(seed=0, randomize_zero_convs=True)
+    inp = make_inputs(num_frames=f, h=h, w=w)
+    cond = torch.full((2, f, 3, h * 8, w * 8), -1.0)
+    sched = EulerKarrasOracle()
+    sched.set_timesteps(SAMPLING_STEPS)
+    lat = inp["latents"]
+    times = []
+    for i in range(warmup + steps):
+        sched._step_index = None
+        k = i % SAMPLING_STEPS
+        t0 = time.perf_counter()
+        lat_new = denoise_step(unet, cnet, sched, lat, k, sched.timesteps[k], inp["image_latents"], inp["image_embeddings"],
+                               cond, inp["added_time_ids"], inp["guidance"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        del lat_new
+    t_step = sum(times) / len(times)
+    full, _ = step_flops(SVDConfig(), frames=FRAMES, h=LAT_H, w=LAT_W)
+    part, _ = step_flops(SVDConfig(), frames=f, h=h, w=w)
+    value = (part / full) / t_step
+    sample = (f"oracle (torch CPU fp32 restatement of the reference) on {f} of {FRAMES} frames at latent {h}x{w}, "
+              f"{steps} timed step(s) of {t_step:.2f} s each, scaled by algorithmic FLOPs {part / 1e12:.2f}/{full / 1e12:.2f} TFLOP")
+    return value, t_step, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, t_step, cores, sample = cpu_oracle_steps_per_sec(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "weights": "random-init SVD-shaped UNet 1524.6M + ControlNetSDV 682.0M",
+                   "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------------------------
+def time_op_classes(step_ops, stream, reps: int = 2):
+    """CUDA-event time of every launch descriptor of one step (eager replay on `stream`), summed per kernel class."""
+    import torch
+    acc = {}
+    for rep in range(reps + 1):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(step_ops) + 1)]
+        evs[0].record(stream)
+        for i, op in enumerate(step_ops):
+            op.launch(stream.cuda_stream)
+            evs[i + 1].record(stream)
+        stream.synchronize()
+        if rep == 0:
+            continue  # warm
+        for i, op in enumerate(step_ops):
+            ms = evs[i].elapsed_time(evs[i + 1])
+            d = acc.setdefault(op.kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += ms / reps
+            d["flops"] += op.alg_flops / reps
+            d["bytes"] += op.alg_bytes / reps
+            d["launches"] += 1.0 / reps
+    return acc
+
+
+def _synthetic_condition(frames, H, W):
+    """One track, 14 points linearly from (100,80) to (460,240) px, drawn per frame transition as a
+    red 3-px segment + green end disc on black, frame F-1 black, scaled to [-1, 1] like VaeImageProcessor.preprocess."""
+    import torch
+    img = torch.zeros(frames, 3, H, W)
+    xs = torch.linspace(100, 460, frames)
+    ys = torch.linspace(80, 240, frames)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    for k in range(frames - 1):
+        x0, y0, x1, y1 = xs[k], ys[k], xs[k + 1], ys[k + 1]
+        dx, dy = x1 - x0, y1 - y0
+        tt = (((xx - x0) * dx + (yy - y0) * dy) / (dx * dx + dy * dy)).clamp(0, 1)
+        dist = ((xx - (x0 + tt * dx)) ** 2 + (yy - (y0 + tt * dy)) ** 2).sqrt()
+        img[k, 0][dist <= 1.5] = 1.0
+        disc = ((xx - x1) ** 2 + (yy - y1) ** 2).sqrt() <= 3.0
+        img[k, 0][disc] = 0.0
+        img[k, 1][disc] = 1.0
+    return img * 2.0 - 1.0
+
+
+def run_own(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from posetraj_b200 import _lib
+    from posetraj_b200.config import SVDConfig
+    from posetraj_b200.models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    from posetraj_b200.roofline import step_flops
+
+    cfg = SVDConfig()
+    unet = UNetSpatioTemporalConditionControlNetModel.from_random(cfg, dev, seed=0)
+    cnet = ControlNetSDVModel.from_random(cfg, dev, seed=0, faithful_zero_init=False)
+    pipe = StableVideoDiffusionPipelineControlNet(unet=unet, controlnet=cnet)
+
+    # ---- synthetic inputs of one video, in pinned host memory (each rank its own seed = its own video) ----------
+    g = torch.Generator().manual_seed(1234 + rank)
+    H, W = LAT_H * 8, LAT_W * 8
+    lat_unit = torch.randn(1, FRAMES, 4, LAT_H, LAT_W, generator=g).pin_memory()
+    img = torch.randn(1, 4, LAT_H, LAT_W, generator=g)
+    image_latents = torch.cat([torch.zeros_like(img), img]).pin_memory()
+    emb = torch.randn(1, 1, cfg.cross_attention_dim, generator=g)
+    image_embeddings = torch.cat([torch.zeros_like(emb), emb]).pin_memory()
+    cond = _synthetic_condition(FRAMES, H, W).pin_memory()   # [F,3,H,W] in [-1,1]
+
+    def call_pipeline():
+        out = pipe(None, cond, height=H, width=W, num_frames=FRAMES, num_inference_steps=SAMPLING_STEPS,
+                   latents=lat_unit, output_type="latent", image_embeddings=image_embeddings, image_latents=image_latents)
+        return out.frames.to("cpu")
+
+    # first call builds the plans, stages everything, captures the CUDA graph of one step
+    lat_final = call_pipeline()
+    if not torch.isfinite(lat_final).all():
+        raise SystemExit("bench.py: non-finite latents")
+    eng = pipe.engine_for(FRAMES, LAT_H, LAT_W, (H, W))
+    assert eng.graph is not None
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps/s ----------------------------------------------------------------------------------
+    def run_steps(n, start_at=0):
+        for i in range(n):
+            if (start_at + i) % SAMPLING_STEPS == 0:
+                eng.reset()
+            eng.graph.replay()
+
+    run_steps(args.warmup)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_steps(args.steps, start_at=args.warmup)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public API with host buffers --------------------------------------------------------
+    n_calls = max(1, round(args.steps / SAMPLING_STEPS))
+    call_pipeline()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(n_calls):
+        call_pipeline()
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([max(e0.elapsed_time(e1) / 1e3, wall)], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * n_calls * SAMPLING_STEPS / e2e_s
+    h2d = sum(x.numel() * x.element_size() for x in (cond, lat_unit, image_latents, image_embeddings)) + 26 * 4 + 2 * 3 * 4
+    d2h = lat_final.numel() * lat_final.element_size()
+
+    line = None
+    if rank == 0:
+        # ---- per-kernel-class CUDA-event times of one step (eager replay of the same launch list) -------------------
+        eng.reset()
+        classes = time_op_classes(eng.step_ops, stream)
+        peaks = _peaks()
+        gem = classes["gemm"]
+        gemm_tf = gem["flops"] / (gem["ms"] * 1e-3) / 1e12
+        total_ms = sum(c["ms"] for c in classes.values())
+        ess, _ = step_flops(cfg, frames=FRAMES, h=LAT_H, w=LAT_W, essential=True)
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (linear / implicit-GEMM conv, all launches of one step)",
+                    "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"],
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
+                    "launches_per_step": int(round(gem["launches"])), "avg_launch_ms": gem["ms"] / gem["launches"],
+                    "share_of_step": gem["ms"] / total_ms, "traffic": None}
+        per_class = {}
+        for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
+            e = {"ms": round(c["ms"], 4), "launches": int(round(c["launches"])), "share": round(c["ms"] / total_ms, 4)}
+            if c["flops"] > 0:
+                e["tflops"] = round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 1)
+            if c["bytes"] > 0:
+                e["alg_gbs"] = round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)
+                e["frac_hbm"] = round(e["alg_gbs"] / peaks["hbm"], 3)
+            per_class[k] = e
+        step_tf = ess / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "weights": "random-init SVD-shaped UNet 1524.6M + ControlNetSDV 682.0M (zero-convs re-randomised)",
+                       "sharding": "one video (CFG pair) per GPU, no data-path collective" if world > 1 else "single GPU",
+                       "l2": "per-step working set (4.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush",
+                       "videos_per_min": value * 60.0 / SAMPLING_STEPS},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / SAMPLING_STEPS,
+                    "d2h_bytes_per_step": d2h / SAMPLING_STEPS, "calls": n_calls,
+                    "api": "StableVideoDiffusionPipelineControlNet.__call__(host tensors, output_type='latent') + .cpu()",
+                    "videos_per_min": e2e_value * 60.0 / SAMPLING_STEPS},
+            "gpu_launches": int(eng.launches_per_step * args.steps + 3 * ((args.steps + SAMPLING_STEPS - 1) // SAMPLING_STEPS)),
+            "roofline": roofline,
+            "step_roofline": {"essential_tflop_per_step": ess / 1e12, "achieved_tflops": step_tf,
+                              "frac_of_sustained_peak": step_tf / peaks["tf_sustained"]},
+            "kernel_classes": per_class,
+            "lib_launch_count": int(_lib.lib().pt_launch_count()),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, t_step, cores, sample = cpu_oracle_steps_per_sec(1, 1, budget_s=40.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

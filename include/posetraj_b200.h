@@ -141,7 +141,8 @@ typedef struct PtGroupNormArgs {
   int32_t c0, c1, ld0, ld1;
   int32_t rows_per_stat;    /* rows sharing statistics: H*W (per frame) or F*H*W (TemporalResnetBlock) */
   int32_t num_stat;         /* number of statistics groups: B*F or B */
-  void* stats;              /* workspace: double [num_stat, 32, 2] */
+  void* stats;              /* workspace of pt_groupnorm_workspace_bytes(): per-CTA fp64 partial sums, reduced in a
+                             * fixed order (no atomics: two runs of the same input are bit-identical) */
   const float* gamma;       /* [c0+c1] */
   const float* beta;
   float eps;
@@ -152,6 +153,8 @@ typedef struct PtGroupNormArgs {
   int32_t H, W;
 } PtGroupNormArgs;
 int pt_groupnorm(const PtGroupNormArgs* a, void* stream);
+/* bytes of PtGroupNormArgs.stats needed for this problem (-1 on bad arguments) */
+int64_t pt_groupnorm_workspace_bytes(int32_t num_stat, int32_t rows_per_stat, int32_t channels);
 
 /* LayerNorm (BasicTransformerBlock / TemporalBasicTransformerBlock norms, eps 1e-5).  Optional fused
  * `hidden_states + emb` of models/modified_svd.py:196-197: addvec[frame] is added first and the sum is also

@@ -132,6 +132,7 @@ _SIGNATURES = {
     "pt_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_gemm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_groupnorm_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "pt_layernorm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_attention_spatial": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_attention_temporal": (C.c_int, [C.c_void_p, C.c_void_p]),

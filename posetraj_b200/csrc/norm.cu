@@ -17,7 +17,9 @@
 namespace pt {
 
 // ---------------------------------------------------------------------------------------------------------
-// GroupNorm statistics: sum / sum of squares per (stat group s, norm group g) accumulated in fp64 atomics
+// GroupNorm statistics: per-CTA partial sum / sum of squares per (stat group s, split, norm group g).
+// Deterministic on purpose: no atomics anywhere, every reduction runs in a fixed order, so two runs of the same
+// step are bit-identical (a 1-ulp wobble in a mean flips bf16 roundings downstream and decorrelates whole runs).
 // ---------------------------------------------------------------------------------------------------------
 struct GnStatsParams {
   const bf16* x0;
@@ -26,11 +28,11 @@ struct GnStatsParams {
   int rows_per_stat;  // rows sharing statistics (H*W, or F*H*W for the temporal 5-D norm)
   int num_stat;       // number of statistics groups (B*F or B)
   int splits;         // CTAs per statistics group
-  double* stats;      // [num_stat, 32, 2], zeroed by the launcher
+  double* partials;   // [num_stat, splits, 32, 2]
 };
 
 __global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
-  __shared__ float s_sum[32], s_sq[32];
+  extern __shared__ float s_red[];  // [rpar][C] sums, [rpar][C] squares, then [C] + [C] per-channel totals
   const int C = p.c0 + p.c1;
   const int cvec = C >> 3;            // threads along channels (8 channels each)
   const int rpar = blockDim.x / cvec; // row lanes
@@ -38,11 +40,6 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
   const int tr = threadIdx.x / cvec;
   const int stat = blockIdx.x / p.splits;
   const int split = blockIdx.x - stat * p.splits;
-  if (threadIdx.x < 32) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
   const int c = tc * 8;
   const bf16* src;
   int ld;
@@ -59,30 +56,47 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-  if (tr < rpar) {
-    const size_t base = (size_t)stat * p.rows_per_stat;
-    for (int r = r_begin + tr; r < r_end; r += rpar) {
-      const uint4 u = ldg_nc_u4(src + (base + r) * ld);
-      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-      const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sum[j] += v[j];
-        sq[j] = fmaf(v[j], v[j], sq[j]);
-      }
-    }
-    const int cg = C >> 5;
+  const size_t base = (size_t)stat * p.rows_per_stat;
+  for (int r = r_begin + tr; r < r_end; r += rpar) {
+    const uint4 u = ldg_nc_u4(src + (base + r) * ld);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cg;
-      atomicAdd(&s_sum[g], sum[j]);
-      atomicAdd(&s_sq[g], sq[j]);
+      sum[j] += v[j];
+      sq[j] = fmaf(v[j], v[j], sq[j]);
     }
+  }
+  float* s_sum = s_red;
+  float* s_sq = s_red + (size_t)rpar * C;
+  float* c_sum = s_sq + (size_t)rpar * C;
+  float* c_sq = c_sum + C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_sum[tr * C + c + j] = sum[j];
+    s_sq[tr * C + c + j] = sq[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < rpar; ++i) {
+      a += s_sum[i * C + ch];
+      b += s_sq[i * C + ch];
+    }
+    c_sum[ch] = a;
+    c_sq[ch] = b;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    atomicAdd(&p.stats[((size_t)stat * 32 + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
-    atomicAdd(&p.stats[((size_t)stat * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+    const int cg = C >> 5;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < cg; ++i) {
+      a += (double)c_sum[threadIdx.x * cg + i];
+      b += (double)c_sq[threadIdx.x * cg + i];
+    }
+    double* dst = p.partials + (((size_t)stat * p.splits + split) * 32 + threadIdx.x) * 2;
+    dst[0] = a;
+    dst[1] = b;
   }
 }
 
@@ -94,7 +108,7 @@ struct GnApplyParams {
   const bf16* x1;
   int c0, c1, ld0, ld1;
   int rows_per_stat, num_stat, splits;
-  const double* stats;
+  const double* partials;  // [num_stat, splits, 32, 2] from gn_stats_kernel
   const float* gamma;
   const float* beta;
   float eps;
@@ -107,22 +121,34 @@ struct GnApplyParams {
 
 __global__ void __launch_bounds__(512) gn_apply_kernel(const GnApplyParams p) {
   extern __shared__ float s_ab[];  // [C] scale, [C] shift
+  __shared__ float s_mean[32], s_rstd[32];
   const int C = p.c0 + p.c1;
   float* s_scale = s_ab;
   float* s_shift = s_ab + C;
   const int stat = blockIdx.x / p.splits;
   const int split = blockIdx.x - stat * p.splits;
   const int cg = C >> 5;
-  const double cnt = (double)p.rows_per_stat * cg;
+  if (threadIdx.x < 32) {
+    // fixed-order fp64 sum of the per-CTA partials: identical in every CTA of this statistics group
+    const double* src = p.partials + ((size_t)stat * p.splits * 32 + threadIdx.x) * 2;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < p.splits; ++i) {
+      a += src[(size_t)i * 64];
+      b += src[(size_t)i * 64 + 1];
+    }
+    const double cnt = (double)p.rows_per_stat * cg;
+    const double m = a / cnt;
+    double var = b / cnt - m * m;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = (float)m;
+    s_rstd[threadIdx.x] = rsqrtf((float)var + p.eps);
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cg;
-    const double m = p.stats[((size_t)stat * 32 + g) * 2] / cnt;
-    double var = p.stats[((size_t)stat * 32 + g) * 2 + 1] / cnt - m * m;
-    if (var < 0) var = 0;
-    const float rstd = rsqrtf((float)var + p.eps);
-    const float ga = p.gamma[c] * rstd;
+    const float ga = p.gamma[c] * s_rstd[g];
     s_scale[c] = ga;
-    s_shift[c] = p.beta[c] - (float)m * ga;
+    s_shift[c] = p.beta[c] - s_mean[g] * ga;
   }
   __syncthreads();
 
@@ -294,6 +320,21 @@ static int gn_block_threads(int C) {
   return cvec * rpar;
 }
 
+static int gn_splits(int num_stat, int rows_per_stat, int C) {
+  const int threads = gn_block_threads(C);
+  int splits = (pt_num_sms() * 4 + num_stat - 1) / num_stat;
+  const int rpar = threads / (C / 8);
+  const int max_splits = (rows_per_stat + rpar * 4 - 1) / (rpar * 4);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+extern "C" int64_t pt_groupnorm_workspace_bytes(int32_t num_stat, int32_t rows_per_stat, int32_t channels) {
+  if (num_stat < 1 || rows_per_stat < 1 || channels < 32 || channels % 8) return -1;
+  return (int64_t)sizeof(double) * 64 * num_stat * gn_splits(num_stat, rows_per_stat, channels);
+}
+
 extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   PT_CHECK_ARG(a != nullptr && a->x0 != nullptr && a->out != nullptr && a->stats != nullptr && a->gamma && a->beta,
                "pt_groupnorm: null argument");
@@ -305,14 +346,9 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   PT_CHECK_ARG(!a->halo || (a->H > 0 && a->W > 0 && a->rows_per_stat % (a->H * a->W) == 0),
                "pt_groupnorm: halo output needs H*W dividing rows_per_stat");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(a->stats, 0, sizeof(double) * 64 * (size_t)a->num_stat, st);
-  if (e != cudaSuccess) return pt_fail(e, "pt_groupnorm: memset");
   const int threads = gn_block_threads(C);
-  int splits = (pt_num_sms() * 4 + a->num_stat - 1) / a->num_stat;
+  const int splits = gn_splits(a->num_stat, a->rows_per_stat, C);
   const int rpar = threads / (C / 8);
-  const int max_splits = (a->rows_per_stat + rpar * 4 - 1) / (rpar * 4);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
 
   GnStatsParams s;
   s.x0 = reinterpret_cast<const bf16*>(a->x0);
@@ -321,15 +357,16 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   s.rows_per_stat = a->rows_per_stat;
   s.num_stat = a->num_stat;
   s.splits = splits;
-  s.stats = reinterpret_cast<double*>(a->stats);
-  gn_stats_kernel<<<a->num_stat * splits, threads, 0, st>>>(s);
+  s.partials = reinterpret_cast<double*>(a->stats);
+  const size_t stats_smem = sizeof(float) * ((size_t)2 * rpar * C + 2 * C);
+  gn_stats_kernel<<<a->num_stat * splits, threads, stats_smem, st>>>(s);
   int rc = pt_launched("pt_groupnorm(stats)");
   if (rc) return rc;
 
   GnApplyParams p;
   p.x0 = s.x0; p.x1 = s.x1; p.c0 = a->c0; p.c1 = a->c1; p.ld0 = a->ld0; p.ld1 = a->ld1;
   p.rows_per_stat = a->rows_per_stat; p.num_stat = a->num_stat; p.splits = splits;
-  p.stats = s.stats;
+  p.partials = s.partials;
   p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.out_ld = a->out_ld;

@@ -161,7 +161,8 @@ class NetPlan:
         self.time_ids = torch.zeros(batch * 3, device=device, dtype=F32)
         self.t_buf = torch.zeros(batch, device=device, dtype=F32)
         self.sigmas, self.step_index = sigmas, step_index
-        self.stats = torch.zeros(self.n * 64, device=device, dtype=torch.float64)
+        # GroupNorm partial-sum workspace: at most 4 CTAs per SM plus one per statistics group
+        self.stats = torch.zeros((2 * self.n + 4 * ops.NUM_SMS + 64) * 64, device=device, dtype=torch.float64)
         self.level_hw = [(height >> i, width >> i) for i in range(len(ch))]
 
         # ---- time embedding ops (first in every step) ---------------------------------------------------
@@ -431,7 +432,7 @@ class NetPlan:
         kw = on_skip(0)
         x = self._gemm(self.x_in, w.conv3("conv_in.weight", self.cin_pad), ch[0], taps=ops.conv3x3_taps(hw[1]),
                        bias=w.f32("conv_in.bias"), res1=conv_in_res, halo=hw, out_rows=self.n * hw[0] * hw[1],
-                       name="conv_in", **kw)
+                       name="conv_in", alg_k=9 * cfg.in_channels, **kw)
         on_skip.done(0, x)
         idx = 1
         for i in range(n):

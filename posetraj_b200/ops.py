@@ -62,7 +62,7 @@ class Gemm:
                  res2: Optional[torch.Tensor] = None, res2_scale: float = 1.0,
                  out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_scale: float = 0.0,
                  halo: Optional[tuple] = None, ostride: int = 1, out_halo: bool = False,
-                 act_silu: bool = False, name: str = "gemm"):
+                 act_silu: bool = False, name: str = "gemm", alg_k: Optional[int] = None):
         assert a0.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
         assert a0.dim() == 2 and w.dim() == 2 and a0.stride(1) == 1 and w.stride(1) == 1
         self.name = name
@@ -163,6 +163,11 @@ class Gemm:
             a.map_mode = 0
             assert out_rows == rows_total
         a.act_silu = 1 if act_silu else 0
+        # algorithmic FLOPs (bench.py roofline): true output pixels x true (un-padded) K
+        valid_rows = out_rows if not (halo is not None and out_halo) else n_img * a.oH * a.oW
+        self.kind = "gemm"
+        self.alg_flops = 2.0 * valid_rows * n_out * (2 if geglu else 1) * (alg_k if alg_k is not None else ntaps * (k0 + k1))
+        self.alg_bytes = 0.0
         self.args = a
         self._keep = (a0, a1, w, out, bias, rowvec, res1, res2, out2, aux)
         self._argp = C.addressof(a)
@@ -206,6 +211,11 @@ class CfgEuler:
             a.next_padded = 1 if next_padded else 0
         a.mode = mode
         a.single_pred = 1 if single_pred else 0
+        self.kind = "cfg_euler"
+        self.name = "pt_cfg_euler_step"
+        self.alg_flops = 0.0
+        # F*C*H*W*(2*2 + 4 + 4) B, plus the fused bf16 write of the next model input (2 rows x 2C ch)
+        self.alg_bytes = F_ * Cc * H * W * (2 * 2 + 4 + 4.0) + (2 * F_ * H * W * 2 * Cc * 2.0 if next_in is not None else 0.0)
         self.args = a
         self._keep = (noise_pred, latents, guidance, sigmas, step_index, next_in, image_latents)
         self._argp = C.addressof(a)
@@ -217,6 +227,9 @@ class CfgEuler:
 class _Op:
     """Base: holds a ctypes args struct + the C entry point; launch() is one ctypes call."""
     fn_name = ""
+    kind = "misc"
+    alg_flops = 0.0   # algorithmic FLOPs / bytes of one launch (SURVEY.md Appendix F), for bench.py's roofline
+    alg_bytes = 0.0
 
     def _finish(self, args, keep, name=None):
         self.args = args
@@ -248,7 +261,8 @@ class GroupNorm(_Op):
         assert gamma.numel() == a.c0 + a.c1
         a.rows_per_stat = rows_per_stat
         a.num_stat = rows // rows_per_stat
-        assert stats.numel() >= a.num_stat * 64
+        need = _lib.lib().pt_groupnorm_workspace_bytes(a.num_stat, rows_per_stat, a.c0 + a.c1)
+        assert need > 0 and stats.numel() * 8 >= need, (need, stats.numel())
         a.stats = stats.data_ptr()
         a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
         a.eps = eps
@@ -260,6 +274,8 @@ class GroupNorm(_Op):
             assert out.shape[0] == n_img * (halo[0] + 1) * (halo[1] + 1)
         else:
             assert out.shape[0] == rows
+        self.kind = "groupnorm"
+        self.alg_bytes = 2.0 * rows * (a.c0 + a.c1) * 2
         self._finish(a, (x0, x1, out, gamma, beta, stats), name)
 
 
@@ -279,6 +295,8 @@ class LayerNorm(_Op):
             if sum_out is not None:
                 assert sum_out.stride(0) == out.stride(0) and sum_out.dtype == torch.bfloat16
                 a.sum_out = sum_out.data_ptr()
+        self.kind = "layernorm"
+        self.alg_bytes = (3.0 if sum_out is not None else 2.0) * x.shape[0] * x.shape[1] * 2
         self._finish(a, (x, out, gamma, beta, addvec, sum_out), name)
 
 
@@ -296,6 +314,9 @@ class AttnSpatial(_Op):
         a.tmap_qkv = C.addressof(self.tm)
         a.out, a.out_ld = out.data_ptr(), out.stride(0)
         a.S, a.heads, a.C, a.n_img = S, heads, Cc, n_img
+        self.kind = "attn_spatial"
+        self.alg_flops = 4.0 * S * S * 64 * heads * n_img
+        self.alg_bytes = 4.0 * rows * Cc * 2
         self._finish(a, (qkv, out), name)
 
 
@@ -309,6 +330,9 @@ class AttnTemporal(_Op):
         a.qkv, a.ld = qkv.data_ptr(), qkv.stride(0)
         a.out, a.out_ld = out.data_ptr(), out.stride(0)
         a.B, a.F, a.HW, a.heads, a.C = batch, frames, hw, heads, qkv.shape[1] // 3
+        self.kind = "attn_temporal"
+        self.alg_flops = 4.0 * frames * frames * 64 * heads * batch * hw
+        self.alg_bytes = 4.0 * qkv.shape[0] * a.C * 2
         self._finish(a, (qkv, out), name)
 
 
@@ -355,6 +379,8 @@ class Upsample2x(_Op):
         a.n, a.H, a.W, a.C, a.halo, a.scale = n, H, W, x.shape[1], int(halo), scale
         exp_rows = n * (scale * H + 1) * (scale * W + 1) if halo else n * scale * scale * H * W
         assert out.shape[0] == exp_rows
+        self.kind = "upsample"
+        self.alg_bytes = (x.shape[0] + out.shape[0]) * x.shape[1] * 2.0
         self._finish(a, (x, out), name)
 
 
@@ -400,6 +426,7 @@ class StepAdvance:
         assert step_index.dtype == torch.int32
         self.step_index = step_index
         self.name = "pt_step_advance"
+        self.kind, self.alg_flops, self.alg_bytes = "misc", 0.0, 0.0
 
     def launch(self, stream_ptr: int) -> None:
         _lib.check(_lib.lib().pt_step_advance(self.step_index.data_ptr(), stream_ptr), self.name)

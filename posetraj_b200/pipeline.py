@@ -85,6 +85,13 @@ class DenoiseEngine:
         self.controlnet.stage_condition(self.cplan, controlnet_condition, camera_cond, None, sp)
         self.cplan.set_conditioning_scale(cond_scale)
         self.prepare_op.launch(sp)
+        self._latents0 = self.latents.clone()
+
+    def reset(self) -> None:
+        """Re-arm the loop on the inputs staged by the last load(): device-side only (3 tiny launches)."""
+        self.latents.copy_(self._latents0)
+        self.step_index.zero_()
+        self.prepare_op.launch(torch.cuda.current_stream().cuda_stream)
 
     def step(self) -> None:
         """One denoise step (all kernels of ControlNet + UNet + CFG/Euler)."""

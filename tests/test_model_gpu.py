@@ -9,7 +9,16 @@ import torch
 from parity_util import make_small_inputs, oracle_pair, rel_l2, small_cfg
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-2
+TOL = 1e-2       # north_star: per-step noise prediction, relative L2, bf16
+TOL_RES = 2e-2   # ControlNet residuals are deeper intermediate tensors; the reference's own bf16 path (torch bf16 of
+                 # the oracle) is 4e-3 .. 2e-2 away from fp32 on exactly these tensors (tests/golden/README.md)
+
+
+def _record(name, value):
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_errors.jsonl", "a") as f:
+        f.write(json.dumps({"test": name, "value": value}) + "\n")
 
 
 def to_dev(d, dev):
@@ -49,13 +58,15 @@ def test_single_step_parity(small_setup, cuda_dev, sigma, use_cam):
                      camera_cond=None if cam is None else d["camera_cond"], conditioning_scale=0.8, return_dict=False)
     torch.cuda.synchronize()
     errs = [rel_l2(a, b) for a, b in zip(down + [mid], o_down + [o_mid])]
-    assert max(errs) < TOL, errs
+    _record(f"residuals sigma={sigma} cam={use_cam}", errs)
+    assert max(errs) < TOL_RES, errs
     assert all(a.shape == b.shape for a, b in zip(down + [mid], o_down + [o_mid]))
     pred = unet(xd, t.to(cuda_dev), d["image_embeddings"], down_block_additional_residuals=down,
                 mid_block_additional_residual=mid, added_time_ids=d["added_time_ids"], return_dict=False)[0]
     torch.cuda.synchronize()
     assert pred.shape == o_pred.shape
     e = rel_l2(pred, o_pred)
+    _record(f"noise_pred sigma={sigma} cam={use_cam}", e)
     assert e < TOL, e
 
 
@@ -77,6 +88,7 @@ def test_external_residual_tensors(small_setup, cuda_dev):
                 down_block_additional_residuals=[r.to(cuda_dev) for r in o_down],
                 mid_block_additional_residual=o_mid.to(cuda_dev), added_time_ids=d["added_time_ids"]).sample
     torch.cuda.synchronize()
+    _record("noise_pred external residuals", rel_l2(pred, o_pred))
     assert rel_l2(pred, o_pred) < TOL
 
 
@@ -111,6 +123,7 @@ def test_pipeline_three_steps(small_setup, cuda_dev):
                image_embeddings=inp["image_embeddings"].to(cuda_dev), image_latents=inp["image_latents"].to(cuda_dev)).frames
     torch.cuda.synchronize()
     assert got.shape == want.shape
+    _record("latents after 4 steps", rel_l2(got, want))
     assert rel_l2(got, want) < TOL
     # eager replay (callback path) must agree with the graph path
     got2 = pipe(None, inp["controlnet_condition"][0].to(cuda_dev), height=h * 8, width=w * 8, num_frames=cfg.num_frames,
