@@ -29,6 +29,20 @@ out = pipe(None, cond, height=h * 8, width=w * 8, num_frames=F, num_inference_st
 eng = pipe.engine_for(F, h, w, (h * 8, w * 8))
 eng.reset()
 torch.cuda.synchronize()
+# launch-ordered op list (GroupNorm = 2 kernels) so the ncu launch list can be joined with layer names offline
+import json
+oplist = []
+for op in eng.step_ops:
+    d = {"name": op.name, "kind": op.kind, "flops": op.alg_flops, "bytes": op.alg_bytes,
+         "kernels": 2 if op.kind == "groupnorm" else 1}
+    if op.kind == "gemm":
+        a = op.args
+        d.update(block_n=a.block_n, n_out=a.n_out, rows=a.rows_per_batch * a.batches, taps=a.num_taps,
+                 k=(a.k0_chunks + a.k1_chunks) * 64, geglu=a.geglu)
+    oplist.append(d)
+os.makedirs("gpurun_out", exist_ok=True)
+with open(os.environ.get("PT_OPLIST", "gpurun_out/oplist.json"), "w") as f:
+    json.dump(oplist, f)
 torch.cuda.profiler.start()
 NetPlan.run(eng.step_ops, torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
