@@ -1,2 +1,6 @@
-"""posetraj_b200 — B200-native (sm_100a) implementation of PoseTraj's denoising hot path."""
-__version__ = "0.1.0"
+"""posetraj_b200 — B200-native (sm_100a) implementation of PoseTraj's denoising hot path behind the reference's
+own Python signatures.  See DESIGN.md; the compute lives in libposetraj_b200.so (csrc/, C ABI in include/)."""
+from .config import SVDConfig  # noqa: F401
+from .models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel  # noqa: F401
+from .pipeline import StableVideoDiffusionPipelineControlNet  # noqa: F401
+from .scheduler import EulerDiscreteScheduler  # noqa: F401
