@@ -57,110 +57,199 @@ struct alignas(64) TmapParam {
   uint64_t opaque[16];
 };
 
-PT_DEVICE void store8(int out_dtype, void* base, size_t off, const float* v, int nvalid) {
-  if (out_dtype == PT_DT_BF16) {
-    bf16* o = reinterpret_cast<bf16*>(base) + off;
-    if (nvalid == 8) {
-      uint4 u;
-      u.x = pack_bf16x2(v[0], v[1]);
-      u.y = pack_bf16x2(v[2], v[3]);
-      u.z = pack_bf16x2(v[4], v[5]);
-      u.w = pack_bf16x2(v[6], v[7]);
-      stg_u4(o, u);
-    } else {
-      for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16(v[j]);
-    }
-  } else {
-    float* o = reinterpret_cast<float*>(base) + off;
-    if (nvalid == 8) {
-      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-      for (int j = 0; j < nvalid; ++j) o[j] = v[j];
-    }
-  }
-}
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue building blocks.
+//
+// tcgen05.ld hands every thread ONE accumulator row (32 consecutive fp32 columns).  Doing the epilogue in that
+// layout makes every global access touch 32 different rows per instruction.  Instead each epilogue warp transposes
+// its 32x32 chunk through a private, XOR-swizzled smem tile so that afterwards a lane owns 8 consecutive columns
+// of a row and 4 neighbouring lanes cover 64 contiguous bytes: residual loads and output stores are coalesced
+// row segments, and each lane only needs 16 bytes per operand in flight.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kEpiWarps = 8;
+constexpr int kStageWarpBytes = 32 * 32 * 4;   // fp32 32x32 (the GEGLU path stages bf16 and uses half of it)
 
-// 8 bf16 of a residual-like operand -> raw registers (zero when absent); vector path needs 16-byte alignment,
-// which holds whenever ld % 8 == 0 and n % 8 == 0 (checked on the host for the vector case).
-PT_DEVICE uint4 load8_raw(const bf16* src, int nvalid) {
-  if (nvalid == 8) return ldg_u4(src);
-  uint32_t w[4] = {0u, 0u, 0u, 0u};
-  for (int j = 0; j < nvalid; ++j) {
-    const uint32_t b = (uint32_t)__bfloat16_as_ushort(src[j]);
-    w[j >> 1] |= (j & 1) ? (b << 16) : b;
-  }
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-PT_DEVICE void fma8(float* v, uint4 u, float s) {
+PT_DEVICE void unpack8(uint4 u, float* f) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-  v[0] = fmaf(s, a.x, v[0]); v[1] = fmaf(s, a.y, v[1]); v[2] = fmaf(s, b.x, v[2]); v[3] = fmaf(s, b.y, v[3]);
-  v[4] = fmaf(s, c.x, v[4]); v[5] = fmaf(s, c.y, v[5]); v[6] = fmaf(s, d.x, v[6]); v[7] = fmaf(s, d.y, v[7]);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-// Operands of one 32-column chunk of one accumulator row, fetched BEFORE the TMEM wait so that their
-// global-load latency overlaps the tcgen05.ld and is paid once per chunk rather than once per 8 columns.
-struct ChunkOperands {
-  uint4 r1[4], r2[4], ax[4];
-  float rv[32];
+PT_DEVICE uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  return u;
+}
+
+PT_DEVICE float ex2_approx(float x);
+PT_DEVICE float rcp_approx(float x);
+
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, below fp32 GELU noise; two MUFU + 7 FMA instead of erff's
+// ~30 instructions) — the GEGLU epilogue evaluates 128 x block_n/2 of these per tile and is otherwise ALU-bound.
+PT_DEVICE float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = poly * t * ex2_approx(-z * z * 1.4426950408889634f);  // 1 - erf(z)
+  const float erf_abs = 1.0f - e;
+  const float erf_x = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_x);
+}
+
+// slow path of the store side: fewer than 8 valid columns in this lane's segment (only conv_out: n_out = 4)
+__device__ __noinline__ void epilogue_tail(const GemmParams& p, const float* acc, const float* sb_seg, int ncol,
+                                           int nvalid, long long orow, int grp) {
+  for (int j = 0; j < nvalid; ++j) {
+    float v = acc[j] + sb_seg[j];
+    if (p.rowvec_mode != 0) v += __ldg(p.rowvec + (size_t)grp * p.rowvec_ld + ncol + j);
+    v *= p.acc_scale;
+    if (p.act_silu) v = silu_f(v);
+    if (p.res1 != nullptr) v = fmaf(p.res1_scale, __bfloat162float(p.res1[(size_t)orow * p.res_ld + ncol + j]), v);
+    if (p.res2 != nullptr) v = fmaf(p.res2_scale, __bfloat162float(p.res2[(size_t)orow * p.res_ld + ncol + j]), v);
+    const size_t off = (size_t)orow * p.out_ld + ncol + j;
+    if (p.out_dtype == PT_DT_BF16) reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(p.out)[off] = v;
+    if (p.out2 != nullptr) {
+      v = fmaf(p.aux_scale, __bfloat162float(p.aux[off]), v);
+      if (p.out_dtype == PT_DT_BF16) reinterpret_cast<bf16*>(p.out2)[off] = __float2bfloat16(v);
+      else reinterpret_cast<float*>(p.out2)[off] = v;
+    }
+  }
+}
+
+struct EpiRows {
+  long long out_off[4];  // element offset of the 4 output rows this lane finishes
+  long long res_off[4];
+  int grp[4];
+  uint32_t vmask;
 };
 
-PT_DEVICE void prefetch_chunk(const GemmParams& p, ChunkOperands& o, int n, long long orow, int grp, bool valid) {
-#pragma unroll
-  for (int g8 = 0; g8 < 4; ++g8) {
-    const int nn = n + g8 * 8;
-    const int nvalid = valid ? max(0, min(8, p.n_out - nn)) : 0;
-    o.r1[g8] = (p.res1 != nullptr && nvalid > 0) ? load8_raw(p.res1 + (size_t)orow * p.res_ld + nn, nvalid) : make_uint4(0, 0, 0, 0);
-    o.r2[g8] = (p.res2 != nullptr && nvalid > 0) ? load8_raw(p.res2 + (size_t)orow * p.res_ld + nn, nvalid) : make_uint4(0, 0, 0, 0);
-    o.ax[g8] = (p.out2 != nullptr && nvalid > 0) ? load8_raw(p.aux + (size_t)orow * p.out_ld + nn, nvalid) : make_uint4(0, 0, 0, 0);
-  }
-  if (p.rowvec_mode != 0 && valid) {
-    const float* rv = p.rowvec + (size_t)grp * p.rowvec_ld + n;
-    if (n + 32 <= p.n_out) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(rv) + j);
-        o.rv[4 * j] = t.x; o.rv[4 * j + 1] = t.y; o.rv[4 * j + 2] = t.z; o.rv[4 * j + 3] = t.w;
+PT_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+PT_DEVICE float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Lean epilogue of one accumulator tile for bf16 outputs (see kEpiFast).  val = acc_scale*(acc + bias + rowvec) +
+// s1*res1 + s2*res2 ; out = val ; out2 = val + aux_scale*aux.
+template <bool kRowvec, bool kRes, bool kOut2>
+PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_acc, uint32_t stage_u32, int n0,
+                             int chunks, int hsel, int lane, uint64_t* tempty) {
+  const int sub_row = lane >> 2;
+  const int seg = lane & 3;
+  bf16* out = reinterpret_cast<bf16*>(p.out);
+  bf16* out2 = reinterpret_cast<bf16*>(p.out2);
+  const bool has_res2 = kRes && p.res2 != nullptr;
+  const bool has_res1 = kRes && p.res1 != nullptr;
+  // Operands are fetched one chunk AHEAD (double-buffered in registers): the global-load latency of chunk c+2
+  // overlaps the TMEM read, transpose and math of chunk c.  (res2 — rare — is fetched in the chunk that uses it.)
+  uint4 r1n[4], axn[4];
+  float4 b0n = make_float4(0.f, 0.f, 0.f, 0.f), b1n = b0n;
+  auto fetch = [&](int c, uint4 (&r1x)[4], uint4 (&axx)[4], float4& b0x, float4& b1x) {
+    const int ncol = n0 + c * 32 + seg * 8;
+    if (c < chunks && ncol < p.n_out) {
+      if (p.bias != nullptr) {
+        b0x = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
+        b1x = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + 1);
       }
-    } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) o.rv[j] = (n + j < p.n_out) ? __ldg(rv + j) : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (kRes) r1x[i] = has_res1 ? ldg_nc_u4(p.res1 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
+        if constexpr (kOut2) axx[i] = ldg_nc_u4(p.aux + R.out_off[i] + ncol);
+      }
     }
-  } else {
+  };
+  fetch(hsel, r1n, axn, b0n, b1n);
+  for (int c = hsel; c < chunks; c += 2) {
+    const int ncol = n0 + c * 32 + seg * 8;
+    const bool act = ncol < p.n_out;  // n_out % 8 == 0 on this path: a segment is full or empty
+    uint32_t v[32];
+    tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
+    uint4 r1[4], r2[4], ax[4];
+    const float4 b0 = b0n, b1 = b1n;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o.rv[j] = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (kRes) r1[i] = r1n[i];
+      if constexpr (kOut2) ax[i] = axn[i];
+      if constexpr (kRes) r2[i] = (act && has_res2) ? ldg_nc_u4(p.res2 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
+    }
+    fetch(c + 2, r1n, axn, b0n, b1n);
+    tmem_wait_ld();
+    if (c + 2 >= chunks) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+    __syncwarp();  // the previous chunk's transposed reads are done
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t addr = stage_u32 + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                   "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = i * 8 + sub_row;
+      const uint32_t a0 = stage_u32 + (uint32_t)rr * 128u + (uint32_t)(((2 * seg) ^ (rr & 7)) << 4);
+      const uint32_t a1 = stage_u32 + (uint32_t)rr * 128u + (uint32_t)(((2 * seg + 1) ^ (rr & 7)) << 4);
+      float f[8];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a0));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(a1));
+      if (!act || !((R.vmask >> i) & 1u)) continue;
+      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+      f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      if constexpr (kRowvec) {
+        const float4* rv = reinterpret_cast<const float4*>(p.rowvec + (size_t)R.grp[i] * p.rowvec_ld + ncol);
+        const float4 v0 = __ldg(rv), v1 = __ldg(rv + 1);
+        f[0] += v0.x; f[1] += v0.y; f[2] += v0.z; f[3] += v0.w;
+        f[4] += v1.x; f[5] += v1.y; f[6] += v1.z; f[7] += v1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= p.acc_scale;
+      if constexpr (kRes) {
+        float r[8];
+        unpack8(r1[i], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(p.res1_scale, r[j], f[j]);
+        if (has_res2) {
+          unpack8(r2[i], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(p.res2_scale, r[j], f[j]);
+        }
+      }
+      stg_u4(out + R.out_off[i] + ncol, pack8(f));
+      if constexpr (kOut2) {
+        float r[8];
+        unpack8(ax[i], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(p.aux_scale, r[j], f[j]);
+        stg_u4(out2 + R.out_off[i] + ncol, pack8(f));
+      }
+    }
   }
 }
 
-// f[32] already holds acc (+bias, GEGLU applied); finish and store the chunk.
-PT_DEVICE void finish_chunk(const GemmParams& p, float* f, const ChunkOperands& o, int n, long long orow) {
-#pragma unroll
-  for (int g8 = 0; g8 < 4; ++g8) {
-    const int nn = n + g8 * 8;
-    const int nvalid = min(8, p.n_out - nn);
-    if (nvalid <= 0) break;
-    float* v = f + g8 * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (v[j] + o.rv[g8 * 8 + j]) * p.acc_scale;
-    if (p.act_silu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-    }
-    if (p.res1 != nullptr) fma8(v, o.r1[g8], p.res1_scale);
-    if (p.res2 != nullptr) fma8(v, o.r2[g8], p.res2_scale);
-    store8(p.out_dtype, p.out, (size_t)orow * p.out_ld + nn, v, nvalid);
-    if (p.out2 != nullptr) {
-      fma8(v, o.ax[g8], p.aux_scale);
-      store8(p.out_dtype, p.out2, (size_t)orow * p.out_ld + nn, v, nvalid);
-    }
-  }
-}
+// kEpi selects the epilogue instantiation: 0 generic (every feature, runtime flags), 1 GEGLU, 2 + bits = lean
+// variants for bf16 outputs with n_out % 8 == 0 and no SiLU (bit 0 per-row vector, bit 1 residual operands,
+// bit 2 second output) — the compiler does not if-convert what is not instantiated.
+constexpr int kEpiGeneric = 0, kEpiGeglu = 1, kEpiFast = 2;
 
-template <bool kGeglu>
+template <int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_constant__ TmapParam tmap_a1,
                     const __grid_constant__ TmapParam tmap_b, const __grid_constant__ GemmParams p) {
+  constexpr bool kGeglu = kEpi == kEpiGeglu;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -172,7 +261,8 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
   uint64_t* tempty_bar = tfull_bar + 2;                    // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sbias = reinterpret_cast<float*>(smem + 256);     // [2][256] bias of the tile, per accumulator stage
-  uint8_t* tiles = smem + kSmemCtl;
+  uint8_t* stage_base = smem + kSmemCtl;                   // kEpiWarps x kStageWarpBytes transpose tiles
+  uint8_t* tiles = stage_base + kEpiWarps * kStageWarpBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -281,8 +371,13 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
     // ------------------------------ epilogue warps ----------------------------
     // 8 warps: warp % 4 selects the TMEM lane quarter (hardware restriction), (warp - 2) / 4 the chunk parity.
     const int q = warp & 3;
-    const int hsel = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    const int hsel = ew >> 2;
     const int etid = threadIdx.x - 64;  // 0..255
+    const int sub_row = lane >> 2;      // row inside a group of 8 after the transpose
+    const int seg = lane & 3;           // which 8 columns of the 32-column chunk
+    uint8_t* stage = stage_base + ew * kStageWarpBytes;
+    const uint32_t stage_u32 = smem_u32(stage);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -290,29 +385,62 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
       const int m_tile = t / p.num_n_tiles;
       const int n_tile = t - m_tile * p.num_n_tiles;
       const int batch = m_tile / p.tiles_per_batch;
-      const int r = (m_tile - batch * p.tiles_per_batch) * kBlockM + q * 32 + lane;
-      bool valid = r < p.rows_per_batch;
-      long long orow = (long long)batch * p.rows_per_batch + r;
-      if (p.map_mode == 1) {
-        const int per_img = p.pW1 * p.pH1;
-        const int img = r / per_img;
-        const int rem = r - img * per_img;
-        const int y = rem / p.pW1;
-        const int x = rem - y * p.pW1;
-        valid = valid && (y < p.pH1 - 1) && (x < p.pW1 - 1) && (y % p.ostride == 0) && (x % p.ostride == 0);
-        const long long oimg = (long long)batch * (p.rows_per_batch / per_img) + img;
-        if (p.out_halo)
-          orow = (oimg * (p.oH + 1) + y / p.ostride) * (p.oW + 1) + x / p.ostride;
-        else
-          orow = (oimg * p.oH + y / p.ostride) * p.oW + x / p.ostride;
+      const int row_base = (m_tile - batch * p.tiles_per_batch) * kBlockM + q * 32;
+      // the 4 rows this lane finishes (after the transpose): row_base + i*8 + sub_row
+      int orow4[4], grp4[4];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row_base + i * 8 + sub_row;
+        bool valid = r < p.rows_per_batch;
+        long long orow = (long long)batch * p.rows_per_batch + r;
+        if (p.map_mode == 1) {
+          const int per_img = p.pW1 * p.pH1;
+          const int img = r / per_img;
+          const int rem = r - img * per_img;
+          const int y = rem / p.pW1;
+          const int x = rem - y * p.pW1;
+          valid = valid && (y < p.pH1 - 1) && (x < p.pW1 - 1) && (y % p.ostride == 0) && (x % p.ostride == 0);
+          const long long oimg = (long long)batch * (p.rows_per_batch / per_img) + img;
+          if (p.out_halo)
+            orow = (oimg * (p.oH + 1) + y / p.ostride) * (p.oW + 1) + x / p.ostride;
+          else
+            orow = (oimg * p.oH + y / p.ostride) * p.oW + x / p.ostride;
+        }
+        int grp = 0;
+        if (p.rowvec_mode == 1) {
+          grp = (int)(orow / p.rv_a);
+        } else if (p.rowvec_mode == 2) {
+          grp = (int)(((orow / p.rv_a) * p.rv_b + orow % p.rv_b) % p.rv_c);
+        }
+        if (!valid) { orow = 0; grp = 0; }
+        orow4[i] = (int)orow;
+        grp4[i] = grp;
+        vmask |= (valid ? 1u : 0u) << i;
       }
-      int grp = 0;
-      if (p.rowvec_mode == 1) {
-        grp = (int)(orow / p.rv_a);
-      } else if (p.rowvec_mode == 2) {
-        grp = (int)(((orow / p.rv_a) * p.rv_b + orow % p.rv_b) % p.rv_c);
+      if constexpr (kEpi >= kEpiFast) {
+        EpiRows R;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          R.out_off[i] = (long long)orow4[i] * p.out_ld;
+          R.res_off[i] = (long long)orow4[i] * p.res_ld;
+          R.grp[i] = grp4[i];
+        }
+        R.vmask = vmask;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_acc_f = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+        const int chunks_f = p.block_n >> 5;
+        if (hsel >= chunks_f) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        constexpr int kBits = kEpi - kEpiFast;
+        epilogue_fast<(kBits & 1) != 0, (kBits & 2) != 0, (kBits & 4) != 0>(
+            p, R, t_acc_f, stage_u32, n_tile * p.block_n, chunks_f, hsel, lane, &tempty_bar[acc]);
+        continue;
       }
-      if (!valid) { orow = 0; grp = 0; }
 
       // stage this tile's bias in smem, indexed like the accumulator columns
       const int half = p.block_n >> 1;
@@ -342,10 +470,11 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
       for (int c = hsel; c < chunks; c += 2) {
-        const int n = n0 + c * 32;
-        float f[32];
+        const int ncol = n0 + c * 32 + seg * 8;      // first of this lane's 8 output columns
+        const int nvalid = min(8, p.n_out - ncol);   // <= 0: nothing to store
         if constexpr (kGeglu) {
-          // GEGLU tiles carry bias only (host-checked): out = (x + bx) * gelu(g + bg)
+          // GEGLU tiles carry bias only (host-checked): out = (x + bx) * gelu(g + bg), computed row-per-thread,
+          // then transposed as bf16 (64-byte rows, 16-byte chunks XOR-swizzled by (row >> 1) & 3)
           uint32_t v[32];
           uint32_t g[32];
           tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
@@ -356,33 +485,137 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
+          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float xv = __uint_as_float(v[j]) + sb[c * 32 + j];
-            const float gv = __uint_as_float(g[j]) + sb[half + c * 32 + j];
-            f[j] = xv * gelu_erf_f(gv);
+          for (int j = 0; j < 32; j += 2) {
+            const float x0 = __uint_as_float(v[j]) + sb[c * 32 + j];
+            const float x1 = __uint_as_float(v[j + 1]) + sb[c * 32 + j + 1];
+            const float g0 = __uint_as_float(g[j]) + sb[half + c * 32 + j];
+            const float g1 = __uint_as_float(g[j + 1]) + sb[half + c * 32 + j + 1];
+            pk[j >> 1] = pack_bf16x2(x0 * gelu_erf_fast(g0), x1 * gelu_erf_fast(g1));
           }
-          if (valid) {
+          __syncwarp();  // the previous chunk's transposed reads are done
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const int nvalid = min(8, p.n_out - (n + g8 * 8));
-              if (nvalid > 0) store8(p.out_dtype, p.out, (size_t)orow * p.out_ld + n + g8 * 8, f + g8 * 8, nvalid);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = stage_u32 + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                         "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + sub_row;
+            const uint32_t addr = stage_u32 + (uint32_t)rr * 64u + (uint32_t)((seg ^ ((rr >> 1) & 3)) << 4);
+            uint4 u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+            if (((vmask >> i) & 1u) && nvalid > 0) {
+              const size_t off = (size_t)orow4[i] * p.out_ld + ncol;
+              if (nvalid == 8 && p.out_dtype == PT_DT_BF16) {
+                stg_u4(reinterpret_cast<bf16*>(p.out) + off, u);
+              } else {
+                float f[8];
+                unpack8(u, f);
+                for (int j = 0; j < nvalid; ++j) {
+                  if (p.out_dtype == PT_DT_BF16) reinterpret_cast<bf16*>(p.out)[off + j] = __float2bfloat16(f[j]);
+                  else reinterpret_cast<float*>(p.out)[off + j] = f[j];
+                }
+              }
             }
           }
         } else {
           uint32_t v[32];
           tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
-          ChunkOperands ops;
-          prefetch_chunk(p, ops, n, orow, grp, valid);
+          // operands of this lane's 4 row segments, fetched before the TMEM wait (coalesced: 4 lanes = 64 B of a row)
+          const bool full = nvalid == 8;
+          uint4 r1[4], r2[4], ax[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = full && ((vmask >> i) & 1u);
+            r1[i] = (ok && p.res1 != nullptr) ? ldg_u4(p.res1 + (size_t)orow4[i] * p.res_ld + ncol) : make_uint4(0, 0, 0, 0);
+            r2[i] = (ok && p.res2 != nullptr) ? ldg_u4(p.res2 + (size_t)orow4[i] * p.res_ld + ncol) : make_uint4(0, 0, 0, 0);
+            ax[i] = (ok && p.out2 != nullptr) ? ldg_u4(p.aux + (size_t)orow4[i] * p.out_ld + ncol) : make_uint4(0, 0, 0, 0);
+          }
           tmem_wait_ld();
           if (c + 2 >= chunks) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
+          __syncwarp();  // the previous chunk's transposed reads are done
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + sb[c * 32 + j];
-          if (valid) finish_chunk(p, f, ops, n, orow);
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = stage_u32 + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                         "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+          }
+          __syncwarp();
+          const float* sb_seg = sb + c * 32 + seg * 8;
+          const float4 b0 = *reinterpret_cast<const float4*>(sb_seg);
+          const float4 b1 = *reinterpret_cast<const float4*>(sb_seg + 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + sub_row;
+            const uint32_t a0 = stage_u32 + (uint32_t)rr * 128u + (uint32_t)(((2 * seg) ^ (rr & 7)) << 4);
+            const uint32_t a1 = stage_u32 + (uint32_t)rr * 128u + (uint32_t)(((2 * seg + 1) ^ (rr & 7)) << 4);
+            float f[8];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a0));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(a1));
+            if (!((vmask >> i) & 1u) || nvalid <= 0) continue;
+            if (!full) {
+              float tmp[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) tmp[j] = f[j];
+              epilogue_tail(p, tmp, sb_seg, ncol, nvalid, orow4[i], grp4[i]);
+              continue;
+            }
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            if (p.rowvec_mode != 0) {
+              const float4* rv = reinterpret_cast<const float4*>(p.rowvec + (size_t)grp4[i] * p.rowvec_ld + ncol);
+              const float4 v0 = __ldg(rv), v1 = __ldg(rv + 1);
+              f[0] += v0.x; f[1] += v0.y; f[2] += v0.z; f[3] += v0.w;
+              f[4] += v1.x; f[5] += v1.y; f[6] += v1.z; f[7] += v1.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= p.acc_scale;
+            if (p.act_silu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+            }
+            if (p.res1 != nullptr) {
+              float r[8];
+              unpack8(r1[i], r);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(p.res1_scale, r[j], f[j]);
+            }
+            if (p.res2 != nullptr) {
+              float r[8];
+              unpack8(r2[i], r);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(p.res2_scale, r[j], f[j]);
+            }
+            const size_t off = (size_t)orow4[i] * p.out_ld + ncol;
+            if (p.out_dtype == PT_DT_BF16) {
+              stg_u4(reinterpret_cast<bf16*>(p.out) + off, pack8(f));
+            } else {
+              float* o = reinterpret_cast<float*>(p.out) + off;
+              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+            if (p.out2 != nullptr) {
+              float r[8];
+              unpack8(ax[i], r);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(p.aux_scale, r[j], f[j]);
+              if (p.out_dtype == PT_DT_BF16) {
+                stg_u4(reinterpret_cast<bf16*>(p.out2) + off, pack8(f));
+              } else {
+                float* o = reinterpret_cast<float*>(p.out2) + off;
+                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              }
+            }
+          }
         }
       }
     }
@@ -436,7 +669,7 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.geglu = a->geglu ? 1 : 0;
   p.gate_row_offset = a->gate_row_offset;
   p.stage_bytes = kABytes + a->block_n * kBlockK * 2;
-  const int smem_limit = 227 * 1024 - kSmemCtl - 1024;
+  const int smem_limit = 227 * 1024 - kSmemCtl - 1024 - kEpiWarps * kStageWarpBytes;
   int stages = smem_limit / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
@@ -472,14 +705,30 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.out_halo = a->out_halo;
   p.act_silu = a->act_silu;
 
-  const size_t smem_bytes = (size_t)kSmemCtl + (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem_bytes = (size_t)kSmemCtl + (size_t)kEpiWarps * kStageWarpBytes + (size_t)p.stages * p.stage_bytes + 1024;
+  typedef void (*KernelFn)(TmapParam, TmapParam, TmapParam, GemmParams);
+  static const KernelFn kernels[10] = {
+      gemm_tcgen05_kernel<0>, gemm_tcgen05_kernel<1>, gemm_tcgen05_kernel<2>, gemm_tcgen05_kernel<3>,
+      gemm_tcgen05_kernel<4>, gemm_tcgen05_kernel<5>, gemm_tcgen05_kernel<6>, gemm_tcgen05_kernel<7>,
+      gemm_tcgen05_kernel<8>, gemm_tcgen05_kernel<9>};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cudaFuncSetAttribute");
+    for (int i = 0; i < 10; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cudaFuncSetAttribute");
+    }
     attr_set = true;
+  }
+  int epi = kEpiGeneric;
+  if (p.geglu) {
+    epi = kEpiGeglu;
+  } else if (p.out_dtype == PT_DT_BF16 && (p.n_out % 8) == 0 && !p.act_silu && (p.out_ld % 8) == 0 &&
+             (p.res_ld % 8) == 0 && (p.rowvec_mode == 0 || (p.rowvec_ld % 4) == 0) &&
+             ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.out2) | reinterpret_cast<uintptr_t>(p.res1) |
+               reinterpret_cast<uintptr_t>(p.res2) | reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.bias) |
+               reinterpret_cast<uintptr_t>(p.rowvec)) & 15u) == 0) {
+    epi = kEpiFast + (p.rowvec_mode != 0 ? 1 : 0) + ((p.res1 != nullptr || p.res2 != nullptr) ? 2 : 0) +
+          (p.out2 != nullptr ? 4 : 0);
   }
   const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
   const int sms = pt_num_sms();
@@ -489,9 +738,6 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   memcpy(&ta0, a->tmap_a0, sizeof(TmapParam));
   memcpy(&ta1, a->tmap_a1 ? a->tmap_a1 : a->tmap_a0, sizeof(TmapParam));
   memcpy(&tb, a->tmap_b, sizeof(TmapParam));
-  if (p.geglu)
-    gemm_tcgen05_kernel<true><<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
-  else
-    gemm_tcgen05_kernel<false><<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
+  kernels[epi]<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
   return pt_launched("pt_gemm");
 }

@@ -43,6 +43,11 @@ def main():
         fl = 2.0 * M * w.shape[0] * K
         t0 = bench(lambda: torch.matmul(a, w.t()))
         rows.append((f"linear M{M} N{N} K{K} geglu{int(geglu)} bn{g.block_n}", ms, fl / ms / 1e9, fl / t0 / 1e9))
+        if not geglu and N <= 1280 and M > 8192:
+            res = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+            g2 = Gemm(a, w, out, bias=bias, res1=res)
+            ms = bench(lambda: g2.launch(sp))
+            rows.append((f"  + residual operand", ms, fl / ms / 1e9, 0.0))
     for (n, H, W, Cin, Cout) in [(28, 40, 72, 320, 320), (28, 20, 36, 640, 640), (28, 10, 18, 1280, 1280),
                                  (28, 5, 9, 1280, 1280), (28, 10, 18, 2560, 1280)]:
         a = torch.randn(n * (H + 1) * (W + 1), Cin, device="cuda").to(torch.bfloat16)
