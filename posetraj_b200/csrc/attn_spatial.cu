@@ -4,27 +4,29 @@
 // 5/10/20, sequence H*W in {2880, 720, 180, 45}).  Input is the fused QKV projection [rows, 3C] (Q | K | V,
 // head h at columns h*64 of each part); output [rows, C].
 //
-// One CTA per (128-query tile, head, image):
-//   warp 0 lane 0 : TMA producer  — Q tile once, then a ring of {K_j, V_j} tiles (128 keys each)
-//   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T (128x128, fp32 in TMEM, double-buffered), O_j = P_j V_j (128x64)
-//   warps 2..5    : softmax       — one thread per query row: tcgen05.ld S, online max/sum with exp2, P_j as
-//                                   bf16 into a SWIZZLE_128B smem tile (A operand of the PV MMA), running output
-//                                   kept in registers and rescaled there (O_j is read back from TMEM per tile).
-// The QK^T of tile j+1 is issued before the softmax of tile j finishes, so the tensor pipe overlaps the
-// MUFU-bound softmax.  FLOPs: 4*S*64 per query row per head.
+// One CTA per (NQ x 128 queries, head, image), NQ = 2 (two query tiles share every K/V tile) or 1 (S <= 128):
+//   warp 0 lane 0   : TMA producer — the NQ Q tiles once, then a ring of {K_j, V_j} tiles (128 keys each)
+//   warp 1 lane 0   : MMA issuer   — S_g = Q_g K_j^T (128x128 fp32 in TMEM), O_g += P_g V_j (128x64 in TMEM)
+//   warps 2..5 (+6..9) : softmax group g — one thread per query row: ONE tcgen05.ld of S per tile (128 registers),
+//                     running max with LAZY rescaling (O and l are only rescaled when the max grew by more than 2^8,
+//                     so O stays in TMEM and is read back once at the end), P_g as bf16 into a SWIZZLE_128B smem
+//                     tile (A operand of the PV MMA).
+// While group 0 runs its softmax the tensor pipe works for group 1 and vice versa; the exponentials (MUFU ex2,
+// 16/clk/SM) are the floor: 256x128 of them per K/V tile against 1024 MMA cycles.
+// FLOPs: 4*S*64 per query row per head.
 #include "common.cuh"
 #include "launch.h"
 #include "../../include/posetraj_b200.h"
 
 namespace pt {
 
-constexpr int kAttnThreads = 192;
 constexpr int kQTile = 128;
 constexpr int kKTile = 128;
 constexpr int kHd = 64;
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KiB: Q, K, V tiles and each 64-key half of P
 constexpr int kKvStages = 3;
-constexpr uint32_t kAttnTmemCols = 512;   // S0 [0,128) S1 [128,256) O [256,320)
+constexpr uint32_t kAttnTmemCols = 512;   // S_0 [0,128) S_1 [128,256) O_0 [256,320) O_1 [320,384)
+constexpr float kRescaleThreshold = 8.0f; // in log2 units: P <= 2^8 between rescales
 
 struct AttnParams {
   int S, heads, C;
@@ -37,7 +39,8 @@ struct alignas(64) AttnTmap {
   uint64_t opaque[16];
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+template <int NQ>
+__global__ void __launch_bounds__(64 + 128 * NQ, 1)
 attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -46,17 +49,17 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* kv_full = q_full + 1;              // [kKvStages]
   uint64_t* kv_empty = kv_full + kKvStages;    // [kKvStages]
-  uint64_t* s_full = kv_empty + kKvStages;     // [2]
-  uint64_t* p_full = s_full + 2;               // [1]
-  uint64_t* o_full = p_full + 1;               // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
-  uint8_t* sQ = smem + 1024;
-  uint8_t* sP = sQ + kTileBytes;               // 2 x 16 KiB (keys 0-63 | keys 64-127)
-  uint8_t* sKV = sP + 2 * kTileBytes;          // kKvStages x (K 16 KiB + V 16 KiB)
+  uint64_t* s_full = kv_empty + kKvStages;     // [2]  S_g(j) complete
+  uint64_t* p_full = s_full + 2;               // [2]  P_g(j) in smem, S_g(j) consumed, O_g rescaled
+  uint64_t* o_done = p_full + 2;               // [2]  PV_g(j) retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint8_t* sQ = smem + 1024;                   // NQ x 16 KiB
+  uint8_t* sP = sQ + NQ * kTileBytes;          // NQ x 2 x 16 KiB (keys 0-63 | keys 64-127)
+  uint8_t* sKV = sP + NQ * 2 * kTileBytes;     // kKvStages x (K 16 KiB + V 16 KiB)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kQTile;
+  const int q0 = blockIdx.x * (kQTile * NQ);
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const int n_kv = (p.S + kKTile - 1) / kKTile;
@@ -68,10 +71,11 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&o_done[g], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kAttnTmemCols);
@@ -82,8 +86,8 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_3d(sQ, &tmap_qkv, q_full, head * kHd, q0, img);
+      mbar_arrive_expect_tx(q_full, NQ * kTileBytes);
+      for (int g = 0; g < NQ; ++g) tma_load_3d(sQ + g * kTileBytes, &tmap_qkv, q_full, head * kHd, q0 + g * kQTile, img);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
@@ -102,145 +106,157 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major: hd contiguous)
-      const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ));
-      auto issue_s = [&](int j, int stage) {
+      auto issue_s = [&](int g, int stage) {
+        const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ + g * kTileBytes));
         const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sKV + (size_t)stage * 2 * kTileBytes));
-        const uint32_t d = tmem_base + (uint32_t)(j & 1) * 128u;
+        const uint32_t d = tmem_base + (uint32_t)g * 128u;
 #pragma unroll
         for (int k = 0; k < kHd / 16; ++k)
           tc_mma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
-        tc_commit(&s_full[j & 1]);
+        tc_commit(&s_full[g]);
       };
       mbar_wait(q_full, 0);
-      int stage_s = 0;  // stage of the next S to issue
-      uint32_t phase_s = 0;
-      int stage_o = 0;  // stage of the next PV to issue
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      if (++stage_s == kKvStages) { stage_s = 0; phase_s ^= 1u; }
+      for (int g = 0; g < NQ; ++g) issue_s(g, 0);
+      int stage = 0;       // stage of K_j / V_j
+      int stage_n = 1 % kKvStages;  // stage of K_{j+1}
+      uint32_t phase_n = (kKvStages == 1) ? 1u : 0u;
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) {
-          mbar_wait(&kv_full[stage_s], phase_s);
+          mbar_wait(&kv_full[stage_n], phase_n);
           tc_fence_after();
-          issue_s(j + 1, stage_s);
-          if (++stage_s == kKvStages) { stage_s = 0; phase_s ^= 1u; }
         }
-        mbar_wait(p_full, (uint32_t)j & 1u);  // P_j in smem, O TMEM drained, S_j consumed
-        tc_fence_after();
-        const uint32_t sV = smem_u32(sKV + (size_t)stage_o * 2 * kTileBytes + kTileBytes);
+        const uint32_t sV = smem_u32(sKV + (size_t)stage * 2 * kTileBytes + kTileBytes);
         // V tile: rows = keys (128 B each, 8-row swizzle atoms of 1024 B): MN-major B operand, K step of 16 keys
         // = 2048 B; LBO (stride between 64-wide N blocks) is unused for N = 64.
         const uint64_t vdesc = make_smem_desc(sV, 1024, 1024, 2);
+        for (int g = 0; g < NQ; ++g) {
+          mbar_wait(&p_full[g], (uint32_t)j & 1u);  // P_g(j) in smem, S_g(j) consumed, O_g rescaled
+          tc_fence_after();
+          const uint32_t sPg = smem_u32(sP + (size_t)g * 2 * kTileBytes);
 #pragma unroll
-        for (int k = 0; k < kKTile / 16; ++k) {
-          const uint64_t pdesc = make_desc_kmajor_sw128(smem_u32(sP) + (uint32_t)(k >> 2) * kTileBytes) +
-                                 (uint64_t)(2 * (k & 3));
-          tc_mma_bf16(tmem_base + 256u, pdesc, vdesc + (uint64_t)(k * 128), idesc_o, k != 0 ? 1u : 0u);
+          for (int k = 0; k < kKTile / 16; ++k) {
+            const uint64_t pdesc = make_desc_kmajor_sw128(sPg + (uint32_t)(k >> 2) * kTileBytes) + (uint64_t)(2 * (k & 3));
+            tc_mma_bf16(tmem_base + 256u + (uint32_t)g * 64u, pdesc, vdesc + (uint64_t)(k * 128), idesc_o,
+                        (j | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&o_done[g]);
+          if (j + 1 < n_kv) issue_s(g, stage_n);
         }
-        tc_commit(o_full);
-        tc_commit(&kv_empty[stage_o]);
-        if (++stage_o == kKvStages) stage_o = 0;
+        tc_commit(&kv_empty[stage]);
+        stage = stage_n;
+        if (++stage_n == kKvStages) {
+          stage_n = 0;
+          phase_n ^= 1u;
+        }
       }
     }
   } else {
     // ------------------------------ softmax warps ----------------------------
-    const int q = warp & 3;
-    const int row = q * 32 + lane;  // query row inside the tile == TMEM lane
+    const int g = (warp - 2) >> 2;      // query tile of this warp
+    const int q = warp & 3;             // TMEM lane quarter
+    const int row = q * 32 + lane;      // query row inside the tile == TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    float o_acc[kHd];
-#pragma unroll
-    for (int d = 0; d < kHd; ++d) o_acc[d] = 0.f;
-    float m_run = -INFINITY;  // running max of raw scores
+    const uint32_t t_s = t_lane + (uint32_t)g * 128u;
+    const uint32_t t_o = t_lane + 256u + (uint32_t)g * 64u;
+    uint8_t* sPg = sP + (size_t)g * 2 * kTileBytes;
+    float m_ref = -INFINITY;  // the max the exponent offsets currently refer to (raw score units)
     float l_run = 0.f;
-    float alpha_prev = 1.f;   // rescale owed to o_acc before adding the previous tile's O
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1u);
+      mbar_wait(&s_full[g], (uint32_t)j & 1u);
       tc_fence_after();
-      const uint32_t t_s = t_lane + (uint32_t)(j & 1) * 128u;
       const int kvalid = min(kKTile, p.S - j * kKTile);  // keys beyond S are TMA zero-fill: mask them
-      // pass 1: row max
-      float m_new = m_run;
+      uint32_t v[128];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + (uint32_t)c * 32u, v);
-        tmem_wait_ld();
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + (uint32_t)c * 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      tmem_wait_ld();
+      float m_tile = -INFINITY;
+      if (kvalid == kKTile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kvalid) m_new = fmaxf(m_new, __uint_as_float(v[i]));
+        for (int i = 0; i < 128; ++i) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i < kvalid) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
       }
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);  // 0 on the first tile (m_run = -inf)
-      // fold the previous tile's O into the register accumulator (also frees the O columns of TMEM)
+      // PV_g(j-1) must have retired before P_g is overwritten / O_g is rescaled
       if (j > 0) {
-        mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
+        mbar_wait(&o_done[g], (uint32_t)(j - 1) & 1u);
         tc_fence_after();
+      }
+      const bool grow = (m_tile - m_ref) * p.scale_log2 > kRescaleThreshold;  // also true on the first tile
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? m_tile : m_ref;
+        const float alpha = ex2_approx((m_ref - m_new) * p.scale_log2);  // 0 on the first tile, 1 for rows that keep m_ref
+        l_run *= alpha;
+        m_ref = m_new;
+        if (j > 0) {
+          // rare path (the running max grew by > 2^8): 8 columns at a time keeps the live S registers intact
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            uint32_t o[8];
+            tmem_ld_32x8(t_o + (uint32_t)c * 8u, o);
+            tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_lane + 256u + (uint32_t)c * 32u, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x8(t_o + (uint32_t)c * 8u, o);
+          }
+          tmem_wait_st();
         }
       }
-      alpha_prev = alpha;
-      // pass 2: P = exp2((s - m) * scale), row sum, bf16 P into the swizzled smem tile
-      const float mb = m_new * p.scale_log2;
+      // P = exp2((s - m_ref) * scale) as bf16 into the swizzled smem tile; row sum of what the MMA will multiply
+      const float mb = m_ref * p.scale_log2;
       float lsum = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + (uint32_t)c * 32u, v);
-        tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < kvalid) ? exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb)) : 0.f;
-          float p1 = (c * 32 + i + 1 < kvalid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mb)) : 0.f;
+          const int k0 = c * 32 + i;
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[k0]), p.scale_log2, -mb));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[k0 + 1]), p.scale_log2, -mb));
+          if (k0 >= kvalid) p0 = 0.f;
+          if (k0 + 1 >= kvalid) p1 = 0.f;
           pk[i >> 1] = pack_bf16x2(p0, p1);
-          // sum what the tensor core will actually multiply (bf16-rounded probabilities)
           const float2 r = unpack_bf16x2(pk[i >> 1]);
           lsum += r.x + r.y;
         }
         // keys [c*32, c*32+32) -> half (c >> 1), 16-byte chunks (c & 1)*4 .. +3 of this row, XOR-swizzled
-        uint8_t* prow = sP + (size_t)(c >> 1) * kTileBytes + (size_t)row * 128;
+        uint8_t* prow = sPg + (size_t)(c >> 1) * kTileBytes + (size_t)row * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int chunk = ((c & 1) * 4 + ch) ^ (row & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) =
-              make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
         }
       }
-      l_run = fmaf(l_run, alpha, lsum);
-      m_run = m_new;
+      l_run += lsum;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[g]);
     }
-    // last tile's O
-    mbar_wait(o_full, (uint32_t)(n_kv - 1) & 1u);
+    // O_g = sum_j P_g(j) V_j is complete once the last PV retired
+    mbar_wait(&o_done[g], (uint32_t)(n_kv - 1) & 1u);
     tc_fence_after();
+    const int qrow = q0 + g * kQTile + row;
+    const float inv = 1.0f / l_run;
+    bf16* dst = p.out + ((size_t)img * p.S + qrow) * p.out_ld + head * kHd;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_lane + 256u + (uint32_t)c * 32u, v);
+      uint32_t o[32];
+      tmem_ld_32x32(t_o + (uint32_t)c * 32u, o);
       tmem_wait_ld();
+      if (qrow < p.S) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
-    }
-    if (q0 + row < p.S) {
-      const float inv = 1.0f / l_run;
-      bf16* dst = p.out + ((size_t)img * p.S + q0 + row) * p.out_ld + head * kHd;
-#pragma unroll
-      for (int d = 0; d < kHd; d += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(o_acc[d] * inv, o_acc[d + 1] * inv);
-        u.y = pack_bf16x2(o_acc[d + 2] * inv, o_acc[d + 3] * inv);
-        u.z = pack_bf16x2(o_acc[d + 4] * inv, o_acc[d + 5] * inv);
-        u.w = pack_bf16x2(o_acc[d + 6] * inv, o_acc[d + 7] * inv);
-        stg_u4(dst + d, u);
+        for (int d = 0; d < 32; d += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[d]) * inv, __uint_as_float(o[d + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[d + 2]) * inv, __uint_as_float(o[d + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[d + 4]) * inv, __uint_as_float(o[d + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[d + 6]) * inv, __uint_as_float(o[d + 7]) * inv);
+          stg_u4(dst + c * 32 + d, u);
+        }
       }
     }
   }
@@ -252,6 +268,22 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
     tc_fence_after();
     tmem_dealloc(tmem_base, kAttnTmemCols);
   }
+}
+
+template <int NQ>
+static int launch_attn(const PtAttnSpatialArgs* a, const AttnParams& p, cudaStream_t st) {
+  const size_t smem_bytes = 1024 + (size_t)kTileBytes * (NQ + 2 * NQ + 2 * kKvStages) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_spatial_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return pt_fail(e, "pt_attention_spatial: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  AttnTmap tm;
+  memcpy(&tm, a->tmap_qkv, sizeof(tm));
+  dim3 grid((a->S + kQTile * NQ - 1) / (kQTile * NQ), a->heads, a->n_img);
+  attn_spatial_kernel<NQ><<<grid, 64 + 128 * NQ, smem_bytes, st>>>(tm, p);
+  return pt_launched("pt_attention_spatial");
 }
 
 }  // namespace pt
@@ -269,16 +301,6 @@ extern "C" int pt_attention_spatial(const PtAttnSpatialArgs* a, void* stream) {
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.out_ld = a->out_ld;
-  const size_t smem_bytes = 1024 + (size_t)kTileBytes * (1 + 2 + 2 * kKvStages) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return pt_fail(e, "pt_attention_spatial: cudaFuncSetAttribute");
-    attr_set = true;
-  }
-  AttnTmap tm;
-  memcpy(&tm, a->tmap_qkv, sizeof(tm));
-  dim3 grid((a->S + kQTile - 1) / kQTile, a->heads, a->n_img);
-  attn_spatial_kernel<<<grid, kAttnThreads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
-  return pt_launched("pt_attention_spatial");
+  if (a->S <= kQTile) return launch_attn<1>(a, p, (cudaStream_t)stream);
+  return launch_attn<2>(a, p, (cudaStream_t)stream);
 }

@@ -28,6 +28,18 @@ PT_DEVICE uint32_t lane_id() {
   return l;
 }
 
+PT_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+PT_DEVICE float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 PT_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // exact (erf) GELU, as diffusers' GEGLU uses F.gelu(gate) with approximate="none"
@@ -211,6 +223,19 @@ PT_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// 32 lanes x 32 columns store: thread i writes lane (base_lane + i), columns [c, c+32)
+PT_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
 PT_DEVICE void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -219,6 +244,19 @@ PT_DEVICE void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+
+PT_DEVICE void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+PT_DEVICE void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 
 // ----------------------------------------------------------------------------------

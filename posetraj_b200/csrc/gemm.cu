@@ -83,9 +83,6 @@ PT_DEVICE uint4 pack8(const float* v) {
   return u;
 }
 
-PT_DEVICE float ex2_approx(float x);
-PT_DEVICE float rcp_approx(float x);
-
 // erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, below fp32 GELU noise; two MUFU + 7 FMA instead of erff's
 // ~30 instructions) — the GEGLU epilogue evaluates 128 x block_n/2 of these per tile and is otherwise ALU-bound.
 PT_DEVICE float gelu_erf_fast(float x) {
@@ -128,17 +125,6 @@ struct EpiRows {
   int grp[4];
   uint32_t vmask;
 };
-
-PT_DEVICE float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-PT_DEVICE float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // Lean epilogue of one accumulator tile for bf16 outputs (see kEpiFast).  val = acc_scale*(acc + bias + rowvec) +
 // s1*res1 + s2*res2 ; out = val ; out2 = val + aux_scale*aux.
