@@ -85,7 +85,7 @@ enum { PT_DT_BF16 = 0, PT_DT_F32 = 1 };
 typedef struct PtGemmArgs {
   const PtTensorMap* tmap_a0; /* rank-3 {K0, rows_per_batch, batches}, box {64,128,1} */
   const PtTensorMap* tmap_a1; /* optional second K-range (channel concat); NULL if unused */
-  const PtTensorMap* tmap_b;  /* rank-2 {num_taps*(K0+K1), N_rows}, box {64, b_box_rows} */
+  const PtTensorMap* tmap_b;  /* rank-2 {num_taps*(K0+K1), N_rows}, box {64, block_n/2} */
   int32_t rows_per_batch;     /* A/accumulator row space per batch */
   int32_t batches;
   int32_t n_out;              /* number of output columns (GEGLU: the gated width, = half of W rows) */
@@ -127,6 +127,8 @@ typedef struct PtGemmArgs {
                                * are never written (the caller zeroes the buffer once) */
   int32_t act_silu;           /* apply SiLU after acc_scale and before the residual terms (cond-embedding convs,
                                * models/controlnet_sdv.py:103-109) */
+  int32_t cta_pair;           /* 1: run as clusters of two CTAs sharing 256 x block_n tiles (tcgen05 cta_group::2);
+                               * tmap_b's box is block_n/2 rows in both modes */
 } PtGemmArgs;
 int pt_gemm(const PtGemmArgs* a, void* stream);
 

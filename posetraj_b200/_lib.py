@@ -69,7 +69,7 @@ class PtGemmArgs(C.Structure):
         ("aux_scale", C.c_float),
         ("map_mode", C.c_int32),
         ("pW1", C.c_int32), ("pH1", C.c_int32), ("ostride", C.c_int32), ("oW", C.c_int32), ("oH", C.c_int32),
-        ("out_halo", C.c_int32), ("act_silu", C.c_int32),
+        ("out_halo", C.c_int32), ("act_silu", C.c_int32), ("cta_pair", C.c_int32),
     ]
 
 

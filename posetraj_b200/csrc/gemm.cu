@@ -128,9 +128,9 @@ struct EpiRows {
 
 // Lean epilogue of one accumulator tile for bf16 outputs (see kEpiFast).  val = acc_scale*(acc + bias + rowvec) +
 // s1*res1 + s2*res2 ; out = val ; out2 = val + aux_scale*aux.
-template <bool kRowvec, bool kRes, bool kOut2>
+template <bool kRowvec, bool kRes, bool kOut2, typename ArriveFn>
 PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_acc, uint32_t stage_u32, int n0,
-                             int chunks, int hsel, int lane, uint64_t* tempty) {
+                             int chunks, int hsel, int lane, const ArriveFn& arrive_drained) {
   const int sub_row = lane >> 2;
   const int seg = lane & 3;
   bf16* out = reinterpret_cast<bf16*>(p.out);
@@ -174,7 +174,7 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
     if (c + 2 >= chunks) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
+      if (lane == 0) arrive_drained();
     }
     __syncwarp();  // the previous chunk's transposed reads are done
 #pragma unroll
@@ -231,7 +231,11 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
 // bit 2 second output) — the compiler does not if-convert what is not instantiated.
 constexpr int kEpiGeneric = 0, kEpiGeglu = 1, kEpiFast = 2;
 
-template <int kEpi>
+// kPair: the kernel runs as clusters of two CTAs (one SM pair) that share one 256 x block_n tile through
+// tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of A and HALF of the B tile, so a k-step costs
+// 16 KiB + block_n*64 B of L2->SM traffic per SM instead of 16 KiB + block_n*128 B: the large-M layers are
+// L2-bandwidth bound with single-CTA tiles (profiles/r1b).
+template <int kEpi, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_constant__ TmapParam tmap_a1,
                     const __grid_constant__ TmapParam tmap_b, const __grid_constant__ GemmParams p) {
@@ -255,7 +259,13 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int k_chunks = p.k0_chunks + p.k1_chunks;
   const int k_iters = p.num_taps * k_chunks;
-  const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
+  const int half = p.block_n >> 1;
+  const uint32_t b_half_bytes = (uint32_t)half * kBlockK * 2;
+  // pair mode: cta_rank 0 is the leader (issues the MMAs, owns the full / tmem-empty barriers both CTAs signal)
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const int tile_first = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)num_clusters_x() : (int)gridDim.x;
+  constexpr int kTileM = kPair ? 2 * kBlockM : kBlockM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a0);
@@ -267,15 +277,17 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, kTmemCols);
+    if constexpr (kPair) tmem_alloc_pair(tmem_ptr, kTmemCols);
+    else tmem_alloc(tmem_ptr, kTmemCols);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer's barriers must be initialised before anything remote
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -284,12 +296,11 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile_first; t < num_tiles; t += tile_step) {
         const int m_tile = t / p.num_n_tiles;
         const int n_tile = t - m_tile * p.num_n_tiles;
         const int batch = m_tile / p.tiles_per_batch;
-        const int r0 = (m_tile - batch * p.tiles_per_batch) * kBlockM;
-        const int half = p.block_n >> 1;
+        const int r0 = (m_tile - batch * p.tiles_per_batch) * kTileM + (int)cta_rank * kBlockM;
         const int n0 = kGeglu ? n_tile * half : n_tile * p.block_n;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int arow = r0 + p.tap_shift[tap];
@@ -297,19 +308,24 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sA = tiles + (size_t)stage * p.stage_bytes;
             uint8_t* sB = sA + kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kABytes + b_bytes);
-            if (kc < p.k0_chunks) {
-              tma_load_3d(sA, &tmap_a0, &full_bar[stage], kc * kBlockK, arow, batch);
-            } else {
-              tma_load_3d(sA, &tmap_a1, &full_bar[stage], (kc - p.k0_chunks) * kBlockK, arow, batch);
-            }
             const int kcol = (tap * k_chunks + kc) * kBlockK;
-            if constexpr (kGeglu) {
-              tma_load_2d(sB, &tmap_b, &full_bar[stage], kcol, n0);
-              tma_load_2d(sB + (size_t)half * kBlockK * 2, &tmap_b, &full_bar[stage], kcol,
-                          p.gate_row_offset + n0);
+            const int ak = (kc < p.k0_chunks ? kc : kc - p.k0_chunks) * kBlockK;
+            const TmapParam* ta = kc < p.k0_chunks ? &tmap_a0 : &tmap_a1;
+            if constexpr (kPair) {
+              // both CTAs credit the LEADER's full barrier; the leader expects the bytes of the whole pair
+              const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0u);
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * ((uint32_t)kABytes + b_half_bytes));
+              tma_load_3d_pair(sA, ta, bar, ak, arow, batch);
+              // B rows of this CTA: the second half of the tile's N range for rank 1 (GEGLU: rank 0 = value rows,
+              // rank 1 = gate rows, which is exactly the accumulator column order [value | gate])
+              const int brow = kGeglu ? (cta_rank == 0 ? n0 : p.gate_row_offset + n0) : n0 + (int)cta_rank * half;
+              tma_load_2d_pair(sB, &tmap_b, bar, kcol, brow);
             } else {
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kABytes + 2u * b_half_bytes);
+              tma_load_3d(sA, ta, &full_bar[stage], ak, arow, batch);
               tma_load_2d(sB, &tmap_b, &full_bar[stage], kcol, n0);
+              tma_load_2d(sB + b_half_bytes, &tmap_b, &full_bar[stage], kcol,
+                          kGeglu ? p.gate_row_offset + n0 : n0 + half);
             }
             if (++stage == p.stages) {
               stage = 0;
@@ -321,12 +337,12 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)p.block_n, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = tile_first; t < num_tiles; t += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -341,16 +357,22 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                        (ki | k) != 0 ? 1u : 0u);
+            if constexpr (kPair)
+              tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
+            else
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (kPair) tc_commit_pair(&empty_bar[stage], 3);
+          else tc_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (kPair) tc_commit_pair(&tfull_bar[acc], 3);
+        else tc_commit(&tfull_bar[acc]);
       }
     }
   } else {
@@ -364,14 +386,20 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
     const int seg = lane & 3;           // which 8 columns of the 32-column chunk
     uint8_t* stage = stage_base + ew * kStageWarpBytes;
     const uint32_t stage_u32 = smem_u32(stage);
+    // "accumulator drained" goes to the LEADER's barrier (remote arrive for rank 1 of a pair)
+    const uint32_t tempty_addr0 = kPair ? map_to_cta(smem_u32(&tempty_bar[0]), 0u) : smem_u32(&tempty_bar[0]);
+    auto arrive_tempty = [&](int acc) {
+      if constexpr (kPair) mbar_arrive_cluster(tempty_addr0 + (uint32_t)acc * 8u);
+      else mbar_arrive(&tempty_bar[acc]);
+    };
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile_first; t < num_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int m_tile = t / p.num_n_tiles;
       const int n_tile = t - m_tile * p.num_n_tiles;
       const int batch = m_tile / p.tiles_per_batch;
-      const int row_base = (m_tile - batch * p.tiles_per_batch) * kBlockM + q * 32;
+      const int row_base = (m_tile - batch * p.tiles_per_batch) * kTileM + (int)cta_rank * kBlockM + q * 32;
       // the 4 rows this lane finishes (after the transpose): row_base + i*8 + sub_row
       int orow4[4], grp4[4];
       uint32_t vmask = 0;
@@ -420,16 +448,15 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         if (hsel >= chunks_f) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) arrive_tempty(acc);
         }
         constexpr int kBits = kEpi - kEpiFast;
         epilogue_fast<(kBits & 1) != 0, (kBits & 2) != 0, (kBits & 4) != 0>(
-            p, R, t_acc_f, stage_u32, n_tile * p.block_n, chunks_f, hsel, lane, &tempty_bar[acc]);
+            p, R, t_acc_f, stage_u32, n_tile * p.block_n, chunks_f, hsel, lane, [&]() { arrive_tempty(acc); });
         continue;
       }
 
       // stage this tile's bias in smem, indexed like the accumulator columns
-      const int half = p.block_n >> 1;
       const int n0 = kGeglu ? n_tile * half : n_tile * p.block_n;
       float* sb = sbias + acc * 256;
       if (etid < p.block_n) {
@@ -453,7 +480,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
       if (hsel >= chunks) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) arrive_tempty(acc);
       }
       for (int c = hsel; c < chunks; c += 2) {
         const int ncol = n0 + c * 32 + seg * 8;      // first of this lane's 8 output columns
@@ -469,7 +496,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
           if (c + 2 >= chunks) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) arrive_tempty(acc);
           }
           uint32_t pk[16];
 #pragma unroll
@@ -525,7 +552,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
           if (c + 2 >= chunks) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) arrive_tempty(acc);
           }
           __syncwarp();  // the previous chunk's transposed reads are done
 #pragma unroll
@@ -609,11 +636,13 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
 
   // ------------------------------ teardown -------------------------------------
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer may still read this CTA's smem / signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -626,6 +655,8 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: null argument");
   if (a->block_n < 32 || a->block_n > 256 || (a->block_n % 32) != 0)
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: block_n must be a multiple of 32 in [32,256]");
+  if (a->cta_pair && a->block_n < 64)
+    return pt_fail(cudaErrorInvalidValue, "pt_gemm: cta_pair needs block_n >= 64");
   if (a->geglu && (a->block_n % 64) != 0)
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: GEGLU needs block_n multiple of 64");
   if (a->num_taps < 1 || a->num_taps > 9 || a->k0_chunks < 1 || a->k1_chunks < 0)
@@ -654,12 +685,14 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.block_n = a->block_n;
   p.geglu = a->geglu ? 1 : 0;
   p.gate_row_offset = a->gate_row_offset;
-  p.stage_bytes = kABytes + a->block_n * kBlockK * 2;
+  p.stage_bytes = kABytes + (a->cta_pair ? a->block_n / 2 : a->block_n) * kBlockK * 2;
   const int smem_limit = 227 * 1024 - kSmemCtl - 1024 - kEpiWarps * kStageWarpBytes;
   int stages = smem_limit / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  p.tiles_per_batch = (a->rows_per_batch + kBlockM - 1) / kBlockM;
+  const bool pair = a->cta_pair != 0;
+  const int tile_m = pair ? 2 * kBlockM : kBlockM;
+  p.tiles_per_batch = (a->rows_per_batch + tile_m - 1) / tile_m;
   p.num_m_tiles = p.tiles_per_batch * a->batches;
   const int n_per_tile = a->geglu ? a->block_n / 2 : a->block_n;
   p.num_n_tiles = (a->n_out + n_per_tile - 1) / n_per_tile;
@@ -693,16 +726,22 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
 
   const size_t smem_bytes = (size_t)kSmemCtl + (size_t)kEpiWarps * kStageWarpBytes + (size_t)p.stages * p.stage_bytes + 1024;
   typedef void (*KernelFn)(TmapParam, TmapParam, TmapParam, GemmParams);
-  static const KernelFn kernels[10] = {
-      gemm_tcgen05_kernel<0>, gemm_tcgen05_kernel<1>, gemm_tcgen05_kernel<2>, gemm_tcgen05_kernel<3>,
-      gemm_tcgen05_kernel<4>, gemm_tcgen05_kernel<5>, gemm_tcgen05_kernel<6>, gemm_tcgen05_kernel<7>,
-      gemm_tcgen05_kernel<8>, gemm_tcgen05_kernel<9>};
+  static const KernelFn kernels[2][10] = {
+      {gemm_tcgen05_kernel<0, false>, gemm_tcgen05_kernel<1, false>, gemm_tcgen05_kernel<2, false>,
+       gemm_tcgen05_kernel<3, false>, gemm_tcgen05_kernel<4, false>, gemm_tcgen05_kernel<5, false>,
+       gemm_tcgen05_kernel<6, false>, gemm_tcgen05_kernel<7, false>, gemm_tcgen05_kernel<8, false>,
+       gemm_tcgen05_kernel<9, false>},
+      {gemm_tcgen05_kernel<0, true>, gemm_tcgen05_kernel<1, true>, gemm_tcgen05_kernel<2, true>,
+       gemm_tcgen05_kernel<3, true>, gemm_tcgen05_kernel<4, true>, gemm_tcgen05_kernel<5, true>,
+       gemm_tcgen05_kernel<6, true>, gemm_tcgen05_kernel<7, true>, gemm_tcgen05_kernel<8, true>,
+       gemm_tcgen05_kernel<9, true>}};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 10; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cudaFuncSetAttribute");
-    }
+    for (int m = 0; m < 2; ++m)
+      for (int i = 0; i < 10; ++i) {
+        cudaError_t e = cudaFuncSetAttribute(kernels[m][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cudaFuncSetAttribute");
+      }
     attr_set = true;
   }
   int epi = kEpiGeneric;
@@ -718,12 +757,30 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   }
   const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
   const int sms = pt_num_sms();
-  const int grid = (int)(tiles < sms ? tiles : sms);
 
   TmapParam ta0, ta1, tb;
   memcpy(&ta0, a->tmap_a0, sizeof(TmapParam));
   memcpy(&ta1, a->tmap_a1 ? a->tmap_a1 : a->tmap_a0, sizeof(TmapParam));
   memcpy(&tb, a->tmap_b, sizeof(TmapParam));
-  kernels[epi]<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
+  if (pair) {
+    const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[1][epi], ta0, ta1, tb, p);
+    if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cluster launch");
+  } else {
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    kernels[0][epi]<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
+  }
   return pt_launched("pt_gemm");
 }

@@ -29,24 +29,82 @@ def _stream_ptr(stream=None) -> int:
     return stream.cuda_stream
 
 
-def pick_block_n(m_tiles: int, n_out: int, geglu: bool = False, k_iters: int = 8) -> int:
-    """Tile-width heuristic: minimise (waves x per-tile cost) over the legal accumulator widths."""
+# ---------------------------------------------------------------------------------------------------------------
+# Tile configuration: (cta_pair, block_n) per GEMM shape.
+#   1. shapes of the configs[1] denoise step measured on B200 by tools/gemm_sweep.py (gpurun_out/r16_sweep.log);
+#   2. otherwise the argmin of a per-tile cost model fitted to that sweep (8.6 % rms log error, picks within 4 % of
+#      the measured optimum on 24 of 26 shapes): time = max tiles per CTA(-pair) x (k_iters x k-step + epilogue).
+# ---------------------------------------------------------------------------------------------------------------
+TUNED = {
+    # (rows, n_out, K per tap, taps, geglu): (cta_pair, block_n)
+    (80640, 320, 320, 1, 0): (False, 128),    # 59.4 us
+    (80640, 960, 320, 1, 0): (False, 160),    # 77.8 us
+    (80640, 1280, 320, 1, 1): (False, 256),   # 168.9 us
+    (80640, 320, 1280, 1, 0): (False, 160),   # 86.0 us
+    (20160, 640, 640, 1, 0): (False, 128),    # 36.9 us
+    (20160, 1920, 640, 1, 0): (False, 192),   # 55.3 us
+    (20160, 2560, 640, 1, 1): (True, 256),    # 118.8 us
+    (20160, 640, 2560, 1, 0): (True, 224),    # 73.7 us
+    (5040, 1280, 1280, 1, 0): (False, 192),   # 28.7 us
+    (5040, 3840, 1280, 1, 0): (False, 224),   # 49.2 us
+    (5040, 5120, 1280, 1, 1): (True, 256),    # 102.4 us
+    (5040, 1280, 5120, 1, 0): (True, 192),    # 69.6 us
+    (1260, 1280, 1280, 1, 0): (False, 128),   # 18.4 us
+    (1260, 5120, 1280, 1, 1): (True, 256),    # 36.9 us
+    (1260, 1280, 5120, 1, 0): (False, 128),   # 36.9 us
+    (83804, 320, 320, 9, 0): (False, 160),    # 147.5 us
+    (21756, 640, 640, 9, 0): (True, 224),     # 132.1 us
+    (5852, 1280, 1280, 9, 0): (True, 256),    # 131.0 us
+    (1680, 1280, 1280, 9, 0): (False, 160),   # 67.7 us
+    (83804, 320, 640, 9, 0): (False, 160),    # 274.4 us
+    (21756, 640, 1280, 9, 0): (True, 224),    # 256.0 us
+    (5852, 1280, 2560, 9, 0): (True, 224),    # 251.9 us
+    (80640, 320, 320, 3, 0): (False, 160),    # 69.7 us
+    (20160, 640, 640, 3, 0): (False, 224),    # 59.4 us
+    (5040, 1280, 1280, 3, 0): (False, 192),   # 55.3 us
+    (1260, 1280, 1280, 3, 0): (False, 96),    # 30.7 us
+}
+
+_C_MMA, _C_FLOOR, _C_B, _C_E0, _C_E1, _C_FLOOR_P, _C_B_P = 0.893, 265.8, 0.2507, -315.3, 11.73, 305.1, 0.0097
+
+
+def tile_cost_ns(rows: int, batches: int, n_out: int, k_iters: int, geglu: bool, has_res: bool, pair: bool, bn: int) -> float:
+    tm = 256 if pair else 128
+    m_tiles = batches * math.ceil(rows / batches / tm)
+    per = bn // 2 if geglu else bn
+    n_tiles = math.ceil(n_out / per)
+    units = NUM_SMS // 2 if pair else NUM_SMS
+    t_max = math.ceil(m_tiles * n_tiles / units)
+    kstep = max(bn * _C_MMA, (_C_FLOOR_P + _C_B_P * bn) if pair else (_C_FLOOR + _C_B * bn))
+    epi = _C_E0 + _C_E1 * per * (2.0 if geglu else 1.0) * (1.3 if has_res else 1.0)
+    return t_max * (k_iters * kstep + epi)
+
+
+def pick_config(rows: int, batches: int, n_out: int, k_per_tap: int, taps: int, geglu: bool, has_res: bool,
+                block_n: Optional[int] = None, cta_pair: Optional[bool] = None):
+    """(cta_pair, block_n) for a GEMM shape; explicit arguments are honoured."""
+    if block_n is None and cta_pair is None:
+        hit = TUNED.get((rows, n_out, k_per_tap, taps, int(geglu)))
+        if hit is not None:
+            return hit
+    k_iters = taps * k_per_tap // 64
     best = None
-    cands = [256, 192, 128, 64] if geglu else [256, 224, 192, 160, 128, 96, 64, 32]
-    for bn in cands:
-        per_tile_n = bn // 2 if geglu else bn
-        if per_tile_n > max(32, ((n_out + 31) // 32) * 32):
-            continue
-        n_tiles = math.ceil(n_out / per_tile_n)
-        tiles = m_tiles * n_tiles
-        waves = math.ceil(tiles / NUM_SMS)
-        # MMA time ~ bn per k-iteration; the epilogue (~bn columns of TMEM traffic) overlaps unless K is tiny;
-        # a fixed per-tile overhead covers pipeline fill/drain.
-        cost = waves * (k_iters * max(bn, 128) * 0.5 + 1.5 * bn + 200)
-        if best is None or cost < best[0] - 1e-9:
-            best = (cost, bn)
-    assert best is not None
-    return best[1]
+    for pair in ((False, True) if cta_pair is None else (bool(cta_pair),)):
+        cands = [256, 192, 128, 64] if geglu else [256, 224, 192, 160, 128, 96, 64, 32]
+        if block_n is not None:
+            cands = [block_n]
+        for bn in cands:
+            if pair and bn < 64:
+                continue
+            per = bn // 2 if geglu else bn
+            if block_n is None and per > max(64 if pair else 32, ((n_out + 31) // 32) * 32):
+                continue
+            c = tile_cost_ns(rows, batches, n_out, k_iters, geglu, has_res, pair, bn)
+            if best is None or c < best[0] - 1e-9:
+                best = (c, pair, bn)
+    if best is None:
+        return (bool(cta_pair), 64 if cta_pair else 32)
+    return best[1], best[2]
 
 
 class Gemm:
@@ -62,7 +120,8 @@ class Gemm:
                  res2: Optional[torch.Tensor] = None, res2_scale: float = 1.0,
                  out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_scale: float = 0.0,
                  halo: Optional[tuple] = None, ostride: int = 1, out_halo: bool = False,
-                 act_silu: bool = False, name: str = "gemm", alg_k: Optional[int] = None):
+                 act_silu: bool = False, name: str = "gemm", alg_k: Optional[int] = None,
+                 cta_pair: Optional[bool] = None):
         assert a0.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
         assert a0.dim() == 2 and w.dim() == 2 and a0.stride(1) == 1 and w.stride(1) == 1
         self.name = name
@@ -84,11 +143,11 @@ class Gemm:
         else:
             gate_off = 0
             n_out = w.shape[0] if n_out is None else n_out
-        m_tiles = batches * math.ceil(rpb / 128)
-        if block_n is None:
-            block_n = pick_block_n(m_tiles, n_out, geglu, ntaps * (k0 + k1) // 64)
+        cta_pair, block_n = pick_config(rows_total, batches, n_out, k0 + k1, ntaps, geglu,
+                                        res1 is not None or res2 is not None or out2 is not None, block_n, cta_pair)
+        self.cta_pair = bool(cta_pair)
         self.block_n = block_n
-        b_box_rows = block_n // 2 if geglu else block_n
+        b_box_rows = block_n // 2   # each CTA of a pair stages half of B; a single CTA issues two such loads
 
         self.tm_a0 = _lib.encode_tensormap(a0.data_ptr(), [k0, rpb, batches],
                                            [a0.stride(0) * 2, a0.stride(0) * 2 * rpb], [64, 128, 1])
@@ -163,6 +222,7 @@ class Gemm:
             a.map_mode = 0
             assert out_rows == rows_total
         a.act_silu = 1 if act_silu else 0
+        a.cta_pair = 1 if cta_pair else 0
         # algorithmic FLOPs (bench.py roofline): true output pixels x true (un-padded) K
         valid_rows = out_rows if not (halo is not None and out_halo) else n_img * a.oH * a.oW
         self.kind = "gemm"

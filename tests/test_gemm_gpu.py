@@ -28,16 +28,17 @@ def rnd(*shape, scale=1.0, dev="cuda"):
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (256, 128, 128, None), (1000, 320, 320, 160),
-                                      (5000, 1280, 640, 256), (333, 96, 192, 96), (4096, 640, 2560, None),
+                                      (5000, 1280, 640, 256), (333, 96, 192, 96), (80000, 320, 320, None), (4096, 640, 2560, None),
                                       (1260, 1280, 1280, None)])
-def test_linear(cuda_dev, M, N, K, bn):
+@pytest.mark.parametrize("pair", [False, True])
+def test_linear(cuda_dev, pair, M, N, K, bn):
     from posetraj_b200.ops import Gemm
     torch.manual_seed(0)
     a = rnd(M, K)
     w = rnd(N, K, scale=1 / math.sqrt(K))
     bias = torch.randn(N, device="cuda")
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    Gemm(a, w, out, bias=bias, block_n=bn).launch(sp())
+    Gemm(a, w, out, bias=bias, block_n=bn, cta_pair=pair).launch(sp())
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t() + bias
     assert rel_l2(out, ref) < TOL
@@ -57,7 +58,8 @@ def test_linear_f32_out_small_n(cuda_dev):
     assert rel_l2(out, ref) < 1e-4
 
 
-def test_epilogue_residual_rowvec_out2(cuda_dev):
+@pytest.mark.parametrize("pair", [False, True])
+def test_epilogue_residual_rowvec_out2(cuda_dev, pair):
     from posetraj_b200.ops import Gemm
     torch.manual_seed(2)
     groups, per = 4, 300
@@ -70,7 +72,7 @@ def test_epilogue_residual_rowvec_out2(cuda_dev):
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     out2 = torch.empty_like(out)
     Gemm(a, w, out, bias=bias, rowvec=rowvec, rowvec_mode=1, rv=(per, 1, 1), acc_scale=0.375,
-         res1=r1, res1_scale=1.0, res2=r2, res2_scale=0.625, out2=out2, aux=aux, aux_scale=3.0).launch(sp())
+         res1=r1, res1_scale=1.0, res2=r2, res2_scale=0.625, out2=out2, aux=aux, aux_scale=3.0, cta_pair=pair).launch(sp())
     torch.cuda.synchronize()
     core = a.float() @ w.float().t() + bias + rowvec.repeat_interleave(per, 0)
     ref = 0.375 * core + r1.float() + 0.625 * r2.float()
@@ -78,7 +80,8 @@ def test_epilogue_residual_rowvec_out2(cuda_dev):
     assert rel_l2(out2, ref + 3.0 * aux.float()) < TOL
 
 
-def test_rowvec_mode2(cuda_dev):
+@pytest.mark.parametrize("pair", [False, True])
+def test_rowvec_mode2(cuda_dev, pair):
     """Temporal cross-attention quirk: vector index ((row // (F*HW)) * HW + row % HW) % B."""
     from posetraj_b200.ops import Gemm
     torch.manual_seed(3)
@@ -88,7 +91,7 @@ def test_rowvec_mode2(cuda_dev):
     w = rnd(N, K, scale=1 / math.sqrt(K))
     rowvec = torch.randn(B, N, device="cuda")
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    Gemm(a, w, out, rowvec=rowvec, rowvec_mode=2, rv=(Fr * HW, HW, B)).launch(sp())
+    Gemm(a, w, out, rowvec=rowvec, rowvec_mode=2, rv=(Fr * HW, HW, B), cta_pair=pair).launch(sp())
     torch.cuda.synchronize()
     rows = torch.arange(M, device="cuda")
     g = ((rows // (Fr * HW)) * HW + rows % HW) % B
@@ -97,14 +100,15 @@ def test_rowvec_mode2(cuda_dev):
 
 
 @pytest.mark.parametrize("M,C,bn", [(512, 320, None), (2000, 640, 256), (700, 64, 64)])
-def test_geglu(cuda_dev, M, C, bn):
+@pytest.mark.parametrize("pair", [False, True])
+def test_geglu(cuda_dev, pair, M, C, bn):
     from posetraj_b200.ops import Gemm
     torch.manual_seed(4)
     a = rnd(M, C)
     w = rnd(8 * C, C, scale=1 / math.sqrt(C))
     bias = torch.randn(8 * C, device="cuda")
     out = torch.empty(M, 4 * C, device="cuda", dtype=torch.bfloat16)
-    Gemm(a, w, out, bias=bias, geglu=True, block_n=bn).launch(sp())
+    Gemm(a, w, out, bias=bias, geglu=True, block_n=bn, cta_pair=pair).launch(sp())
     torch.cuda.synchronize()
     h = a.float() @ w.float().t() + bias
     x, g = h.chunk(2, dim=-1)
@@ -112,14 +116,15 @@ def test_geglu(cuda_dev, M, C, bn):
     assert rel_l2(out, ref) < TOL
 
 
-def test_two_k_sources(cuda_dev):
+@pytest.mark.parametrize("pair", [False, True])
+def test_two_k_sources(cuda_dev, pair):
     from posetraj_b200.ops import Gemm
     torch.manual_seed(5)
     M, K0, K1, N = 900, 640, 320, 640
     a0, a1 = rnd(M, K0), rnd(M, K1)
     w = rnd(N, K0 + K1, scale=1 / math.sqrt(K0 + K1))
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    Gemm(a0, w, out, a1=a1).launch(sp())
+    Gemm(a0, w, out, a1=a1, cta_pair=pair).launch(sp())
     torch.cuda.synchronize()
     ref = torch.cat([a0, a1], 1).float() @ w.float().t()
     assert rel_l2(out, ref) < TOL
@@ -136,7 +141,8 @@ def halo_pack(x_nhwc):
 @pytest.mark.parametrize("n,H,W,Cin,Cout,stride", [(3, 10, 18, 64, 64, 1), (4, 20, 36, 320, 640, 1),
                                                    (5, 5, 9, 128, 192, 1), (3, 10, 18, 128, 128, 2),
                                                    (2, 40, 72, 64, 32, 1)])
-def test_conv3x3(cuda_dev, n, H, W, Cin, Cout, stride):
+@pytest.mark.parametrize("pair", [False, True])
+def test_conv3x3(cuda_dev, pair, n, H, W, Cin, Cout, stride):
     from posetraj_b200.ops import Gemm, conv3x3_taps
     torch.manual_seed(6)
     x = rnd(n, H, W, Cin)
@@ -146,7 +152,7 @@ def test_conv3x3(cuda_dev, n, H, W, Cin, Cout, stride):
     w2 = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
     oH, oW = (H + stride - 1) // stride, (W + stride - 1) // stride
     out = torch.zeros(n * oH * oW, Cout, device="cuda", dtype=torch.bfloat16)
-    Gemm(a, w2, out, taps=conv3x3_taps(W), bias=bias, halo=(H, W), ostride=stride).launch(sp())
+    Gemm(a, w2, out, taps=conv3x3_taps(W), bias=bias, halo=(H, W), ostride=stride, cta_pair=pair).launch(sp())
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=stride, padding=1)
     ref = ref.permute(0, 2, 3, 1).reshape(n * oH * oW, Cout)
@@ -154,7 +160,8 @@ def test_conv3x3(cuda_dev, n, H, W, Cin, Cout, stride):
 
 
 @pytest.mark.parametrize("B,Fr,HW,Cc", [(2, 14, 45, 128), (2, 5, 180, 320), (1, 3, 720, 64)])
-def test_temporal_conv(cuda_dev, B, Fr, HW, Cc):
+@pytest.mark.parametrize("pair", [False, True])
+def test_temporal_conv(cuda_dev, pair, B, Fr, HW, Cc):
     from posetraj_b200.ops import Gemm
     torch.manual_seed(7)
     x = rnd(B, Fr, HW, Cc)
@@ -164,7 +171,7 @@ def test_temporal_conv(cuda_dev, B, Fr, HW, Cc):
     a = x.reshape(B * Fr * HW, Cc)
     w2 = wt.permute(0, 2, 1).reshape(Cc, 3 * Cc).contiguous()
     out = torch.empty(B * Fr * HW, Cc, device="cuda", dtype=torch.bfloat16)
-    Gemm(a, w2, out, batches=B, taps=(-HW, 0, HW), bias=bias, res1=res).launch(sp())
+    Gemm(a, w2, out, batches=B, taps=(-HW, 0, HW), bias=bias, res1=res, cta_pair=pair).launch(sp())
     torch.cuda.synchronize()
     xr = x.float().permute(0, 3, 1, 2)  # [B, C, F, HW]
     ref = F.conv2d(xr, wt.float()[..., None], bias, padding=(1, 0))  # kernel (3,1) over (F, HW)
