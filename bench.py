@@ -200,24 +200,10 @@ def time_op_classes(step_ops, stream, reps: int = 2):
     return acc
 
 
-def _synthetic_condition(frames, H, W):
-    """One track, 14 points linearly from (100,80) to (460,240) px, drawn per frame transition as a
-    red 3-px segment + green end disc on black, frame F-1 black, scaled to [-1, 1] like VaeImageProcessor.preprocess."""
-    import torch
-    img = torch.zeros(frames, 3, H, W)
-    xs = torch.linspace(100, 460, frames)
-    ys = torch.linspace(80, 240, frames)
-    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
-    for k in range(frames - 1):
-        x0, y0, x1, y1 = xs[k], ys[k], xs[k + 1], ys[k + 1]
-        dx, dy = x1 - x0, y1 - y0
-        tt = (((xx - x0) * dx + (yy - y0) * dy) / (dx * dx + dy * dy)).clamp(0, 1)
-        dist = ((xx - (x0 + tt * dx)) ** 2 + (yy - (y0 + tt * dy)) ** 2).sqrt()
-        img[k, 0][dist <= 1.5] = 1.0
-        disc = ((xx - x1) ** 2 + (yy - y1) ** 2).sqrt() <= 3.0
-        img[k, 0][disc] = 0.0
-        img[k, 1][disc] = 1.0
-    return img * 2.0 - 1.0
+def _synthetic_tracks(frames):
+    """One track, `frames` points linearly from (100,80) to (460,240) px."""
+    return [[[int(round(100 + (460 - 100) * k / (frames - 1))), int(round(80 + (240 - 80) * k / (frames - 1)))]
+             for k in range(frames)]]
 
 
 def run_own(args):
@@ -252,9 +238,12 @@ def run_own(args):
     image_latents = torch.cat([torch.zeros_like(img), img]).pin_memory()
     emb = torch.randn(1, 1, cfg.cross_attention_dim, generator=g)
     image_embeddings = torch.cat([torch.zeros_like(emb), emb]).pin_memory()
-    cond = _synthetic_condition(FRAMES, H, W).pin_memory()   # [F,3,H,W] in [-1,1]
+    from posetraj_b200.trajectory import rasterize_tracks
+    tracks = torch.tensor(_synthetic_tracks(FRAMES), dtype=torch.int32).pin_memory()   # [K=1, F, 2] host
 
     def call_pipeline():
+        # R1 on the GPU: tracks (host) -> [F,3,H,W] conditioning maps in [-1,1] (cv2-exact), then the sampling loop
+        cond = rasterize_tracks(tracks, FRAMES, H, W, dev, output="f32")
         out = pipe(None, cond, height=H, width=W, num_frames=FRAMES, num_inference_steps=SAMPLING_STEPS,
                    latents=lat_unit, output_type="latent", image_embeddings=image_embeddings, image_latents=image_latents)
         return out.frames.to("cpu")
@@ -316,7 +305,7 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = world * n_calls * SAMPLING_STEPS / e2e_s
-    h2d = sum(x.numel() * x.element_size() for x in (cond, lat_unit, image_latents, image_embeddings)) + 26 * 4 + 2 * 3 * 4
+    h2d = sum(x.numel() * x.element_size() for x in (tracks, lat_unit, image_latents, image_embeddings)) + 26 * 4 + 2 * 3 * 4
     d2h = lat_final.numel() * lat_final.element_size()
 
     line = None
@@ -355,7 +344,7 @@ def run_own(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / SAMPLING_STEPS,
                     "d2h_bytes_per_step": d2h / SAMPLING_STEPS, "calls": n_calls,
-                    "api": "StableVideoDiffusionPipelineControlNet.__call__(host tensors, output_type='latent') + .cpu()",
+                    "api": "rasterize_tracks(host tracks) + StableVideoDiffusionPipelineControlNet.__call__(host tensors, output_type='latent') + .cpu()",
                     "videos_per_min": e2e_value * 60.0 / SAMPLING_STEPS},
             "gpu_launches": int(eng.launches_per_step * args.steps + 3 * ((args.steps + SAMPLING_STEPS - 1) // SAMPLING_STEPS)),
             "roofline": roofline,

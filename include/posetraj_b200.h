@@ -267,6 +267,23 @@ typedef struct PtLayoutArgs {
 int pt_nchw_to_tokens(const PtLayoutArgs* a, void* stream);
 int pt_tokens_to_nchw(const PtLayoutArgs* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* R1: trajectory maps (scripts/run_inference_vipseg_json_repro.py:438-449, utils/dataset.py:  */
+/* 741-766): per frame transition k a black canvas with, per track in order, cv2.line(p_k,     */
+/* p_k+1, BGR (0,0,255), thickness 3) and cv2.circle(p_k+1, 3, BGR (0,255,0), filled); then    */
+/* BGR->RGB, a black last frame and the pipeline's preprocess (x/255*2-1, :500).  Bit-exact    */
+/* against OpenCV's integer rasterisation.                                                     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct PtRasterArgs {
+  const int32_t* tracks;    /* device [K, F, 2] (x, y) pixel coordinates, already rescaled and int()-truncated */
+  int32_t K, F, H, W;
+  void* order;              /* workspace of pt_rasterize_workspace_bytes(F, H, W) bytes */
+  float* out_f32;           /* optional [F, 3, H, W] fp32 RGB in [-1, 1] (the pipeline's controlnet_condition) */
+  uint8_t* out_u8;          /* optional [F, H, W, 3] uint8 RGB (the PIL images the reference builds) */
+} PtRasterArgs;
+int pt_rasterize_tracks(const PtRasterArgs* a, void* stream);
+int64_t pt_rasterize_workspace_bytes(int32_t F, int32_t H, int32_t W);
+
 #ifdef __cplusplus
 }
 #endif

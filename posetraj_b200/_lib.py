@@ -117,6 +117,9 @@ PtLayoutArgs = _st("PtLayoutArgs", [
     ("n", i32), ("C", i32), ("H", i32), ("W", i32), ("ld", i32), ("halo", i32), ("nchw_f32", i32)])
 
 
+PtRasterArgs = _st("PtRasterArgs", [
+    ("tracks", vp), ("K", i32), ("F", i32), ("H", i32), ("W", i32), ("order", vp), ("out_f32", vp), ("out_u8", vp)])
+
 PT_DT_BF16 = 0
 PT_DT_F32 = 1
 
@@ -142,6 +145,8 @@ _SIGNATURES = {
     "pt_conv3x3_direct": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_nchw_to_tokens": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_tokens_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_rasterize_tracks": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_rasterize_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
 }
 
 _lib = None

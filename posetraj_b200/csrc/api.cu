@@ -106,5 +106,6 @@ extern "C" int pt_sizeof(const char* name) {
   if (!strcmp(name, "PtUpsampleArgs")) return (int)sizeof(PtUpsampleArgs);
   if (!strcmp(name, "PtConvDirectArgs")) return (int)sizeof(PtConvDirectArgs);
   if (!strcmp(name, "PtLayoutArgs")) return (int)sizeof(PtLayoutArgs);
+  if (!strcmp(name, "PtRasterArgs")) return (int)sizeof(PtRasterArgs);
   return -1;
 }
