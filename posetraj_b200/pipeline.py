@@ -82,6 +82,9 @@ class DenoiseEngine:
             plan.ehs.copy_(image_embeddings[:, 0, :])
             plan.time_ids.copy_(added_time_ids.reshape(-1))
             NetPlan.run(plan.embed_ops, sp)
+        # once per video: always re-run the conditioning embedding (a pointer/version cache key could alias a new
+        # tensor that the caching allocator placed at the same address)
+        self.cplan._cond_key = None
         self.controlnet.stage_condition(self.cplan, controlnet_condition, camera_cond, None, sp)
         self.cplan.set_conditioning_scale(cond_scale)
         self.prepare_op.launch(sp)
