@@ -69,6 +69,8 @@ typedef struct PtCfgEulerArgs {
   int32_t next_padded;      /* 1: rows laid out with one zero column/row per image ((H+1)*(W+1) rows/image) */
   int32_t mode;             /* 0: full step (update latents, next_in uses sigma[i+1]); 1: only build next_in for sigma[i] */
   int32_t single_pred;      /* 1: noise_pred holds ONE already-combined prediction [F,...] (plain scheduler.step) */
+  int32_t row_begin;        /* next_in receives the model-input rows [row_begin, row_begin + row_count) of the CFG pair, */
+  int32_t row_count;        /* packed from row 0 of next_in (CFG-branch sharding); row_count 0 means both rows */
 } PtCfgEulerArgs;
 int pt_cfg_euler_step(const PtCfgEulerArgs* a, void* stream);
 /* *step_index += 1 (stream-ordered, so a captured CUDA graph of one step can be replayed) */

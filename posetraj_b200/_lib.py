@@ -33,6 +33,8 @@ class PtCfgEulerArgs(C.Structure):
         ("next_padded", C.c_int32),
         ("mode", C.c_int32),
         ("single_pred", C.c_int32),
+        ("row_begin", C.c_int32),
+        ("row_count", C.c_int32),
     ]
 
 

@@ -22,7 +22,7 @@ struct CfgEulerParams {
   int F, C, H, W;
   bf16* next_in;
   const float* image_latents;
-  int next_ld, next_padded, mode, single_pred;
+  int next_ld, next_padded, mode, single_pred, row_begin, row_count;
 };
 
 // one thread per (f, y, x); C (= 4) channels handled in a short loop
@@ -70,12 +70,13 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const CfgEulerParams p) 
     const float inv = 1.0f / sqrtf(s_in * s_in + 1.0f);
     const int y = pix / p.W;
     const int xq = pix - y * p.W;
-    for (int b = 0; b < 2; ++b) {
+    for (int b = p.row_begin; b < p.row_begin + p.row_count; ++b) {
+      const int lb = b - p.row_begin;  // row inside next_in (a shard holds only its own rows)
       size_t row;
       if (p.next_padded) {
-        row = (size_t)(b * p.F + f) * ((p.H + 1) * (p.W + 1)) + (size_t)y * (p.W + 1) + xq;
+        row = (size_t)(lb * p.F + f) * ((p.H + 1) * (p.W + 1)) + (size_t)y * (p.W + 1) + xq;
       } else {
-        row = (size_t)(b * p.F + f) * HW + pix;
+        row = (size_t)(lb * p.F + f) * HW + pix;
       }
       bf16* o = p.next_in + row * p.next_ld;
       for (int c = 0; c < p.C; ++c) {
@@ -116,6 +117,9 @@ extern "C" int pt_cfg_euler_step(const PtCfgEulerArgs* a, void* stream) {
   p.next_padded = a->next_padded;
   p.mode = a->mode;
   p.single_pred = a->single_pred;
+  p.row_begin = a->row_count > 0 ? a->row_begin : 0;
+  p.row_count = a->row_count > 0 ? a->row_count : 2;
+  PT_CHECK_ARG(p.row_begin >= 0 && p.row_begin + p.row_count <= 2, "pt_cfg_euler_step: row window must lie inside the CFG pair");
   const int total = a->F * a->H * a->W;
   cfg_euler_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
   return pt_launched("pt_cfg_euler_step");

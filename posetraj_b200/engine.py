@@ -137,11 +137,19 @@ class NetPlan:
     def __init__(self, kind: str, cfg: SVDConfig, weights: WeightStore, *, batch: int, frames: int, height: int,
                  width: int, device, cam: bool = False, bbox: bool = False, cond_hw: Optional[tuple] = None,
                  sigmas: Optional[torch.Tensor] = None, step_index: Optional[torch.Tensor] = None,
-                 x_in: Optional[torch.Tensor] = None, residual_bufs: Optional[List[torch.Tensor]] = None):
+                 x_in: Optional[torch.Tensor] = None, residual_bufs: Optional[List[torch.Tensor]] = None,
+                 ctx_batch: Optional[int] = None, row_offset: int = 0):
         assert kind in ("unet", "controlnet")
         self.kind, self.cfg, self.w = kind, cfg, weights
         self.B, self.F, self.H, self.W = batch, frames, height, width
         self.n = batch * frames
+        # CFG-branch sharding: this plan computes rows [row_offset, row_offset + batch) of a call whose
+        # full batch is ctx_batch.  Activations never cross rows, but the 1-token cross-attention constants do
+        # (fact 11), so every shard keeps ALL ctx_batch image embeddings.
+        self.ctx_B = ctx_batch if ctx_batch is not None else batch
+        self.row_offset = row_offset
+        if row_offset + batch > self.ctx_B:
+            raise ValueError("row_offset + batch exceeds ctx_batch")
         self.device = device
         self.cam, self.bbox = cam, bbox
         self.pool = Pool(device)
@@ -157,7 +165,7 @@ class NetPlan:
         P0 = (height + 1) * (width + 1)
         self.cin_pad = _pad64(cfg.in_channels)
         self.x_in = x_in if x_in is not None else torch.zeros(self.n * P0, self.cin_pad, device=device, dtype=BF16)
-        self.ehs = torch.zeros(batch, cfg.cross_attention_dim, device=device, dtype=F32)
+        self.ehs = torch.zeros(self.ctx_B, cfg.cross_attention_dim, device=device, dtype=F32)
         self.time_ids = torch.zeros(batch * 3, device=device, dtype=F32)
         self.t_buf = torch.zeros(batch, device=device, dtype=F32)
         self.sigmas, self.step_index = sigmas, step_index
@@ -313,7 +321,7 @@ class NetPlan:
 
     def _xvec(self, attn_prefix: str, Cc: int) -> torch.Tensor:
         """Constant of the degenerate 1-token cross-attention: to_out(to_v(e_b)) + bias, fp32 [B, C]."""
-        w, dev, B = self.w, self.device, self.B
+        w, dev, B = self.w, self.device, self.ctx_B
         tmp = torch.zeros(B, Cc, device=dev, dtype=F32)
         vec = torch.zeros(B, Cc, device=dev, dtype=F32)
         self.embed_ops.append(ops.SmallLinear(self.ehs, w.linear(attn_prefix + "to_v.weight"), tmp, None,
@@ -344,8 +352,19 @@ class NetPlan:
         HW = H * W
         Cc = x.shape[1]
         sb, tb = prefix + "transformer_blocks.0.", prefix + "temporal_transformer_blocks.0."
-        xvec_s = self._xvec(sb + "attn2.", Cc)
+        xvec_s = self._xvec(sb + "attn2.", Cc)[self.row_offset: self.row_offset + B]
         xvec_t = self._xvec(tb + "attn2.", Cc)
+        rv_t = (Fr * HW, HW, self.ctx_B)
+        if self.ctx_B != B:
+            # hidden row (b, s) of the FULL batch gets the vector of batch ((b*HW + s) mod ctx_B); with only rows
+            # [row_offset, ...) present the kernel sees local b, so pre-rotate the table by row_offset*HW instead
+            if B != 1:
+                raise ValueError("row sharding of the temporal context is implemented for one row per shard")
+            rot = torch.zeros_like(xvec_t)
+            src, shift, nb = xvec_t, (self.row_offset * HW) % self.ctx_B, self.ctx_B
+            self.embed_ops.append(ops.TorchOp(lambda s=src, d=rot, k=shift: d.copy_(torch.roll(s, -k, 0)),
+                                              name=tb + "attn2.rotate"))
+            xvec_t = rot
         pos = self._frame_pos_emb(prefix, Cc)
         g = self._gn(x, None, prefix + "norm", rows_per_stat=HW, eps=1e-6, silu=False)
         h = self._gemm(g, w.linear(prefix + "proj_in.weight"), Cc, bias=w.f32(prefix + "proj_in.bias"), name=prefix + "proj_in")
@@ -383,7 +402,7 @@ class NetPlan:
         self.step_ops.append(ops.AttnTemporal(qkv_t, att_t, batch=B, frames=Fr, hw=HW, heads=heads, name=tb + "attn1"))
         self.pool.put(qkv_t)
         t2 = self._gemm(att_t, w.linear(tb + "attn1.to_out.0.weight"), Cc, bias=w.f32(tb + "attn1.to_out.0.bias"), res1=t1,
-                        rowvec=xvec_t, rowvec_mode=2, rv=(Fr * HW, HW, B), name=tb + "attn1.to_out")
+                        rowvec=xvec_t, rowvec_mode=2, rv=rv_t, name=tb + "attn1.to_out")
         self.pool.put(att_t, t1)
         l3t = self._ln(t2, tb + "norm3")
         f2 = self._gemm(l3t, w.linear(tb + "ff.net.0.proj.weight"), 4 * Cc, geglu=True, bias=w.f32(tb + "ff.net.0.proj.bias"),

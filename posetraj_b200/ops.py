@@ -245,7 +245,7 @@ class CfgEuler:
     def __init__(self, *, noise_pred: Optional[torch.Tensor], latents: torch.Tensor, guidance: torch.Tensor,
                  sigmas: torch.Tensor, step_index: torch.Tensor, next_in: Optional[torch.Tensor] = None,
                  image_latents: Optional[torch.Tensor] = None, next_padded: bool = True, mode: int = 0,
-                 pred_nchw_f32: bool = False, single_pred: bool = False):
+                 pred_nchw_f32: bool = False, single_pred: bool = False, row_begin: int = 0, row_count: int = 2):
         F_, Cc, H, W = latents.shape[-4:]
         assert latents.dtype == torch.float32 and latents.is_contiguous()
         assert guidance.dtype == torch.float32 and sigmas.dtype == torch.float32 and step_index.dtype == torch.int32
@@ -271,6 +271,7 @@ class CfgEuler:
             a.next_padded = 1 if next_padded else 0
         a.mode = mode
         a.single_pred = 1 if single_pred else 0
+        a.row_begin, a.row_count = row_begin, row_count
         self.kind = "cfg_euler"
         self.name = "pt_cfg_euler_step"
         self.alg_flops = 0.0
@@ -479,6 +480,17 @@ class Layout(_Op):
         rows = a.n * ((a.H + 1) * (a.W + 1) if halo else a.H * a.W)
         assert tokens.shape[0] == rows and tokens.shape[1] >= a.C
         self._finish(a, (nchw, tokens), name)
+
+
+class TorchOp:
+    """A tiny torch-side op inside an op list that is replayed OUTSIDE the per-step graph (embedding staging)."""
+    kind, alg_flops, alg_bytes = "misc", 0.0, 0.0
+
+    def __init__(self, fn, name="torch_op"):
+        self.fn, self.name = fn, name
+
+    def launch(self, stream_ptr: int) -> None:
+        self.fn()
 
 
 class StepAdvance:

@@ -45,12 +45,20 @@ def _get_add_time_ids(noise_aug_strength, dtype, batch_size, fps=4, motion_bucke
 
 
 class DenoiseEngine:
-    """One video's denoise loop: both network plans wired to shared buffers + the fused scheduler kernel."""
+    """One video's denoise loop: both network plans wired to shared buffers + the fused scheduler kernel.
+
+    `rows=(begin, count)` selects which rows of the CFG pair this process computes (CFG-branch
+    sharding): (0, 2) is the whole pair on one GPU; (r, 1) with a 2-rank `group` runs one branch per GPU, all-gathers
+    the two 161 KB noise predictions every step and lets both ranks redo the (2 MB) CFG + Euler update."""
 
     def __init__(self, unet: UNetSpatioTemporalConditionControlNetModel, controlnet: ControlNetSDVModel,
-                 scheduler: EulerDiscreteScheduler, *, frames: int, h: int, w: int, cond_hw: tuple, device):
+                 scheduler: EulerDiscreteScheduler, *, frames: int, h: int, w: int, cond_hw: tuple, device,
+                 rows: tuple = (0, 2), group=None):
         self.unet, self.controlnet, self.scheduler = unet, controlnet, scheduler
         self.F, self.h, self.w, self.device = frames, h, w, device
+        self.row_begin, self.row_count = rows
+        self.group = group
+        self.split = self.row_count != 2
         cfg = unet.cfg
         self.latents = torch.zeros(frames, cfg.out_channels, h, w, device=device, dtype=F32)
         self.image_latents = torch.zeros(2, frames, cfg.out_channels, h, w, device=device, dtype=F32)
@@ -58,13 +66,22 @@ class DenoiseEngine:
         self.step_index = torch.zeros(1, device=device, dtype=torch.int32)
         self.sigmas = torch.zeros(1024, device=device, dtype=F32)
         kw = dict(sigmas=self.sigmas, step_index=self.step_index)
-        self.cplan: NetPlan = controlnet.plan_for(2, frames, h, w, cond_hw=cond_hw, **kw)
-        self.uplan: NetPlan = unet.plan_for(2, frames, h, w, x_in=self.cplan.x_in, residual_bufs=self.cplan.res, **kw)
+        if self.split:
+            kw.update(ctx_batch=2, row_offset=self.row_begin)
+        self.cplan: NetPlan = controlnet.plan_for(self.row_count, frames, h, w, cond_hw=cond_hw, **kw)
+        self.uplan: NetPlan = unet.plan_for(self.row_count, frames, h, w, x_in=self.cplan.x_in,
+                                            residual_bufs=self.cplan.res, **kw)
+        # the prediction of the whole pair: the UNet plan's own buffer, or the all-gather target when sharded
+        self.pred_all = self.uplan.noise_pred if not self.split else torch.zeros(
+            2 * frames * h * w, cfg.out_channels, device=device, dtype=BF16)
         common = dict(latents=self.latents, guidance=self.guidance, sigmas=self.sigmas, step_index=self.step_index,
-                      next_in=self.cplan.x_in, image_latents=self.image_latents, next_padded=True)
+                      next_in=self.cplan.x_in, image_latents=self.image_latents, next_padded=True,
+                      row_begin=self.row_begin, row_count=self.row_count)
         self.prepare_op = ops.CfgEuler(noise_pred=None, mode=1, **common)
-        self.update_op = ops.CfgEuler(noise_pred=self.uplan.noise_pred, mode=0, **common)
-        self.step_ops = self.cplan.step_ops + self.uplan.step_ops + [self.update_op, ops.StepAdvance(self.step_index)]
+        self.update_op = ops.CfgEuler(noise_pred=self.pred_all, mode=0, **common)
+        self.net_ops = self.cplan.step_ops + self.uplan.step_ops
+        self.tail_ops = [self.update_op, ops.StepAdvance(self.step_index)]
+        self.step_ops = self.net_ops + self.tail_ops
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = len(self.step_ops) + sum(1 for o in self.step_ops if isinstance(o, ops.GroupNorm))
 
@@ -72,6 +89,7 @@ class DenoiseEngine:
              controlnet_condition, camera_cond=None, cond_scale: float = 1.0) -> None:
         """Stage one video's inputs (host->device copies happen here) and run the step-invariant prologue."""
         sp = torch.cuda.current_stream().cuda_stream
+        rb, rc = self.row_begin, self.row_count
         self.latents.copy_(latents.reshape(self.latents.shape))
         self.image_latents.copy_(image_latents.reshape(self.image_latents.shape))
         self.guidance.copy_(guidance.reshape(-1))
@@ -79,13 +97,14 @@ class DenoiseEngine:
         self.sigmas[:n].copy_(sigmas)
         self.step_index.zero_()
         for plan in (self.cplan, self.uplan):
-            plan.ehs.copy_(image_embeddings[:, 0, :])
-            plan.time_ids.copy_(added_time_ids.reshape(-1))
+            plan.ehs.copy_(image_embeddings[:, 0, :])            # every shard keeps ALL rows' embeddings (fact 11)
+            plan.time_ids.copy_(added_time_ids[rb:rb + rc].reshape(-1))
             NetPlan.run(plan.embed_ops, sp)
         # once per video: always re-run the conditioning embedding (a pointer/version cache key could alias a new
         # tensor that the caching allocator placed at the same address)
         self.cplan._cond_key = None
-        self.controlnet.stage_condition(self.cplan, controlnet_condition, camera_cond, None, sp)
+        self.controlnet.stage_condition(self.cplan, controlnet_condition[rb:rb + rc],
+                                        None if camera_cond is None else camera_cond[rb:rb + rc], None, sp)
         self.cplan.set_conditioning_scale(cond_scale)
         self.prepare_op.launch(sp)
         self._latents0 = self.latents.clone()
@@ -96,15 +115,30 @@ class DenoiseEngine:
         self.step_index.zero_()
         self.prepare_op.launch(torch.cuda.current_stream().cuda_stream)
 
-    def step(self) -> None:
+    def _exchange(self) -> None:
+        """CFG-branch sharding: all-gather the two branches' predictions (rank == row of the CFG pair)."""
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.pred_all, self.uplan.noise_pred, group=self.group)
+
+    def step(self, use_graph: bool = True) -> None:
         """One denoise step (all kernels of ControlNet + UNet + CFG/Euler)."""
-        if self.graph is not None:
-            self.graph.replay()
+        sp = torch.cuda.current_stream().cuda_stream
+        if not self.split:
+            if use_graph and self.graph is not None:
+                self.graph.replay()
+            else:
+                NetPlan.run(self.step_ops, sp)
+            return
+        if use_graph and self.graph is not None:
+            self.graph.replay()                      # the two networks (this rank's branch)
         else:
-            NetPlan.run(self.step_ops, torch.cuda.current_stream().cuda_stream)
+            NetPlan.run(self.net_ops, sp)
+        self._exchange()
+        NetPlan.run(self.tail_ops, sp)
 
     def capture(self) -> None:
-        """Capture the per-step kernel sequence into a CUDA graph (call after at least one eager step)."""
+        """Capture the per-step kernel sequence into a CUDA graph (call after at least one eager step).  When
+        sharded only the network part is captured; the NCCL exchange and the 2 tail kernels stay eager."""
         if self.graph is not None:
             return
         saved = self.step_index.clone(), self.latents.clone(), self.cplan.x_in.clone()
@@ -113,7 +147,7 @@ class DenoiseEngine:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             with torch.cuda.graph(g, stream=s):
-                NetPlan.run(self.step_ops, torch.cuda.current_stream().cuda_stream)
+                NetPlan.run(self.net_ops if self.split else self.step_ops, torch.cuda.current_stream().cuda_stream)
         torch.cuda.current_stream().wait_stream(s)
         # capture does not execute, but keep state exactly as before anyway
         self.step_index.copy_(saved[0]); self.latents.copy_(saved[1]); self.cplan.x_in.copy_(saved[2])
@@ -134,6 +168,15 @@ class StableVideoDiffusionPipelineControlNet:
         self._guidance_scale = None
         self._num_timesteps = 0
         self.use_cuda_graph = True
+        self._cfg_rows = (0, 2)
+        self._cfg_group = None
+
+    def enable_cfg_split(self, rank: int, group=None) -> None:
+        """Run one branch of the CFG pair per GPU (2 ranks of `group`, rank == row: 0 uncond, 1 cond)."""
+        if rank not in (0, 1):
+            raise ValueError("CFG split runs on exactly 2 ranks")
+        self._cfg_rows, self._cfg_group = (rank, 1), group
+        self._engines.clear()
 
     @property
     def guidance_scale(self):
@@ -166,10 +209,11 @@ class StableVideoDiffusionPipelineControlNet:
         return latents * self.scheduler.init_noise_sigma
 
     def engine_for(self, frames, h, w, cond_hw) -> DenoiseEngine:
-        key = (frames, h, w, tuple(cond_hw))
+        key = (frames, h, w, tuple(cond_hw), self._cfg_rows)
         if key not in self._engines:
             self._engines[key] = DenoiseEngine(self.unet, self.controlnet, self.scheduler, frames=frames, h=h, w=w,
-                                               cond_hw=cond_hw, device=self._execution_device)
+                                               cond_hw=cond_hw, device=self._execution_device, rows=self._cfg_rows,
+                                               group=self._cfg_group)
         return self._engines[key]
 
     @torch.no_grad()
@@ -245,10 +289,7 @@ class StableVideoDiffusionPipelineControlNet:
         for i, t in enumerate(timesteps):
             if use_graph and i == 1:
                 eng.capture()
-            if use_graph and i >= 1:
-                eng.graph.replay()
-            else:
-                NetPlan.run(eng.step_ops, torch.cuda.current_stream().cuda_stream)
+            eng.step(use_graph=use_graph and i >= 1)
             if callback_on_step_end is not None:
                 cb_latents = eng.latents.view(1, num_frames, -1, h, w)
                 out = callback_on_step_end(self, i, t, {"latents": cb_latents})

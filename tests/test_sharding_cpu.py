@@ -1,0 +1,91 @@
+"""Host-side multi-GPU logic on CPU: partition math and a world_size-2 gloo run of the collectives the N>1 path uses
+(SURVEY.md §8e).  The GPU side is tests/test_sharding_gpu.py (needs 2 GPUs)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_video_shard_partitions_exactly():
+    from posetraj_b200.sharding import video_shard
+    for n in (0, 1, 7, 8, 9, 64):
+        for world in (1, 2, 4, 8):
+            got = [i for r in range(world) for i in video_shard(n, r, world)]
+            assert got == list(range(n))
+            sizes = [len(video_shard(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        video_shard(4, 2, 2)
+
+
+def test_frame_shards_ragged():
+    from posetraj_b200.sharding import frame_shards
+    assert frame_shards(25, 8) == [(0, 4), (4, 3), (7, 3), (10, 3), (13, 3), (16, 3), (19, 3), (22, 3)]
+    assert frame_shards(14, 2) == [(0, 7), (7, 7)]
+    assert sum(c for _, c in frame_shards(25, 4)) == 25
+
+
+def test_temporal_context_rotation_matches_reference_indexing():
+    """hidden row (b, s) <- context of batch (b*HW + s) mod B (models/modified_svd.py:152-159 vs :64-66)."""
+    from posetraj_b200.sharding import temporal_context_rotation
+    B = 2
+    for hw in (2880, 720, 180, 45):
+        for row in range(B):
+            rot = temporal_context_rotation(row, hw, B)
+            for s in (0, 1, 2, 43, 44):
+                assert (0 * hw + s + rot) % B == (row * hw + s) % B     # local row 0 + rotation == global indexing
+    assert temporal_context_rotation(1, 45) == 1 and temporal_context_rotation(1, 2880) == 0
+
+
+def test_cfg_split_ranks():
+    from posetraj_b200.sharding import cfg_split_ranks
+    assert cfg_split_ranks(8) == [(0, 1), (2, 3), (4, 5), (6, 7)]
+    with pytest.raises(ValueError):
+        cfg_split_ranks(3)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from posetraj_b200.sharding import gather_latents, max_over_ranks, video_shard
+    vids = list(video_shard(5, rank, world))
+    # pretend-denoise: each rank's "latents" encode the video ids it owns (pad to equal length for the gather)
+    lat = torch.full((3, 2, 4, 2, 2), -1.0)
+    for i, v in enumerate(vids):
+        lat[i] = float(v)
+    allv = gather_latents(lat)
+    ids = sorted(int(x) for x in allv[:, 0, 0, 0, 0].tolist() if x >= 0)
+    t = max_over_ranks(10.0 + rank)
+    # the CFG exchange: all_gather_into_tensor of one row per rank reproduces the [2, ...] prediction
+    pred = torch.full((6, 4), float(rank))
+    both = torch.empty(12, 4)
+    dist.all_gather_into_tensor(both, pred)
+    q.put((rank, ids, t, both[:6].mean().item(), both[6:].mean().item()))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_collectives():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ids, t, m0, m1 in res:
+        assert ids == [0, 1, 2, 3, 4]
+        assert t == 11.0                     # max over ranks
+        assert (m0, m1) == (0.0, 1.0)        # rank r's row lands in slot r
