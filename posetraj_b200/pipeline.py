@@ -118,7 +118,14 @@ class DenoiseEngine:
     def _exchange(self) -> None:
         """CFG-branch sharding: all-gather the two branches' predictions (rank == row of the CFG pair)."""
         import torch.distributed as dist
-        dist.all_gather_into_tensor(self.pred_all, self.uplan.noise_pred, group=self.group)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(self.pred_all, self.uplan.noise_pred, group=self.group)
+        else:
+            # host-staged exchange for non-NCCL process groups (gloo: two test ranks sharing one GPU)
+            mine = self.uplan.noise_pred.cpu()
+            parts = [torch.empty_like(mine) for _ in range(2)]
+            dist.all_gather(parts, mine, group=self.group)
+            self.pred_all.copy_(torch.cat(parts, 0))
 
     def step(self, use_graph: bool = True) -> None:
         """One denoise step (all kernels of ControlNet + UNet + CFG/Euler)."""
