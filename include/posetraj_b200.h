@@ -146,8 +146,9 @@ typedef struct PtGroupNormArgs {
   int32_t rows_per_stat;    /* rows sharing statistics: H*W (per frame) or F*H*W (TemporalResnetBlock) */
   int32_t num_stat;         /* number of statistics groups: B*F or B */
   void* stats;              /* workspace of pt_groupnorm_workspace_bytes() bytes, ZERO-INITIALISED ONCE by the caller (it
-                             * holds ticket counters the kernel re-arms): per-CTA fp64 partial sums folded in a fixed
-                             * order (no floating-point atomics: two runs of the same input are bit-identical) */
+                             * holds rendezvous counters the kernel re-arms): per-CTA fp64 partial sums folded in a
+                             * fixed order (no floating-point atomics: two runs of the same input are bit-identical).
+                             * One launch: statistics and normalisation share a co-resident grid. */
   const float* gamma;       /* [c0+c1] */
   const float* beta;
   float eps;

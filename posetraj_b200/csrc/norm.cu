@@ -17,15 +17,16 @@
 namespace pt {
 
 // ---------------------------------------------------------------------------------------------------------
-// GroupNorm statistics: per-CTA partial sum / sum of squares per (stat group s, split, norm group g); the CTA that
-// finishes last for a statistics group (ticket counter) folds the partials IN A FIXED ORDER into mean / rstd.
-// Deterministic on purpose: no floating-point atomics anywhere, so two runs of the same step are bit-identical
-// (a 1-ulp wobble in a mean flips bf16 roundings downstream and decorrelates whole runs).
-// Workspace layout: uint32 tickets[<= 1024] in a reserved first 4 KiB (zero before the first launch; the kernel
-// re-arms them, and no other region ever overlaps them even when differently shaped problems share one workspace)
-// | float mean_rstd[num_stat*64] | double partials[num_stat*splits*64].
+// GroupNorm (+SiLU) in ONE launch: every CTA reduces its slab of rows to per-group partial sums, publishes them,
+// waits until the other CTAs of the same statistics group have published theirs (the grid is sized to be fully
+// co-resident, so the wait cannot deadlock), folds all partials in a fixed order and normalises the slab it has just
+// read — the second read hits the L2.  HBM traffic: numel*2 B in + out rows*C*2 B out.
+// Deterministic on purpose: no floating-point atomics, every reduction in a fixed order, so two runs of the same
+// step are bit-identical (a 1-ulp wobble in a mean flips bf16 roundings downstream and decorrelates whole runs).
+// Workspace: uint32 arrive[1024] | uint32 depart[1024] (zero before the first launch; the kernel re-arms them)
+//            | double partials[num_stat*splits*64].
 // ---------------------------------------------------------------------------------------------------------
-struct GnStatsParams {
+struct GnParams {
   const bf16* x0;
   const bf16* x1;
   int c0, c1, ld0, ld1;
@@ -33,14 +34,21 @@ struct GnStatsParams {
   int num_stat;       // number of statistics groups (B*F or B)
   int splits;         // CTAs per statistics group
   double* partials;   // [num_stat, splits, 32, 2]
-  float* mean_rstd;   // [num_stat, 32, 2]
-  unsigned int* tickets;  // [num_stat]
+  unsigned int* arrive;  // [num_stat]
+  unsigned int* depart;  // [num_stat]
+  const float* gamma;
+  const float* beta;
   float eps;
+  int silu;
+  bf16* out;
+  int out_ld;
+  int halo;  // 1: out rows are the zero-haloed image space; an image is H x W with H*W dividing rows_per_stat
+  int H, W;
 };
 
-__global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
+__global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   extern __shared__ float s_red[];  // [rpar][C] sums, [rpar][C] squares, then [C] + [C] per-channel totals
-  __shared__ unsigned int s_ticket;
+  __shared__ float s_mean[32], s_rstd[32];
   const int C = p.c0 + p.c1;
   const int cvec = C >> 3;            // threads along channels (8 channels each)
   const int rpar = blockDim.x / cvec; // row lanes
@@ -48,6 +56,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
   const int tr = threadIdx.x / cvec;
   const int stat = blockIdx.x / p.splits;
   const int split = blockIdx.x - stat * p.splits;
+  const int cg = C >> 5;
   const int c = tc * 8;
   const bf16* src;
   int ld;
@@ -61,35 +70,38 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
   const int rows_per_split = (p.rows_per_stat + p.splits - 1) / p.splits;
   const int r_begin = split * rows_per_split;
   const int r_end = min(p.rows_per_stat, r_begin + rows_per_split);
+  const bf16* base = src + (size_t)stat * p.rows_per_stat * ld;
+
+  // ---------------- phase 1: partial statistics of this CTA's rows ----------------
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-  const bf16* base = src + (size_t)stat * p.rows_per_stat * ld;
-  int r = r_begin + tr;
-  // 4 independent 16-byte loads in flight per thread
-  for (; r + 3 * rpar < r_end; r += 4 * rpar) {
-    uint4 u[4];
+  {
+    int r = r_begin + tr;
+    for (; r + 3 * rpar < r_end; r += 4 * rpar) {  // 4 independent 16-byte loads in flight per thread
+      uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = ldg_nc_u4(base + (size_t)(r + k * rpar) * ld);
+      for (int k = 0; k < 4; ++k) u[k] = ldg_u4(base + (size_t)(r + k * rpar) * ld);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), cc = unpack_bf16x2(u[k].z), d = unpack_bf16x2(u[k].w);
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), cc = unpack_bf16x2(u[k].z), d = unpack_bf16x2(u[k].w);
+        const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sum[j] += v[j];
+          sq[j] = fmaf(v[j], v[j], sq[j]);
+        }
+      }
+    }
+    for (; r < r_end; r += rpar) {
+      const uint4 u = ldg_u4(base + (size_t)r * ld);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
       const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         sum[j] += v[j];
         sq[j] = fmaf(v[j], v[j], sq[j]);
       }
-    }
-  }
-  for (; r < r_end; r += rpar) {
-    const uint4 u = ldg_nc_u4(base + (size_t)r * ld);
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sum[j] += v[j];
-      sq[j] = fmaf(v[j], v[j], sq[j]);
     }
   }
   float* s_sum = s_red;
@@ -112,7 +124,6 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
     c_sq[ch] = b;
   }
   __syncthreads();
-  const int cg = C >> 5;
   if (threadIdx.x < 32) {
     double a = 0.0, b = 0.0;
     for (int i = 0; i < cg; ++i) {
@@ -125,12 +136,20 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
     __threadfence();
   }
   __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[stat], 1u);
+
+  // ---------------- rendezvous of the CTAs of this statistics group ----------------
+  if (threadIdx.x == 0) {
+    atomicAdd(&p.arrive[stat], 1u);
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(&p.arrive[stat]) < (unsigned)p.splits) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) asm volatile("trap;");  // a sizing bug becomes an error, not a hung GPU
+    }
+    __threadfence();
+  }
   __syncthreads();
-  if (s_ticket != (unsigned)(p.splits - 1)) return;
-  // last CTA of this statistics group: fixed-order fp64 fold of all partials -> mean, rstd.  The fold is spread
-  // over blockDim/64 slices with 4 loads in flight each (a serial chain of up to ~300 L2 round trips otherwise).
-  __threadfence();
+
+  // ---------------- fixed-order fp64 fold of all partials (identical in every CTA of the group) ----------------
   double* s_part = reinterpret_cast<double*>(s_red);  // [nsl][64], reuses the reduction scratch (>= 4 KiB)
   int nsl = blockDim.x >> 6;
   if (nsl > 8) nsl = 8;
@@ -158,50 +177,19 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const GnStatsParams p) {
     const double m = a / cnt;
     double var = b / cnt - m * m;
     if (var < 0) var = 0;
-    p.mean_rstd[((size_t)stat * 32 + threadIdx.x) * 2] = (float)m;
-    p.mean_rstd[((size_t)stat * 32 + threadIdx.x) * 2 + 1] = rsqrtf((float)var + p.eps);
-    if (threadIdx.x == 0) p.tickets[stat] = 0u;  // re-arm for the next launch
+    s_mean[threadIdx.x] = (float)m;
+    s_rstd[threadIdx.x] = rsqrtf((float)var + p.eps);
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// GroupNorm apply (+SiLU), optional concat input, optional zero-haloed output
-// ---------------------------------------------------------------------------------------------------------
-struct GnApplyParams {
-  const bf16* x0;
-  const bf16* x1;
-  int c0, c1, ld0, ld1;
-  int rows_per_stat, num_stat, splits;
-  const float* mean_rstd;  // [num_stat, 32, 2] from gn_stats_kernel
-  const float* gamma;
-  const float* beta;
-  int silu;
-  bf16* out;
-  int out_ld;
-  int halo;  // 1: out rows are the zero-haloed image space; an image is H x W with H*W dividing rows_per_stat
-  int H, W;
-};
-
-__global__ void __launch_bounds__(512) gn_apply_kernel(const GnApplyParams p) {
-  const int C = p.c0 + p.c1;
-  const int stat = blockIdx.x / p.splits;
-  const int split = blockIdx.x - stat * p.splits;
-  const int cg = C >> 5;
-  const int cvec = C >> 3;
-  const int rpar = blockDim.x / cvec;
-  const int tc = threadIdx.x % cvec;
-  const int tr = threadIdx.x / cvec;
-  const int c = tc * 8;
-  const bf16* src;
-  int ld;
-  if (c < p.c0) {
-    src = p.x0 + c;
-    ld = p.ld0;
-  } else {
-    src = p.x1 + (c - p.c0);
-    ld = p.ld1;
+  __syncthreads();
+  // every CTA has read the partials it needs: the last one to get here re-arms the counters for the next launch
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&p.depart[stat], 1u) == (unsigned)(p.splits - 1)) {
+      p.arrive[stat] = 0u;
+      p.depart[stat] = 0u;
+    }
   }
-  // this thread's 8 channels: scale / shift straight from the folded statistics
+
+  // ---------------- phase 2: normalise (+SiLU) the same rows (L2 hits), write the output layout ----------------
   float sc[8], sh[8];
   {
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
@@ -213,66 +201,71 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const GnApplyParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (c + j) / cg;
-      const float2 mr = __ldg(reinterpret_cast<const float2*>(p.mean_rstd) + (size_t)stat * 32 + g);
-      sc[j] = ga[j] * mr.y;
-      sh[j] = be[j] - mr.x * sc[j];
+      sc[j] = ga[j] * s_rstd[g];
+      sh[j] = be[j] - s_mean[g] * sc[j];
     }
   }
-  // iterate over OUTPUT rows of this statistics group (haloed space if requested), 4 rows in flight per thread
   const int HW = p.H * p.W;
-  const int W1 = p.W + 1, H1 = p.H + 1;
+  const int W1 = p.W + 1;
+  const int P = (p.H + 1) * W1;
   const int imgs_per_stat = p.halo ? p.rows_per_stat / HW : 1;
-  const int P = H1 * W1;
-  const int out_rows = p.halo ? imgs_per_stat * P : p.rows_per_stat;
-  const int rows_per_split = (out_rows + p.splits - 1) / p.splits;
-  const int r_begin = split * rows_per_split;
-  const int r_end = min(out_rows, r_begin + rows_per_split);
-  const bf16* in_base = src + (size_t)stat * p.rows_per_stat * ld;
-  bf16* out_base = p.out + (size_t)stat * out_rows * p.out_ld + c;
+  const size_t out_rows_per_stat = p.halo ? (size_t)imgs_per_stat * P : (size_t)p.rows_per_stat;
+  bf16* out_base = p.out + (size_t)stat * out_rows_per_stat * p.out_ld + c;
   int r = r_begin + tr;
   int img = 0, y = 0, x = 0;
   if (p.halo) {
-    img = r / P;
-    const int rem = r - img * P;
-    y = rem / W1;
-    x = rem - y * W1;
+    img = r / HW;
+    const int rem = r - img * HW;
+    y = rem / p.W;
+    x = rem - y * p.W;
   }
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
   for (; r < r_end; r += 4 * rpar) {
     uint4 u[4];
-    bool live[4], pad[4];
+    bool live[4];
+    size_t orow[4];
+    int px[4], py[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int rk = r + k * rpar;
       live[k] = rk < r_end;
-      pad[k] = false;
-      long long in_row = rk;
+      orow[k] = (size_t)rk;
+      px[k] = py[k] = -1;
       if (p.halo) {
-        pad[k] = (y == p.H) || (x == p.W);
-        in_row = (long long)img * HW + y * p.W + x;
+        orow[k] = (size_t)img * P + (size_t)y * W1 + x;
+        px[k] = x;
+        py[k] = y;
         x += rpar;
-        while (x >= W1) { x -= W1; ++y; }
-        while (y >= H1) { y -= H1; ++img; }
+        while (x >= p.W) { x -= p.W; ++y; }
+        while (y >= p.H) { y -= p.H; ++img; }
       }
-      u[k] = (live[k] && !pad[k]) ? ldg_nc_u4(in_base + (size_t)in_row * ld) : make_uint4(0, 0, 0, 0);
+      u[k] = live[k] ? ldg_u4(base + (size_t)rk * ld) : zero4;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (!live[k]) continue;
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (!pad[k]) {
-        const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), cc = unpack_bf16x2(u[k].z), d = unpack_bf16x2(u[k].w);
-        float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+      const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), cc = unpack_bf16x2(u[k].z), d = unpack_bf16x2(u[k].w);
+      float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] = fmaf(v[j], sc[j], sh[j]);
-          if (p.silu) v[j] = silu_f(v[j]);
-        }
-        o.x = pack_bf16x2(v[0], v[1]);
-        o.y = pack_bf16x2(v[2], v[3]);
-        o.z = pack_bf16x2(v[4], v[5]);
-        o.w = pack_bf16x2(v[6], v[7]);
+      for (int j = 0; j < 8; ++j) {
+        v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (p.silu) v[j] = silu_f(v[j]);
       }
-      stg_u4(out_base + (size_t)(r + k * rpar) * p.out_ld, o);
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]);
+      o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]);
+      o.w = pack_bf16x2(v[6], v[7]);
+      bf16* dst = out_base + orow[k] * p.out_ld;
+      stg_u4(dst, o);
+      if (p.halo) {
+        // the zero halo: one extra column right of every image row, one extra row below every image
+        if (px[k] == p.W - 1) stg_u4(dst + p.out_ld, zero4);
+        if (py[k] == p.H - 1) {
+          stg_u4(dst + (size_t)W1 * p.out_ld, zero4);
+          if (px[k] == p.W - 1) stg_u4(dst + (size_t)(W1 + 1) * p.out_ld, zero4);
+        }
+      }
     }
   }
 }
@@ -399,9 +392,30 @@ static int gn_block_threads(int C) {
   return cvec * rpar;
 }
 
+static int gn_smem_bytes(int C) {
+  const int threads = gn_block_threads(C);
+  const int rpar = threads / (C / 8);
+  size_t b = sizeof(float) * ((size_t)2 * rpar * C + 2 * C);
+  if (b < 4096) b = 4096;
+  return (int)b;
+}
+
+// CTAs per statistics group.  The whole grid must be co-resident (the CTAs of a group wait for each other), so it
+// is capped by what the occupancy calculator says fits on the device at once.
 static int gn_splits(int num_stat, int rows_per_stat, int C) {
   const int threads = gn_block_threads(C);
-  int splits = (pt_num_sms() * 4 + num_stat - 1) / num_stat;
+  const int smem = gn_smem_bytes(C);
+  static int cached_threads = 0, cached_smem = 0, cached_blocks = 0;
+  if (cached_threads != threads || cached_smem != smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_fused_kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    cached_threads = threads;
+    cached_smem = smem;
+    cached_blocks = nb;
+  }
+  int per_sm = cached_blocks < 4 ? cached_blocks : 4;
+  const int capacity = pt_num_sms() * per_sm;
+  int splits = capacity / num_stat;
   const int rpar = threads / (C / 8);
   const int max_splits = (rows_per_stat + rpar * 8 - 1) / (rpar * 8);
   if (splits > max_splits) splits = max_splits;
@@ -409,13 +423,11 @@ static int gn_splits(int num_stat, int rows_per_stat, int C) {
   return splits;
 }
 
-static size_t gn_partials_bytes(int num_stat, int splits) { return sizeof(double) * 64 * (size_t)num_stat * splits; }
-
 extern "C" int64_t pt_groupnorm_workspace_bytes(int32_t num_stat, int32_t rows_per_stat, int32_t channels) {
-  if (num_stat < 1 || rows_per_stat < 1 || channels < 32 || channels % 8) return -1;
-  if (num_stat > 1024) return -1;
-  return (int64_t)(4096 + sizeof(float) * 64 * (size_t)num_stat +
-                   gn_partials_bytes(num_stat, gn_splits(num_stat, rows_per_stat, channels)));
+  if (num_stat < 1 || num_stat > 1024 || rows_per_stat < 1 || channels < 32 || channels % 8) return -1;
+  // splits <= 4 CTAs per SM / num_stat, independent of the occupancy query (which needs a device)
+  const int64_t max_ctas = (int64_t)pt_num_sms() * 4 + num_stat;
+  return 8192 + (int64_t)sizeof(double) * 64 * max_ctas;
 }
 
 extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
@@ -428,46 +440,26 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   PT_CHECK_ARG(a->rows_per_stat > 0 && a->num_stat > 0 && a->num_stat <= 1024, "pt_groupnorm: need 1..1024 statistics groups");
   PT_CHECK_ARG(!a->halo || (a->H > 0 && a->W > 0 && a->rows_per_stat % (a->H * a->W) == 0),
                "pt_groupnorm: halo output needs H*W dividing rows_per_stat");
-  cudaStream_t st = (cudaStream_t)stream;
+  PT_CHECK_ARG(a->num_stat <= pt_num_sms(), "pt_groupnorm: more statistics groups than SMs (co-resident grid)");
   const int threads = gn_block_threads(C);
   const int splits = gn_splits(a->num_stat, a->rows_per_stat, C);
-  const int rpar = threads / (C / 8);
-
-  GnStatsParams s;
-  s.x0 = reinterpret_cast<const bf16*>(a->x0);
-  s.x1 = reinterpret_cast<const bf16*>(a->x1);
-  s.c0 = a->c0; s.c1 = a->c1; s.ld0 = a->ld0; s.ld1 = a->ld1;
-  s.rows_per_stat = a->rows_per_stat;
-  s.num_stat = a->num_stat;
-  s.splits = splits;
+  GnParams p;
+  p.x0 = reinterpret_cast<const bf16*>(a->x0);
+  p.x1 = reinterpret_cast<const bf16*>(a->x1);
+  p.c0 = a->c0; p.c1 = a->c1; p.ld0 = a->ld0; p.ld1 = a->ld1;
+  p.rows_per_stat = a->rows_per_stat;
+  p.num_stat = a->num_stat;
+  p.splits = splits;
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->stats);
-  s.tickets = reinterpret_cast<unsigned int*>(ws);
-  s.mean_rstd = reinterpret_cast<float*>(ws + 4096);
-  s.partials = reinterpret_cast<double*>(ws + 4096 + sizeof(float) * 64 * (size_t)a->num_stat);
-  s.eps = a->eps;
-  size_t stats_smem = sizeof(float) * ((size_t)2 * rpar * C + 2 * C);
-  if (stats_smem < 4096) stats_smem = 4096;
-  gn_stats_kernel<<<a->num_stat * splits, threads, stats_smem, st>>>(s);
-  int rc = pt_launched("pt_groupnorm(stats)");
-  if (rc) return rc;
-
-  GnApplyParams p;
-  p.x0 = s.x0; p.x1 = s.x1; p.c0 = a->c0; p.c1 = a->c1; p.ld0 = a->ld0; p.ld1 = a->ld1;
-  p.rows_per_stat = a->rows_per_stat; p.num_stat = a->num_stat;
-  p.mean_rstd = s.mean_rstd;
-  p.gamma = a->gamma; p.beta = a->beta; p.silu = a->silu;
+  p.arrive = reinterpret_cast<unsigned int*>(ws);
+  p.depart = reinterpret_cast<unsigned int*>(ws + 4096);
+  p.partials = reinterpret_cast<double*>(ws + 8192);
+  p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.out_ld = a->out_ld;
   p.halo = a->halo; p.H = a->H > 0 ? a->H : 1; p.W = a->W > 0 ? a->W : 1;
-  // the apply pass has its own split: enough CTAs to fill the machine, >= 16 rows per row lane
-  const int out_rows = a->halo ? (a->rows_per_stat / (p.H * p.W)) * (p.H + 1) * (p.W + 1) : a->rows_per_stat;
-  int asplits = (pt_num_sms() * 6 + a->num_stat - 1) / a->num_stat;
-  const int amax = (out_rows + rpar * 16 - 1) / (rpar * 16);
-  if (asplits > amax) asplits = amax;
-  if (asplits < 1) asplits = 1;
-  p.splits = asplits;
-  gn_apply_kernel<<<a->num_stat * asplits, threads, 0, st>>>(p);
-  return pt_launched("pt_groupnorm(apply)");
+  gn_fused_kernel<<<a->num_stat * splits, threads, gn_smem_bytes(C), (cudaStream_t)stream>>>(p);
+  return pt_launched("pt_groupnorm");
 }
 
 extern "C" int pt_layernorm(const PtLayerNormArgs* a, void* stream) {

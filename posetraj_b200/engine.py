@@ -170,7 +170,7 @@ class NetPlan:
         self.t_buf = torch.zeros(batch, device=device, dtype=F32)
         self.sigmas, self.step_index = sigmas, step_index
         # GroupNorm partial-sum workspace: at most 4 CTAs per SM plus one per statistics group
-        self.stats = torch.zeros((2 * self.n + 4 * ops.NUM_SMS + 64) * 64 + 512, device=device, dtype=torch.float64)
+        self.stats = torch.zeros((2 * self.n + 4 * ops.NUM_SMS + 64) * 64 + 1024, device=device, dtype=torch.float64)
         self.level_hw = [(height >> i, width >> i) for i in range(len(ch))]
 
         # ---- time embedding ops (first in every step) ---------------------------------------------------

@@ -83,7 +83,7 @@ class DenoiseEngine:
         self.tail_ops = [self.update_op, ops.StepAdvance(self.step_index)]
         self.step_ops = self.net_ops + self.tail_ops
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.launches_per_step = len(self.step_ops) + sum(1 for o in self.step_ops if isinstance(o, ops.GroupNorm))
+        self.launches_per_step = len(self.step_ops)
 
     def load(self, *, latents, image_latents, image_embeddings, added_time_ids, guidance, sigmas,
              controlnet_condition, camera_cond=None, cond_scale: float = 1.0) -> None:

@@ -32,7 +32,7 @@ def test_groupnorm(cuda_dev, n_img, H, W, c0, c1, frames_per_stat, halo, silu):
     x1 = rnd(n_img * H * W, c1, scale=2.0) if c1 else None
     gamma = torch.randn(Cc, device="cuda")
     beta = torch.randn(Cc, device="cuda")
-    stats = torch.zeros((2 * n_img + 4 * 148 + 64) * 64 + 512, device="cuda", dtype=torch.float64)
+    stats = torch.zeros((2 * n_img + 4 * 148 + 64) * 64 + 1024, device="cuda", dtype=torch.float64)
     out_rows = n_img * (H + 1) * (W + 1) if halo else n_img * H * W
     out = torch.full((out_rows, Cc), 7.0, device="cuda", dtype=torch.bfloat16)
     GroupNorm(x0, out, gamma, beta, stats, rows_per_stat=frames_per_stat * H * W, eps=1e-6, silu=silu, x1=x1,

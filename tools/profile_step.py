@@ -34,7 +34,7 @@ import json
 oplist = []
 for op in eng.step_ops:
     d = {"name": op.name, "kind": op.kind, "flops": op.alg_flops, "bytes": op.alg_bytes,
-         "kernels": 2 if op.kind == "groupnorm" else 1}
+         "kernels": 1}
     if op.kind == "gemm":
         a = op.args
         d.update(block_n=a.block_n, n_out=a.n_out, rows=a.rows_per_batch * a.batches, taps=a.num_taps,
