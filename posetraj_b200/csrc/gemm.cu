@@ -24,7 +24,12 @@ namespace pt {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// warp 0 TMA, warp 1 MMA, then the epilogue warps: 8 for the memory-bound epilogues, 12 for GEGLU whose 128 x block_n/2
+// erf evaluations per tile are ALU work that more resident warps hide better (4 schedulers either way)
+constexpr int kEpiGegluId = 1;
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == kEpiGegluId ? 12 : 8; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 32 * epi_warps(epi); }
+__host__ __device__ constexpr int stage_warp_bytes(int epi) { return epi == kEpiGegluId ? 32 * 32 * 2 : 32 * 32 * 4; }
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr uint32_t kTmemCols = 512;             // 2 accumulator stages x 256 fp32 columns
 constexpr int kMaxStages = 8;
@@ -66,8 +71,6 @@ struct alignas(64) TmapParam {
 // of a row and 4 neighbouring lanes cover 64 contiguous bytes: residual loads and output stores are coalesced
 // row segments, and each lane only needs 16 bytes per operand in flight.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kEpiWarps = 8;
-constexpr int kStageWarpBytes = 32 * 32 * 4;   // fp32 32x32 (the GEGLU path stages bf16 and uses half of it)
 
 PT_DEVICE void unpack8(uint4 u, float* f) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -83,19 +86,20 @@ PT_DEVICE uint4 pack8(const float* v) {
   return u;
 }
 
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, below fp32 GELU noise; two MUFU + 7 FMA instead of erff's
-// ~30 instructions) — the GEGLU epilogue evaluates 128 x block_n/2 of these per tile and is otherwise ALU-bound.
-PT_DEVICE float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = poly * t * ex2_approx(-z * z * 1.4426950408889634f);  // 1 - erf(z)
-  const float erf_abs = 1.0f - e;
-  const float erf_x = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_x);
+// GEGLU gate: value * gelu(g) with the exact-erf GELU written as g * Phi(g), Phi from Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, far below bf16 output rounding): Phi(g) = h for g < 0 and 1 - h for g >= 0 with
+// h = 0.5 * t * P(t) * exp(-g^2 / 2), t = 1 / (1 + p |g| / sqrt 2).  2 MUFU + 12 FP32 ops per gate: the GEGLU epilogue
+// evaluates 128 x block_n/2 of these per tile and is issue-bound at K = 320 (profiles/r1b).
+PT_DEVICE float geglu_gate(float value, float g) {
+  const float t = rcp_approx(fmaf(fabsf(g), 0.3275911f * 0.70710678118654752440f, 1.0f));
+  const float e = ex2_approx(g * g * (-0.5f * 1.4426950408889634f));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float h = poly * t * e;
+  const float phi = g >= 0.f ? 1.0f - h : h;
+  return value * g * phi;
 }
 
 // slow path of the store side: fewer than 8 valid columns in this lane's segment (only conv_out: n_out = 4)
@@ -236,10 +240,13 @@ constexpr int kEpiGeneric = 0, kEpiGeglu = 1, kEpiFast = 2;
 // 16 KiB + block_n*64 B of L2->SM traffic per SM instead of 16 KiB + block_n*128 B: the large-M layers are
 // L2-bandwidth bound with single-CTA tiles (profiles/r1b).
 template <int kEpi, bool kPair>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(kEpi), 1)
 gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_constant__ TmapParam tmap_a1,
                     const __grid_constant__ TmapParam tmap_b, const __grid_constant__ GemmParams p) {
   constexpr bool kGeglu = kEpi == kEpiGeglu;
+  constexpr int kEpiWarps = epi_warps(kEpi);
+  constexpr int kStageWarpBytes = stage_warp_bytes(kEpi);
+  constexpr int kChunkStride = kEpiWarps / 4;  // epilogue warps per TMEM lane quarter
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -252,7 +259,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sbias = reinterpret_cast<float*>(smem + 256);     // [2][256] bias of the tile, per accumulator stage
   uint8_t* stage_base = smem + kSmemCtl;                   // kEpiWarps x kStageWarpBytes transpose tiles
-  uint8_t* tiles = stage_base + kEpiWarps * kStageWarpBytes;
+  uint8_t* tiles = stage_base + ((kEpiWarps * kStageWarpBytes + 1023) & ~1023);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -471,7 +478,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         }
         sb[etid] = bv;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -482,7 +489,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         __syncwarp();
         if (lane == 0) arrive_tempty(acc);
       }
-      for (int c = hsel; c < chunks; c += 2) {
+      for (int c = hsel; c < chunks; c += kChunkStride) {
         const int ncol = n0 + c * 32 + seg * 8;      // first of this lane's 8 output columns
         const int nvalid = min(8, p.n_out - ncol);   // <= 0: nothing to store
         if constexpr (kGeglu) {
@@ -493,7 +500,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
           tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
           tmem_ld_32x32(t_acc + (uint32_t)(half + c * 32), g);
           tmem_wait_ld();
-          if (c + 2 >= chunks) {
+          if (c + kChunkStride >= chunks) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive_tempty(acc);
@@ -505,7 +512,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             const float x1 = __uint_as_float(v[j + 1]) + sb[c * 32 + j + 1];
             const float g0 = __uint_as_float(g[j]) + sb[half + c * 32 + j];
             const float g1 = __uint_as_float(g[j + 1]) + sb[half + c * 32 + j + 1];
-            pk[j >> 1] = pack_bf16x2(x0 * gelu_erf_fast(g0), x1 * gelu_erf_fast(g1));
+            pk[j >> 1] = pack_bf16x2(geglu_gate(x0, g0), geglu_gate(x1, g1));
           }
           __syncwarp();  // the previous chunk's transposed reads are done
 #pragma unroll
@@ -549,7 +556,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             ax[i] = (ok && p.out2 != nullptr) ? ldg_u4(p.aux + (size_t)orow4[i] * p.out_ld + ncol) : make_uint4(0, 0, 0, 0);
           }
           tmem_wait_ld();
-          if (c + 2 >= chunks) {
+          if (c + kChunkStride >= chunks) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive_tempty(acc);
@@ -686,7 +693,9 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.geglu = a->geglu ? 1 : 0;
   p.gate_row_offset = a->gate_row_offset;
   p.stage_bytes = kABytes + (a->cta_pair ? a->block_n / 2 : a->block_n) * kBlockK * 2;
-  const int smem_limit = 227 * 1024 - kSmemCtl - 1024 - kEpiWarps * kStageWarpBytes;
+  const int epi_id_for_smem = a->geglu ? kEpiGegluId : 0;
+  const int stage_area = (epi_warps(epi_id_for_smem) * stage_warp_bytes(epi_id_for_smem) + 1023) & ~1023;
+  const int smem_limit = 227 * 1024 - kSmemCtl - 1024 - stage_area;
   int stages = smem_limit / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
@@ -724,7 +733,7 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.out_halo = a->out_halo;
   p.act_silu = a->act_silu;
 
-  const size_t smem_bytes = (size_t)kSmemCtl + (size_t)kEpiWarps * kStageWarpBytes + (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem_bytes = (size_t)kSmemCtl + (size_t)stage_area + (size_t)p.stages * p.stage_bytes + 1024;
   typedef void (*KernelFn)(TmapParam, TmapParam, TmapParam, GemmParams);
   static const KernelFn kernels[2][10] = {
       {gemm_tcgen05_kernel<0, false>, gemm_tcgen05_kernel<1, false>, gemm_tcgen05_kernel<2, false>,
@@ -766,7 +775,7 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kGemmThreads);
+    cfg.blockDim = dim3(gemm_threads(epi));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
@@ -780,7 +789,7 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cluster launch");
   } else {
     const int grid = (int)(tiles < sms ? tiles : sms);
-    kernels[0][epi]<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
+    kernels[0][epi]<<<grid, gemm_threads(epi), smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
   }
   return pt_launched("pt_gemm");
 }
