@@ -52,7 +52,8 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
   uint64_t* s_full = kv_empty + kKvStages;     // [2]  S_g(j) complete
   uint64_t* p_full = s_full + 2;               // [2]  P_g(j) in smem, S_g(j) consumed, O_g rescaled
   uint64_t* o_done = p_full + 2;               // [2]  PV_g(j) retired
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_read = o_done + 2;               // [2]  S_g(j) is in the softmax warps' registers: its TMEM columns are free
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_read + 2);
   uint8_t* sQ = smem + 1024;                   // NQ x 16 KiB
   uint8_t* sP = sQ + NQ * kTileBytes;          // NQ x 2 x 16 KiB (keys 0-63 | keys 64-127)
   uint8_t* sKV = sP + NQ * 2 * kTileBytes;     // kKvStages x (K 16 KiB + V 16 KiB)
@@ -75,6 +76,7 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
       mbar_init(&s_full[g], 1);
       mbar_init(&p_full[g], 4);
       mbar_init(&o_done[g], 1);
+      mbar_init(&s_read[g], 4);
     }
     fence_mbar_init();
   }
@@ -123,7 +125,8 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
       int stage_n = 1 % kKvStages;  // stage of K_{j+1}
       uint32_t phase_n = (kKvStages == 1) ? 1u : 0u;
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
+        const bool has_next = j + 1 < n_kv;
+        if (has_next) {
           mbar_wait(&kv_full[stage_n], phase_n);
           tc_fence_after();
         }
@@ -131,18 +134,37 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
         // V tile: rows = keys (128 B each, 8-row swizzle atoms of 1024 B): MN-major B operand, K step of 16 keys
         // = 2048 B; LBO (stride between 64-wide N blocks) is unused for N = 64.
         const uint64_t vdesc = make_smem_desc(sV, 1024, 1024, 2);
-        for (int g = 0; g < NQ; ++g) {
-          mbar_wait(&p_full[g], (uint32_t)j & 1u);  // P_g(j) in smem, S_g(j) consumed, O_g rescaled
-          tc_fence_after();
-          const uint32_t sPg = smem_u32(sP + (size_t)g * 2 * kTileBytes);
+        // Event-driven issue: S_g(j+1) goes out as soon as the softmax warps hold S_g(j) in registers (its latency
+        // hides behind their exponentials), PV_g(j) as soon as P_g(j) is in shared memory — whichever comes first.
+        uint32_t pend_s = has_next ? ((1u << NQ) - 1u) : 0u;
+        uint32_t pend_pv = (1u << NQ) - 1u;
+        const uint32_t par = (uint32_t)j & 1u;
+        uint32_t spins = 0;
+        while (pend_s | pend_pv) {
+          bool progressed = false;
 #pragma unroll
-          for (int k = 0; k < kKTile / 16; ++k) {
-            const uint64_t pdesc = make_desc_kmajor_sw128(sPg + (uint32_t)(k >> 2) * kTileBytes) + (uint64_t)(2 * (k & 3));
-            tc_mma_bf16(tmem_base + 256u + (uint32_t)g * 64u, pdesc, vdesc + (uint64_t)(k * 128), idesc_o,
-                        (j | k) != 0 ? 1u : 0u);
+          for (int g = 0; g < NQ; ++g) {
+            if (((pend_s >> g) & 1u) && mbar_try_wait(&s_read[g], par)) {
+              tc_fence_after();
+              issue_s(g, stage_n);
+              pend_s &= ~(1u << g);
+              progressed = true;
+            }
+            if (((pend_pv >> g) & 1u) && mbar_try_wait(&p_full[g], par)) {  // P_g(j) in smem, O_g rescaled
+              tc_fence_after();
+              const uint32_t sPg = smem_u32(sP + (size_t)g * 2 * kTileBytes);
+#pragma unroll
+              for (int k = 0; k < kKTile / 16; ++k) {
+                const uint64_t pdesc = make_desc_kmajor_sw128(sPg + (uint32_t)(k >> 2) * kTileBytes) + (uint64_t)(2 * (k & 3));
+                tc_mma_bf16(tmem_base + 256u + (uint32_t)g * 64u, pdesc, vdesc + (uint64_t)(k * 128), idesc_o,
+                            (j | k) != 0 ? 1u : 0u);
+              }
+              tc_commit(&o_done[g]);
+              pend_pv &= ~(1u << g);
+              progressed = true;
+            }
           }
-          tc_commit(&o_done[g]);
-          if (j + 1 < n_kv) issue_s(g, stage_n);
+          if (!progressed && ++spins > (1u << 26)) asm volatile("trap;");
         }
         tc_commit(&kv_empty[stage]);
         stage = stage_n;
@@ -171,6 +193,10 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + (uint32_t)c * 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       tmem_wait_ld();
+      // S_g(j) now lives in registers: hand its TMEM columns back so that Q_g K_{j+1}^T can start right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_read[g]);
       float m_tile = -INFINITY;
       if (kvalid == kKTile) {
 #pragma unroll
