@@ -197,14 +197,25 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_read[g]);
-      float m_tile = -INFINITY;
-      if (kvalid == kKTile) {
+      // row max with 4 independent chains (a single FMNMX chain is 128 dependent ops)
+      float m_tile;
+      {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (kvalid == kKTile) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
-      } else {
+          for (int i = 0; i < 128; i += 4) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i < kvalid) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+            for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i + u < kvalid) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
+          }
+        }
+        m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
       // PV_g(j-1) must have retired before P_g is overwritten / O_g is rescaled
       if (j > 0) {
@@ -233,7 +244,8 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
       }
       // P = exp2((s - m_ref) * scale) as bf16 into the swizzled smem tile; row sum of what the MMA will multiply
       const float mb = m_ref * p.scale_log2;
-      float lsum = 0.f;
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent row-sum chains
+      const bool full_tile = kvalid == kKTile;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
@@ -242,11 +254,14 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
           const int k0 = c * 32 + i;
           float p0 = ex2_approx(fmaf(__uint_as_float(v[k0]), p.scale_log2, -mb));
           float p1 = ex2_approx(fmaf(__uint_as_float(v[k0 + 1]), p.scale_log2, -mb));
-          if (k0 >= kvalid) p0 = 0.f;
-          if (k0 + 1 >= kvalid) p1 = 0.f;
+          if (!full_tile) {
+            if (k0 >= kvalid) p0 = 0.f;
+            if (k0 + 1 >= kvalid) p1 = 0.f;
+          }
           pk[i >> 1] = pack_bf16x2(p0, p1);
+          // sum what the tensor core will actually multiply (bf16-rounded probabilities)
           const float2 r = unpack_bf16x2(pk[i >> 1]);
-          lsum += r.x + r.y;
+          ls4[(i >> 1) & 3] += r.x + r.y;
         }
         // keys [c*32, c*32+32) -> half (c >> 1), 16-byte chunks (c & 1)*4 .. +3 of this row, XOR-swizzled
         uint8_t* prow = sPg + (size_t)(c >> 1) * kTileBytes + (size_t)row * 128;
@@ -256,6 +271,7 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
           *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
         }
       }
+      const float lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       l_run += lsum;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
