@@ -289,7 +289,8 @@ struct LnParams {
 
 constexpr int kLnMaxVec = 8;  // vectors per lane: 8 x 8 channels x 32 lanes = 2048 channels at G = 32
 
-template <int G>
+// V = 16-byte vectors per lane (compile-time so that the row really lives in V*8 registers, not kLnMaxVec*8)
+template <int G, int V>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   constexpr int kRowsPerWarp = 32 / G;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -302,16 +303,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const bf16* src = p.x + (size_t)row * p.ld;
   const float* av = nullptr;
   if (p.addvec != nullptr) av = p.addvec + (size_t)((row / p.hw) % p.F) * p.C;
-  uint4 raw[kLnMaxVec];
+  uint4 raw[V];
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < V; ++i) {
     const int vi = l + i * G;
     raw[i] = (vi < nvec) ? ldg_nc_u4(src + vi * 8) : make_uint4(0, 0, 0, 0);
   }
-  float v[kLnMaxVec][8];
+  float v[V][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < V; ++i) {
     const int vi = l + i * G;
     if (vi < nvec) {
       const float2 a = unpack_bf16x2(raw[i].x), b = unpack_bf16x2(raw[i].y), c = unpack_bf16x2(raw[i].z), d = unpack_bf16x2(raw[i].w);
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const float mean = s / (float)p.C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < V; ++i) {
     const int vi = l + i * G;
     if (vi < nvec) {
 #pragma unroll
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const float rstd = rsqrtf(sq / (float)p.C + p.eps);
   if (!live) return;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < V; ++i) {
     const int vi = l + i * G;
     if (vi < nvec) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
@@ -483,11 +484,24 @@ extern "C" int pt_layernorm(const PtLayerNormArgs* a, void* stream) {
     if (nvec % g == 0 && nvec / g <= kLnMaxVec) { G = g; break; }
   }
   if (nvec < 8) G = 8;
+  const int V = (nvec + G - 1) / G;
   const int rows_per_block = 8 * (32 / G);
   const int blocks = (a->rows + rows_per_block - 1) / rows_per_block;
   cudaStream_t st = (cudaStream_t)stream;
-  if (G == 32) layernorm_kernel<32><<<blocks, 256, 0, st>>>(p);
-  else if (G == 16) layernorm_kernel<16><<<blocks, 256, 0, st>>>(p);
-  else layernorm_kernel<8><<<blocks, 256, 0, st>>>(p);
+#define PT_LN_LAUNCH(GG, VV) layernorm_kernel<GG, VV><<<blocks, 256, 0, st>>>(p)
+#define PT_LN_G(GG)                                   \
+  switch (V) {                                        \
+    case 1: PT_LN_LAUNCH(GG, 1); break;               \
+    case 2: PT_LN_LAUNCH(GG, 2); break;               \
+    case 3: PT_LN_LAUNCH(GG, 3); break;               \
+    case 4: PT_LN_LAUNCH(GG, 4); break;               \
+    case 5: PT_LN_LAUNCH(GG, 5); break;               \
+    case 6: PT_LN_LAUNCH(GG, 6); break;               \
+    case 7: PT_LN_LAUNCH(GG, 7); break;               \
+    default: PT_LN_LAUNCH(GG, 8); break;              \
+  }
+  if (G == 32) { PT_LN_G(32) } else if (G == 16) { PT_LN_G(16) } else { PT_LN_G(8) }
+#undef PT_LN_G
+#undef PT_LN_LAUNCH
   return pt_launched("pt_layernorm");
 }
