@@ -72,6 +72,12 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   const int r_end = min(p.rows_per_stat, r_begin + rows_per_split);
   const bf16* base = src + (size_t)stat * p.rows_per_stat * ld;
 
+  // affine parameters of this thread's 8 channels: fetched now, used after the rendezvous
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c) + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + c) + 1);
+
   // ---------------- phase 1: partial statistics of this CTA's rows ----------------
   float sum[8], sq[8];
 #pragma unroll
@@ -142,8 +148,8 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
     atomicAdd(&p.arrive[stat], 1u);
     unsigned int spins = 0;
     while (*reinterpret_cast<volatile unsigned int*>(&p.arrive[stat]) < (unsigned)p.splits) {
-      __nanosleep(64);
-      if (++spins > (1u << 24)) asm volatile("trap;");  // a sizing bug becomes an error, not a hung GPU
+      __nanosleep(20);
+      if (++spins > (1u << 25)) asm volatile("trap;");  // a sizing bug becomes an error, not a hung GPU
     }
     __threadfence();
   }
@@ -192,10 +198,6 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   // ---------------- phase 2: normalise (+SiLU) the same rows (L2 hits), write the output layout ----------------
   float sc[8], sh[8];
   {
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c) + 1);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + c));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + c) + 1);
     const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
