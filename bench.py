@@ -49,6 +49,16 @@ def _peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def _ncu_traffic(kind):
+    """Per-launch DRAM traffic of a kernel class from the committed ncu capture (None if the file is absent)."""
+    path = os.path.join(ROOT, "profiles", "r1d_dram_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["classes"][kind]["traffic_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # clocks sampling (B200_PROFILING.md recipe) during the timed region
 # ---------------------------------------------------------------------------------------------------------------
@@ -322,7 +332,8 @@ def run_own(args):
                     "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"],
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
                     "launches_per_step": int(round(gem["launches"])), "avg_launch_ms": gem["ms"] / gem["launches"],
-                    "share_of_step": gem["ms"] / total_ms, "traffic": None}
+                    "share_of_step": gem["ms"] / total_ms, "traffic": _ncu_traffic("gemm"),
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the 445 GEMM launches of one step, from the committed ncu capture profiles/r1d_dram_traffic.json (bytes)"}
         per_class = {}
         for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
             e = {"ms": round(c["ms"], 4), "launches": int(round(c["launches"])), "share": round(c["ms"] / total_ms, 4)}
