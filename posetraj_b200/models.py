@@ -158,6 +158,17 @@ class ControlNetSDVModel(_NetBase):
         return cls(cfg, sd, device, cam=cam, bbox=bbox)
 
     @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, variant: Optional[str] = None,
+                        device=None, **config_overrides):
+        """diffusers-style loading (scripts/run_inference_vipseg_json_repro.py:335): `<path>/<subfolder>/config.json` +
+        `diffusion_pytorch_model[.variant].safetensors`.  cam / bbox variants are detected from the keys."""
+        from . import checkpoint
+        d = checkpoint.resolve_dir(pretrained_model_name_or_path, subfolder)
+        sd = checkpoint.load_state_dict(d, variant)
+        cam, bbox = checkpoint.detect_controlnet_flags(sd)
+        return cls(checkpoint.load_config(d, **config_overrides), sd, device, cam=cam, bbox=bbox)
+
+    @classmethod
     def from_unet(cls, unet: "UNetSpatioTemporalConditionControlNetModel", controlnet_conditioning_channel_order="rgb",
                   conditioning_embedding_out_channels=(16, 32, 96, 256), load_weights_from_unet: bool = True,
                   conditioning_channels: int = 3, seed: int = 0):
@@ -232,6 +243,14 @@ class UNetSpatioTemporalConditionControlNetModel(_NetBase):
     def from_random(cls, cfg: SVDConfig = SVDConfig(), device=None, seed: int = 0):
         device = device or torch.device("cuda", torch.cuda.current_device())
         return cls(cfg, random_state_dict(unet_param_shapes(cfg), device, seed), device)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, variant: Optional[str] = None,
+                        device=None, **config_overrides):
+        """diffusers-style loading (scripts/run_inference_vipseg_json_repro.py:337)."""
+        from . import checkpoint
+        d = checkpoint.resolve_dir(pretrained_model_name_or_path, subfolder)
+        return cls(checkpoint.load_config(d, **config_overrides), checkpoint.load_state_dict(d, variant), device)
 
     def forward(self, sample, timestep, encoder_hidden_states, down_block_additional_residuals=None,
                 mid_block_additional_residual=None, return_dict: bool = True, added_time_ids=None, _plan_kwargs=None):
