@@ -259,9 +259,9 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
             if (k0 + 1 >= kvalid) p1 = 0.f;
           }
           pk[i >> 1] = pack_bf16x2(p0, p1);
-          // sum what the tensor core will actually multiply (bf16-rounded probabilities)
-          const float2 r = unpack_bf16x2(pk[i >> 1]);
-          ls4[(i >> 1) & 3] += r.x + r.y;
+          // row sum in fp32 of the un-rounded probabilities (the bf16 rounding of P is unbiased; re-deriving the
+          // rounded values costs 3 extra ALU ops per pair in a loop that is issue-bound)
+          ls4[(i >> 1) & 3] += p0 + p1;
         }
         // keys [c*32, c*32+32) -> half (c >> 1), 16-byte chunks (c & 1)*4 .. +3 of this row, XOR-swizzled
         uint8_t* prow = sPg + (size_t)(c >> 1) * kTileBytes + (size_t)row * 128;
