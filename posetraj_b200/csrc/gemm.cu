@@ -463,6 +463,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         continue;
       }
 
+      long long gout_off[4];
+      bf16* gout = reinterpret_cast<bf16*>(p.out);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gout_off[i] = (long long)orow4[i] * p.out_ld;
       // stage this tile's bias in smem, indexed like the accumulator columns
       const int n0 = kGeglu ? n_tile * half : n_tile * p.block_n;
       float* sb = sbias + acc * 256;
@@ -506,13 +510,17 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             if (lane == 0) arrive_tempty(acc);
           }
           uint32_t pk[16];
+          const float4* sbv = reinterpret_cast<const float4*>(sb + c * 32);
+          const float4* sbg = reinterpret_cast<const float4*>(sb + half + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float x0 = __uint_as_float(v[j]) + sb[c * 32 + j];
-            const float x1 = __uint_as_float(v[j + 1]) + sb[c * 32 + j + 1];
-            const float g0 = __uint_as_float(g[j]) + sb[half + c * 32 + j];
-            const float g1 = __uint_as_float(g[j + 1]) + sb[half + c * 32 + j + 1];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bx = sbv[j >> 2], bg = sbg[j >> 2];  // broadcast 128-bit smem reads
+            const float x0 = __uint_as_float(v[j]) + bx.x, x1 = __uint_as_float(v[j + 1]) + bx.y;
+            const float x2 = __uint_as_float(v[j + 2]) + bx.z, x3 = __uint_as_float(v[j + 3]) + bx.w;
+            const float g0 = __uint_as_float(g[j]) + bg.x, g1 = __uint_as_float(g[j + 1]) + bg.y;
+            const float g2 = __uint_as_float(g[j + 2]) + bg.z, g3 = __uint_as_float(g[j + 3]) + bg.w;
             pk[j >> 1] = pack_bf16x2(geglu_gate(x0, g0), geglu_gate(x1, g1));
+            pk[(j >> 1) + 1] = pack_bf16x2(geglu_gate(x2, g2), geglu_gate(x3, g3));
           }
           __syncwarp();  // the previous chunk's transposed reads are done
 #pragma unroll
@@ -528,19 +536,8 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             const uint32_t addr = stage_u32 + (uint32_t)rr * 64u + (uint32_t)((seg ^ ((rr >> 1) & 3)) << 4);
             uint4 u;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
-            if (((vmask >> i) & 1u) && nvalid > 0) {
-              const size_t off = (size_t)orow4[i] * p.out_ld + ncol;
-              if (nvalid == 8 && p.out_dtype == PT_DT_BF16) {
-                stg_u4(reinterpret_cast<bf16*>(p.out) + off, u);
-              } else {
-                float f[8];
-                unpack8(u, f);
-                for (int j = 0; j < nvalid; ++j) {
-                  if (p.out_dtype == PT_DT_BF16) reinterpret_cast<bf16*>(p.out)[off + j] = __float2bfloat16(f[j]);
-                  else reinterpret_cast<float*>(p.out)[off + j] = f[j];
-                }
-              }
-            }
+            // GEGLU outputs are bf16 with n_out % 8 == 0 (host-checked): a segment is full or empty
+            if (((vmask >> i) & 1u) && nvalid > 0) stg_u4(gout + gout_off[i] + ncol, u);
           }
         } else {
           uint32_t v[32];
@@ -680,6 +677,9 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: out2 without aux");
   if (a->geglu && (a->rowvec_mode != 0 || a->res1 != nullptr || a->res2 != nullptr || a->out2 != nullptr || a->acc_scale != 1.0f))
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: GEGLU tiles support a bias-only epilogue");
+  if (a->geglu && (a->out_dtype != PT_DT_BF16 || (a->n_out % 8) != 0 || (a->out_ld % 8) != 0 ||
+                   (reinterpret_cast<uintptr_t>(a->out) & 15u) != 0))
+    return pt_fail(cudaErrorInvalidValue, "pt_gemm: GEGLU output must be bf16, 16-byte aligned, with n_out and out_ld multiples of 8");
 
   GemmParams p;
   p.rows_per_batch = a->rows_per_batch;
