@@ -294,7 +294,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
   }
   tc_fence_before();
   if constexpr (kPair) cluster_sync_all();  // the peer's barriers must be initialised before anything remote
-  else __syncthreads();
+  __syncthreads();  // (also in pair mode: the CTA-level barrier is what race checkers track for the smem handshake)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
