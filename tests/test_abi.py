@@ -51,3 +51,19 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(_lib.PoseTrajLibError):
         _lib.lib()
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it."""
+    offenders = []
+    for path in list((ROOT / "posetraj_b200").rglob("*.py")) + list((ROOT / "posetraj_b200").rglob("*.cu")) + \
+            list((ROOT / "tools").rglob("*.py")):
+        text = path.read_text()
+        if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M):
+            offenders.append(str(path.relative_to(ROOT)))
+    assert offenders == []
+    bench = (ROOT / "bench.py").read_text()
+    # bench.py: the oracle appears only inside the CPU-baseline function
+    head, _, tail = bench.partition("def cpu_oracle_steps_per_sec")
+    body, _, rest = tail.partition("\ndef ")
+    assert "oracle." not in head.replace("the oracle", "") and "from oracle" not in rest

@@ -1,7 +1,7 @@
 """The "library bar": the oracle's wiring run as plain torch eager bf16 on the same B200 (cuDNN / cuBLAS / SDPA
 kernels, NCHW, no fusion) — what the reference would do on this GPU if diffusers were installed, since the reference
 ships no Blackwell kernel of its own.  Test infrastructure (imports oracle/): never part of the product path.
-Usage: python tools/eager_baseline.py [steps]"""
+Lives under tests/ because only test infrastructure may import oracle/.  Usage: python tests/torch_eager_baseline.py [steps]"""
 import os
 import sys
 import time
