@@ -102,7 +102,9 @@ typedef struct PtGemmArgs {
   const float* bias;          /* [>= n rows of Wt] fp32 or NULL */
   const float* rowvec;        /* fp32 [groups, rowvec_ld] or NULL */
   int32_t rowvec_ld;
-  int32_t rowvec_mode;        /* 0 none; 1: g = orow / rv_a; 2: g = ((orow / rv_a) * rv_b + orow % rv_b) % rv_c */
+  int32_t rowvec_mode;        /* 0 none; 1: g = orow / rv_a; 2: g = ((orow / rv_a) * rv_b + orow % rv_mod + rv_off) % rv_c
+                               * (rv_mod = 0 means rv_b, rv_off = 0: the unsharded case; a pixel-sharded temporal block
+                               * passes its local pixel count in rv_mod and its first global pixel in rv_off) */
   int32_t rv_a, rv_b, rv_c;
   float acc_scale;
   const void* res1;           /* bf16 [out rows, res_ld] or NULL */
@@ -131,6 +133,7 @@ typedef struct PtGemmArgs {
                                * models/controlnet_sdv.py:103-109) */
   int32_t cta_pair;           /* 1: run as clusters of two CTAs sharing 256 x block_n tiles (tcgen05 cta_group::2);
                                * tmap_b's box is block_n/2 rows in both modes */
+  int32_t rv_mod, rv_off;     /* see rowvec_mode 2 */
 } PtGemmArgs;
 int pt_gemm(const PtGemmArgs* a, void* stream);
 
@@ -157,6 +160,13 @@ typedef struct PtGroupNormArgs {
   int32_t out_ld;
   int32_t halo;             /* 1: write the zero-haloed image layout ((H+1)*(W+1) rows per image, pads zeroed) */
   int32_t H, W;
+  /* Sharded statistics (frame/pixel-sharded TemporalResnetBlock norms: the statistics group spans ranks):
+   *   mode 0: statistics + normalisation in one launch (default)
+   *   mode 1: statistics only — writes fp64 {sum, sum of squares} per (group, norm group) to `sums` [num_stat,32,2]
+   *   mode 2: normalisation only — reads (all-reduced) `sums`, `count` = elements per (statistics, norm) group */
+  int32_t mode;
+  double* sums;
+  double count;
 } PtGroupNormArgs;
 int pt_groupnorm(const PtGroupNormArgs* a, void* stream);
 /* bytes of PtGroupNormArgs.stats needed for this problem (-1 on bad arguments) */
@@ -269,6 +279,32 @@ typedef struct PtLayoutArgs {
 } PtLayoutArgs;
 int pt_nchw_to_tokens(const PtLayoutArgs* a, void* stream);
 int pt_tokens_to_nchw(const PtLayoutArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Row-block copy between differently ordered token layouts (frame-sharded <-> pixel-sharded activations around a */
+/* temporal sub-block): for i < n_blocks copies `rows[i]` rows of `cols` bf16 from src row src_row[i] to dst row   */
+/* dst_row[i].  The three int32 tables live on the device.                                                       */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct PtRowBlockCopyArgs {
+  const void* src;
+  void* dst;
+  int32_t src_ld, dst_ld, cols;
+  const int32_t* src_row;
+  const int32_t* dst_row;
+  const int32_t* rows;
+  int32_t n_blocks;
+} PtRowBlockCopyArgs;
+int pt_row_block_copy(const PtRowBlockCopyArgs* a, void* stream);
+
+/* out = x + scale * y on bf16 [rows, cols] (skip_i = h_i + m_i * r_i when the injection cannot ride a GEMM epilogue) */
+typedef struct PtAxpyArgs {
+  const void* x;
+  const void* y;
+  void* out;
+  int32_t ld_x, ld_y, ld_out, rows, cols;
+  float scale;
+} PtAxpyArgs;
+int pt_axpy_bf16(const PtAxpyArgs* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* R1: trajectory maps (scripts/run_inference_vipseg_json_repro.py:438-449, utils/dataset.py:  */

@@ -72,6 +72,7 @@ class PtGemmArgs(C.Structure):
         ("map_mode", C.c_int32),
         ("pW1", C.c_int32), ("pH1", C.c_int32), ("ostride", C.c_int32), ("oW", C.c_int32), ("oH", C.c_int32),
         ("out_halo", C.c_int32), ("act_silu", C.c_int32), ("cta_pair", C.c_int32),
+        ("rv_mod", C.c_int32), ("rv_off", C.c_int32),
     ]
 
 
@@ -85,7 +86,8 @@ i32, f32, vp = C.c_int32, C.c_float, C.c_void_p
 PtGroupNormArgs = _st("PtGroupNormArgs", [
     ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32),
     ("rows_per_stat", i32), ("num_stat", i32), ("stats", vp), ("gamma", vp), ("beta", vp),
-    ("eps", f32), ("silu", i32), ("out", vp), ("out_ld", i32), ("halo", i32), ("H", i32), ("W", i32)])
+    ("eps", f32), ("silu", i32), ("out", vp), ("out_ld", i32), ("halo", i32), ("H", i32), ("W", i32),
+    ("mode", i32), ("sums", vp), ("count", C.c_double)])
 
 PtLayerNormArgs = _st("PtLayerNormArgs", [
     ("x", vp), ("ld", i32), ("gamma", vp), ("beta", vp), ("eps", f32), ("out", vp), ("out_ld", i32),
@@ -119,6 +121,14 @@ PtLayoutArgs = _st("PtLayoutArgs", [
     ("n", i32), ("C", i32), ("H", i32), ("W", i32), ("ld", i32), ("halo", i32), ("nchw_f32", i32)])
 
 
+PtRowBlockCopyArgs = _st("PtRowBlockCopyArgs", [
+    ("src", vp), ("dst", vp), ("src_ld", i32), ("dst_ld", i32), ("cols", i32),
+    ("src_row", vp), ("dst_row", vp), ("rows", vp), ("n_blocks", i32)])
+
+PtAxpyArgs = _st("PtAxpyArgs", [
+    ("x", vp), ("y", vp), ("out", vp), ("ld_x", i32), ("ld_y", i32), ("ld_out", i32), ("rows", i32), ("cols", i32),
+    ("scale", f32)])
+
 PtRasterArgs = _st("PtRasterArgs", [
     ("tracks", vp), ("K", i32), ("F", i32), ("H", i32), ("W", i32), ("order", vp), ("out_f32", vp), ("out_u8", vp)])
 
@@ -148,6 +158,8 @@ _SIGNATURES = {
     "pt_nchw_to_tokens": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_tokens_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_rasterize_tracks": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_row_block_copy": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_axpy_bf16": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_rasterize_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
 }
 

@@ -107,5 +107,7 @@ extern "C" int pt_sizeof(const char* name) {
   if (!strcmp(name, "PtConvDirectArgs")) return (int)sizeof(PtConvDirectArgs);
   if (!strcmp(name, "PtLayoutArgs")) return (int)sizeof(PtLayoutArgs);
   if (!strcmp(name, "PtRasterArgs")) return (int)sizeof(PtRasterArgs);
+  if (!strcmp(name, "PtRowBlockCopyArgs")) return (int)sizeof(PtRowBlockCopyArgs);
+  if (!strcmp(name, "PtAxpyArgs")) return (int)sizeof(PtAxpyArgs);
   return -1;
 }

@@ -44,7 +44,7 @@ struct GemmParams {
   int tiles_per_batch, num_m_tiles, num_n_tiles;
   const float* bias;
   const float* rowvec;
-  int rowvec_ld, rowvec_mode, rv_a, rv_b, rv_c;
+  int rowvec_ld, rowvec_mode, rv_a, rv_b, rv_c, rv_mod, rv_off;
   float acc_scale;
   const bf16* res1;
   const bf16* res2;
@@ -432,7 +432,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         if (p.rowvec_mode == 1) {
           grp = (int)(orow / p.rv_a);
         } else if (p.rowvec_mode == 2) {
-          grp = (int)(((orow / p.rv_a) * p.rv_b + orow % p.rv_b) % p.rv_c);
+          grp = (int)(((orow / p.rv_a) * p.rv_b + orow % p.rv_mod + p.rv_off) % p.rv_c);
         }
         if (!valid) { orow = 0; grp = 0; }
         orow4[i] = (int)orow;
@@ -712,6 +712,8 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.rv_a = a->rv_a > 0 ? a->rv_a : 1;
   p.rv_b = a->rv_b > 0 ? a->rv_b : 1;
   p.rv_c = a->rv_c > 0 ? a->rv_c : 1;
+  p.rv_mod = a->rv_mod > 0 ? a->rv_mod : p.rv_b;
+  p.rv_off = a->rv_off > 0 ? a->rv_off : 0;
   p.acc_scale = a->acc_scale;
   p.res1 = reinterpret_cast<const bf16*>(a->res1);
   p.res2 = reinterpret_cast<const bf16*>(a->res2);

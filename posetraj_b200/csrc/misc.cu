@@ -287,9 +287,95 @@ __global__ void tokens_to_nchw_kernel(const LayoutParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// row-block copy (layout exchange around a sharded temporal sub-block) and bf16 axpy
+// ---------------------------------------------------------------------------------------------------------
+struct RowBlockCopyParams {
+  const bf16* src;
+  bf16* dst;
+  int src_ld, dst_ld, cvec;
+  const int* src_row;
+  const int* dst_row;
+  const int* rows;
+};
+
+// grid (x: slices of a block, y: block); each thread moves 16 bytes at a time
+__global__ void __launch_bounds__(256) row_block_copy_kernel(const RowBlockCopyParams p) {
+  const int blk = blockIdx.y;
+  const long long total = (long long)p.rows[blk] * p.cvec;
+  const bf16* s = p.src + (size_t)p.src_row[blk] * p.src_ld;
+  bf16* d = p.dst + (size_t)p.dst_row[blk] * p.dst_ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / p.cvec;
+    const int cv = (int)(i - r * p.cvec);
+    stg_u4(d + r * p.dst_ld + cv * 8, ldg_nc_u4(s + r * p.src_ld + cv * 8));
+  }
+}
+
+struct AxpyParams {
+  const bf16* x;
+  const bf16* y;
+  bf16* out;
+  int ld_x, ld_y, ld_out, rows, cvec;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) axpy_bf16_kernel(const AxpyParams p) {
+  const long long total = (long long)p.rows * p.cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / p.cvec;
+    const int cv = (int)(i - r * p.cvec);
+    const uint4 a = ldg_nc_u4(p.x + r * p.ld_x + cv * 8), b = ldg_nc_u4(p.y + r * p.ld_y + cv * 8);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+    const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+    uint4 o;
+    o.x = pack_bf16x2(fmaf(p.scale, b0.x, a0.x), fmaf(p.scale, b0.y, a0.y));
+    o.y = pack_bf16x2(fmaf(p.scale, b1.x, a1.x), fmaf(p.scale, b1.y, a1.y));
+    o.z = pack_bf16x2(fmaf(p.scale, b2.x, a2.x), fmaf(p.scale, b2.y, a2.y));
+    o.w = pack_bf16x2(fmaf(p.scale, b3.x, a3.x), fmaf(p.scale, b3.y, a3.y));
+    stg_u4(p.out + r * p.ld_out + cv * 8, o);
+  }
+}
+
 }  // namespace pt
 
 using namespace pt;
+
+extern "C" int pt_row_block_copy(const PtRowBlockCopyArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->src && a->dst && a->src_row && a->dst_row && a->rows, "pt_row_block_copy: null argument");
+  PT_CHECK_ARG(a->n_blocks > 0 && a->n_blocks <= 65535 && a->cols > 0 && a->cols % 8 == 0 && a->src_ld % 8 == 0 && a->dst_ld % 8 == 0,
+               "pt_row_block_copy: cols / strides must be multiples of 8, 1..65535 blocks");
+  RowBlockCopyParams p;
+  p.src = reinterpret_cast<const bf16*>(a->src);
+  p.dst = reinterpret_cast<bf16*>(a->dst);
+  p.src_ld = a->src_ld; p.dst_ld = a->dst_ld; p.cvec = a->cols / 8;
+  p.src_row = a->src_row; p.dst_row = a->dst_row; p.rows = a->rows;
+  int slices = (pt_num_sms() * 8 + a->n_blocks - 1) / a->n_blocks;
+  if (slices < 1) slices = 1;
+  if (slices > 64) slices = 64;
+  dim3 grid(slices, a->n_blocks);
+  row_block_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  return pt_launched("pt_row_block_copy");
+}
+
+extern "C" int pt_axpy_bf16(const PtAxpyArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->x && a->y && a->out, "pt_axpy_bf16: null argument");
+  PT_CHECK_ARG(a->rows > 0 && a->cols > 0 && a->cols % 8 == 0 && a->ld_x % 8 == 0 && a->ld_y % 8 == 0 && a->ld_out % 8 == 0,
+               "pt_axpy_bf16: cols / strides must be multiples of 8");
+  AxpyParams p;
+  p.x = reinterpret_cast<const bf16*>(a->x);
+  p.y = reinterpret_cast<const bf16*>(a->y);
+  p.out = reinterpret_cast<bf16*>(a->out);
+  p.ld_x = a->ld_x; p.ld_y = a->ld_y; p.ld_out = a->ld_out; p.rows = a->rows; p.cvec = a->cols / 8;
+  p.scale = a->scale;
+  const long long total = (long long)a->rows * p.cvec;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)pt_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  axpy_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return pt_launched("pt_axpy_bf16");
+}
+
 
 extern "C" int pt_small_linear(const PtSmallLinearArgs* a, void* stream) {
   PT_CHECK_ARG(a != nullptr && a->in && a->w && a->out, "pt_small_linear: null argument");

@@ -44,6 +44,9 @@ struct GnParams {
   int out_ld;
   int halo;  // 1: out rows are the zero-haloed image space; an image is H x W with H*W dividing rows_per_stat
   int H, W;
+  int mode;       // 0 fused, 1 statistics only (-> sums), 2 normalise only (<- sums, count)
+  double* sums;   // [num_stat, 32, 2]
+  double count;   // mode 2: elements per (statistics, norm) group over ALL ranks
 };
 
 __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-  {
+  if (p.mode != 2) {
     int r = r_begin + tr;
     for (; r + 3 * rpar < r_end; r += 4 * rpar) {  // 4 independent 16-byte loads in flight per thread
       uint4 u[4];
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
       }
     }
   }
+  if (p.mode != 2) {
   float* s_sum = s_red;
   float* s_sq = s_red + (size_t)rpar * C;
   float* c_sum = s_sq + (size_t)rpar * C;
@@ -179,6 +183,13 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
       a += s_part[sl * 64 + 2 * threadIdx.x];
       b += s_part[sl * 64 + 2 * threadIdx.x + 1];
     }
+    if (p.mode == 1) {
+      // statistics only: the folded sums of this rank's rows (one CTA per group writes them); the caller all-reduces
+      if (split == 0) {
+        p.sums[((size_t)stat * 32 + threadIdx.x) * 2] = a;
+        p.sums[((size_t)stat * 32 + threadIdx.x) * 2 + 1] = b;
+      }
+    }
     const double cnt = (double)p.rows_per_stat * cg;
     const double m = a / cnt;
     double var = b / cnt - m * m;
@@ -195,6 +206,20 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
     }
   }
 
+  if (p.mode == 1) return;
+  } else {
+    // normalise only: statistics were reduced across ranks by the caller
+    if (threadIdx.x < 32) {
+      const double a = p.sums[((size_t)stat * 32 + threadIdx.x) * 2];
+      const double b = p.sums[((size_t)stat * 32 + threadIdx.x) * 2 + 1];
+      const double m = a / p.count;
+      double var = b / p.count - m * m;
+      if (var < 0) var = 0;
+      s_mean[threadIdx.x] = (float)m;
+      s_rstd[threadIdx.x] = rsqrtf((float)var + p.eps);
+    }
+    __syncthreads();
+  }
   // ---------------- phase 2: normalise (+SiLU) the same rows (L2 hits), write the output layout ----------------
   float sc[8], sh[8];
   {
@@ -434,7 +459,7 @@ extern "C" int64_t pt_groupnorm_workspace_bytes(int32_t num_stat, int32_t rows_p
 }
 
 extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
-  PT_CHECK_ARG(a != nullptr && a->x0 != nullptr && a->out != nullptr && a->stats != nullptr && a->gamma && a->beta,
+  PT_CHECK_ARG(a != nullptr && a->x0 != nullptr && (a->out != nullptr || a->mode == 1) && a->stats != nullptr && a->gamma && a->beta,
                "pt_groupnorm: null argument");
   const int C = a->c0 + a->c1;
   PT_CHECK_ARG(a->c0 > 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0 && C % 32 == 0 && C / 8 <= 512,
@@ -461,6 +486,10 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   p.out = reinterpret_cast<bf16*>(a->out);
   p.out_ld = a->out_ld;
   p.halo = a->halo; p.H = a->H > 0 ? a->H : 1; p.W = a->W > 0 ? a->W : 1;
+  p.mode = a->mode; p.sums = a->sums; p.count = a->count;
+  PT_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "pt_groupnorm: mode must be 0, 1 or 2");
+  PT_CHECK_ARG(a->mode == 0 || a->sums != nullptr, "pt_groupnorm: modes 1/2 need `sums`");
+  PT_CHECK_ARG(a->mode != 2 || a->count > 0, "pt_groupnorm: mode 2 needs `count`");
   gn_fused_kernel<<<a->num_stat * splits, threads, gn_smem_bytes(C), (cudaStream_t)stream>>>(p);
   return pt_launched("pt_groupnorm");
 }

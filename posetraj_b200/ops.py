@@ -180,7 +180,10 @@ class Gemm:
             a.rowvec = _ptr(rowvec)
             a.rowvec_ld = rowvec.stride(0) if rowvec.dim() == 2 else rowvec.numel()
             a.rowvec_mode = rowvec_mode if rowvec_mode else 1
-            a.rv_a, a.rv_b, a.rv_c = (int(v) for v in rv)
+            rv = tuple(int(v) for v in rv)
+            a.rv_a, a.rv_b, a.rv_c = rv[:3]
+            if len(rv) == 5:
+                a.rv_mod, a.rv_off = rv[3], rv[4]
         a.acc_scale = acc_scale
         out_rows = out.shape[0]
         for r in (res1, res2):
@@ -307,8 +310,13 @@ class GroupNorm(_Op):
     fn_name = "pt_groupnorm"
 
     def __init__(self, x0, out, gamma, beta, stats, *, rows_per_stat, eps, silu=True, x1=None,
-                 halo: Optional[tuple] = None, name=None):
+                 halo: Optional[tuple] = None, name=None, mode: int = 0, sums: Optional[torch.Tensor] = None,
+                 count: float = 0.0):
         a = _lib.PtGroupNormArgs()
+        a.mode = mode
+        if mode != 0:
+            assert sums is not None and sums.dtype == torch.float64 and sums.is_contiguous()
+            a.sums, a.count = sums.data_ptr(), float(count)
         assert x0.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and stats.dtype == torch.float64
         assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
         rows = x0.shape[0]
@@ -336,8 +344,8 @@ class GroupNorm(_Op):
         else:
             assert out.shape[0] == rows
         self.kind = "groupnorm"
-        self.alg_bytes = 2.0 * rows * (a.c0 + a.c1) * 2
-        self._finish(a, (x0, x1, out, gamma, beta, stats), name)
+        self.alg_bytes = 2.0 * rows * (a.c0 + a.c1) * 2 * (0.5 if mode else 1.0)
+        self._finish(a, (x0, x1, out, gamma, beta, stats, sums), name)
 
 
 class LayerNorm(_Op):
@@ -480,6 +488,43 @@ class Layout(_Op):
         rows = a.n * ((a.H + 1) * (a.W + 1) if halo else a.H * a.W)
         assert tokens.shape[0] == rows and tokens.shape[1] >= a.C
         self._finish(a, (nchw, tokens), name)
+
+
+class RowBlockCopy(_Op):
+    """Copies row blocks between two token layouts: block i = `rows[i]` rows from src row `src_row[i]` to dst row `dst_row[i]`."""
+    fn_name = "pt_row_block_copy"
+    kind = "layout"
+
+    def __init__(self, src, dst, src_rows, dst_rows, rows, name=None):
+        a = _lib.PtRowBlockCopyArgs()
+        assert src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and src.shape[1] == dst.shape[1]
+        dev = src.device
+        self.t_src = torch.tensor(src_rows, dtype=torch.int32, device=dev)
+        self.t_dst = torch.tensor(dst_rows, dtype=torch.int32, device=dev)
+        self.t_rows = torch.tensor(rows, dtype=torch.int32, device=dev)
+        assert len(src_rows) == len(dst_rows) == len(rows) > 0
+        a.src, a.dst = src.data_ptr(), dst.data_ptr()
+        a.src_ld, a.dst_ld, a.cols = src.stride(0), dst.stride(0), src.shape[1]
+        a.src_row, a.dst_row, a.rows = self.t_src.data_ptr(), self.t_dst.data_ptr(), self.t_rows.data_ptr()
+        a.n_blocks = len(rows)
+        self.alg_bytes = 2.0 * sum(rows) * src.shape[1] * 2
+        self._finish(a, (src, dst), name)
+
+
+class Axpy(_Op):
+    """out = x + scale * y (bf16)."""
+    fn_name = "pt_axpy_bf16"
+    kind = "layout"
+
+    def __init__(self, x, y, out, scale: float, name=None):
+        a = _lib.PtAxpyArgs()
+        assert x.dtype == y.dtype == out.dtype == torch.bfloat16 and x.shape == y.shape == out.shape
+        a.x, a.y, a.out = x.data_ptr(), y.data_ptr(), out.data_ptr()
+        a.ld_x, a.ld_y, a.ld_out = x.stride(0), y.stride(0), out.stride(0)
+        a.rows, a.cols = x.shape
+        a.scale = float(scale)
+        self.alg_bytes = 3.0 * x.numel() * 2
+        self._finish(a, (x, y, out), name)
 
 
 class TorchOp:

@@ -177,6 +177,7 @@ class StableVideoDiffusionPipelineControlNet:
         self.use_cuda_graph = True
         self._cfg_rows = (0, 2)
         self._cfg_group = None
+        self._frame_shard = None   # (rank, world, group) when one video is frame-sharded over several GPUs
 
     def enable_cfg_split(self, rank: int, group=None) -> None:
         """Run one branch of the CFG pair per GPU (2 ranks of `group`, rank == row: 0 uncond, 1 cond)."""
@@ -215,7 +216,24 @@ class StableVideoDiffusionPipelineControlNet:
             latents = latents.to(device)
         return latents * self.scheduler.init_noise_sigma
 
-    def engine_for(self, frames, h, w, cond_hw) -> DenoiseEngine:
+    def enable_frame_sharding(self, rank: int, world: int, group=None) -> None:
+        """Shard ONE video over `world` GPUs by frames (spatial layers) / pixels (temporal layers) with an all-to-all
+        around every temporal sub-block (posetraj_b200/frame_sharding.py)."""
+        if not (0 <= rank < world):
+            raise ValueError("rank out of range")
+        self._frame_shard = (rank, world, group)
+        self._engines.clear()
+
+    def engine_for(self, frames, h, w, cond_hw):
+        if self._frame_shard is not None:
+            from .frame_sharding import FrameShardedEngine
+            rank, world, group = self._frame_shard
+            key = (frames, h, w, tuple(cond_hw), "frames", rank, world)
+            if key not in self._engines:
+                self._engines[key] = FrameShardedEngine(self.unet, self.controlnet, self.scheduler, frames=frames, h=h, w=w,
+                                                        cond_hw=cond_hw, device=self._execution_device, rank=rank,
+                                                        world=world, group=group)
+            return self._engines[key]
         key = (frames, h, w, tuple(cond_hw), self._cfg_rows)
         if key not in self._engines:
             self._engines[key] = DenoiseEngine(self.unet, self.controlnet, self.scheduler, frames=frames, h=h, w=w,
@@ -298,12 +316,17 @@ class StableVideoDiffusionPipelineControlNet:
                 eng.capture()
             eng.step(use_graph=use_graph and i >= 1)
             if callback_on_step_end is not None:
+                if self._frame_shard is not None:
+                    raise ValueError("posetraj_b200: step-end callbacks are not available with frame sharding")
                 cb_latents = eng.latents.view(1, num_frames, -1, h, w)
                 out = callback_on_step_end(self, i, t, {"latents": cb_latents})
                 new = out.pop("latents", cb_latents) if isinstance(out, dict) else cb_latents
                 if new.data_ptr() != eng.latents.data_ptr():
                     eng.latents.copy_(new.reshape(eng.latents.shape))
-        latents = eng.latents.view(1, num_frames, -1, h, w).clone()
+        if self._frame_shard is not None:
+            latents = eng.gather_latents().view(1, num_frames, -1, h, w)
+        else:
+            latents = eng.latents.view(1, num_frames, -1, h, w).clone()
 
         if output_type != "latent":
             if self.vae is None:
