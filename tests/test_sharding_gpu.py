@@ -142,8 +142,12 @@ def _frame_worker(rank, world, port, q, n_gpus):
         eng = pipe2.engine_for(cfg.num_frames, 40, 72, (320, 576))
         outs["collectives"] = eng.collectives_per_step
         q.put((rank, outs))
+        eng.graph = None                 # captured NCCL work would make the communicator teardown wait
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        q.close()
+        q.join_thread()
+        os._exit(0)
     except Exception:  # noqa: BLE001
         import traceback
         q.put((rank, {"error": traceback.format_exc()}))

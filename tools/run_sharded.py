@@ -55,4 +55,9 @@ if rank == 0:
     print(f"frame-sharded x{world} ({'graph' if eng.graph is not None else 'eager'}): frames={F} latent={h}x{w} finite={bool(torch.isfinite(out).all())} {ms:.2f} ms/step "
           f"({fl / ms / 1e9:.0f} TFLOP/s aggregate), {eng.launches_per_step} launches + {eng.collectives_per_step} collectives per step, "
           f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB/rank")
-dist.destroy_process_group()
+# captured NCCL graphs keep communicator work alive: drop them, sync, and leave without the (slow) collective teardown
+eng.graph = None
+torch.cuda.synchronize()
+dist.barrier()
+sys.stdout.flush()
+os._exit(0)
