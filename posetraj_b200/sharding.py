@@ -9,8 +9,9 @@ path has a real exchange step.
                    cross batch rows; the temporal cross-attention context DOES depend on every row's image embedding
                    (reference quirk), so each rank keeps both embeddings and
                    `temporal_context_rotation` says how its lookup table is rotated.
-  * frames       — next round (frame-sharded spatial layers + all-to-all around the temporal sub-blocks); `frame_shards`
-                   already fixes the ragged partition (F = 25 is not divisible by 2/4/8).
+  * frames       — one video on N GPUs: posetraj_b200/frame_sharding.py (frame-sharded spatial layers, pixel-sharded
+                   temporal layers, all-to-all around every temporal sub-block); `frame_shards` fixes the ragged
+                   partition (F = 25 is not divisible by 2/4/8).
 """
 from __future__ import annotations
 
