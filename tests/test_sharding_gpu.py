@@ -141,7 +141,8 @@ def _frame_worker(rank, world, port, q, n_gpus):
         outs["sharded"] = pipe2(None, cond, **kw).frames.float().cpu()
         eng = pipe2.engine_for(cfg.num_frames, 40, 72, (320, 576))
         outs["collectives"] = eng.collectives_per_step
-        q.put((rank, outs))
+        # numpy, not torch tensors: torch shares tensors through file descriptors that die with this process
+        q.put((rank, {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in outs.items()}))
         eng.graph = None                 # captured NCCL work would make the communicator teardown wait
         torch.cuda.synchronize()
         dist.barrier()
@@ -206,6 +207,7 @@ def test_frame_sharding_matches_single_gpu(world):
             p.join(timeout=20)
             if p.is_alive():
                 p.kill()
+    res = {r: {k: (torch.from_numpy(v) if hasattr(v, "dtype") else v) for k, v in o.items()} for r, o in res.items()}
     single, oracle = res[0]["single"], res[0]["oracle"]
     e_single = ((single - oracle).norm() / oracle.norm()).item()
     for r in range(world):
