@@ -319,6 +319,9 @@ typedef struct PtRasterArgs {
   void* order;              /* workspace of pt_rasterize_workspace_bytes(F, H, W) bytes */
   float* out_f32;           /* optional [F, 3, H, W] fp32 RGB in [-1, 1] (the pipeline's controlnet_condition) */
   uint8_t* out_u8;          /* optional [F, H, W, 3] uint8 RGB (the PIL images the reference builds) */
+  int32_t swap_per_track;   /* 1: reproduce utils/dataset.py:741-766, where cv2.cvtColor(BGR2RGB) sits INSIDE the track loop:
+                             * the canvas channels swap after every track, so a line drawn by track k ends up red iff
+                             * (K - k) is odd, blue otherwise (discs are green either way) */
 } PtRasterArgs;
 int pt_rasterize_tracks(const PtRasterArgs* a, void* stream);
 int64_t pt_rasterize_workspace_bytes(int32_t F, int32_t H, int32_t W);

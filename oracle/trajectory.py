@@ -33,6 +33,21 @@ def trajectory_maps_cv2(tracks, num_frames, height, width, start=0):
     return out
 
 
+def trajectory_maps_cv2_dataset(tracks, num_frames, height, width, start=0):
+    """utils/dataset.py:741-766 line for line: the cvtColor sits INSIDE the track loop (channels swap once per track)."""
+    import cv2
+    out = np.zeros((num_frames, height, width, 3), dtype=np.uint8)
+    for k in range(num_frames - 1):
+        mask_img = np.zeros((height, width, 3), dtype=np.uint8)
+        for tr in tracks:
+            a, b = tr[start + k], tr[start + k + 1]
+            cv2.line(mask_img, (int(a[0]), int(a[1])), (int(b[0]), int(b[1])), (0, 0, 255), 3)
+            cv2.circle(mask_img, (int(b[0]), int(b[1])), 3, (0, 255, 0), -1)
+            mask_img = cv2.cvtColor(mask_img, cv2.COLOR_BGR2RGB)
+        out[k] = mask_img
+    return out
+
+
 def preprocess(images_u8):
     """VaeImageProcessor.preprocess on the RGB images: [F, H, W, 3] uint8 -> [F, 3, H, W] float32 in [-1, 1]."""
     x = images_u8.astype(np.float32) / 255.0

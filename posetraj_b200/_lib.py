@@ -130,7 +130,8 @@ PtAxpyArgs = _st("PtAxpyArgs", [
     ("scale", f32)])
 
 PtRasterArgs = _st("PtRasterArgs", [
-    ("tracks", vp), ("K", i32), ("F", i32), ("H", i32), ("W", i32), ("order", vp), ("out_f32", vp), ("out_u8", vp)])
+    ("tracks", vp), ("K", i32), ("F", i32), ("H", i32), ("W", i32), ("order", vp), ("out_f32", vp), ("out_u8", vp),
+    ("swap_per_track", i32)])
 
 PT_DT_BF16 = 0
 PT_DT_F32 = 1

@@ -31,6 +31,7 @@ struct RasterParams {
   unsigned int* order;  // [F-1, H, W]
   float* out_f32;       // [F, 3, H, W] or null
   uint8_t* out_u8;      // [F, H, W, 3] or null
+  int swap_per_track;   // dataset variant: channels swap after every track
 };
 
 // cv::clipLine(Size2l, Point2l&, Point2l&)
@@ -288,17 +289,26 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(const RasterParams 
     if (f < p.F - 1) v = p.order[(size_t)f * hw + pix];  // the last frame is the reference's black padding image
     const bool line = v != 0 && (v & 1u);
     const bool disc = v != 0 && !(v & 1u);
+    // inference scripts: one BGR->RGB at the end -> lines red.  Dataset variant: the conversion runs after EVERY track,
+    // so the pixels of track k are swapped (K - k) times: red iff that count is odd.
+    bool first = line, last = false;  // first / last channel of the stored array
+    if (line && p.swap_per_track) {
+      const int k = (int)((v - 1u) >> 1);
+      const bool odd = ((p.K - k) & 1) != 0;
+      first = odd;
+      last = !odd;
+    }
     if (p.out_u8 != nullptr) {
       uint8_t* o = p.out_u8 + idx * 3;
-      o[0] = line ? 255 : 0;
+      o[0] = first ? 255 : 0;
       o[1] = disc ? 255 : 0;
-      o[2] = 0;
+      o[2] = last ? 255 : 0;
     }
     if (p.out_f32 != nullptr) {
       float* o = p.out_f32 + (size_t)f * 3 * hw + pix;
-      o[0] = line ? 1.0f : -1.0f;  // x / 255 * 2 - 1
+      o[0] = first ? 1.0f : -1.0f;  // x / 255 * 2 - 1
       o[hw] = disc ? 1.0f : -1.0f;
-      o[2 * hw] = -1.0f;
+      o[2 * hw] = last ? 1.0f : -1.0f;
     }
   }
 }
@@ -325,6 +335,7 @@ extern "C" int pt_rasterize_tracks(const PtRasterArgs* a, void* stream) {
   p.order = reinterpret_cast<unsigned int*>(a->order);
   p.out_f32 = a->out_f32;
   p.out_u8 = a->out_u8;
+  p.swap_per_track = a->swap_per_track;
   if (a->F > 1) {
     cudaError_t e = cudaMemsetAsync(p.order, 0, sizeof(unsigned int) * (size_t)(a->F - 1) * a->H * a->W, st);
     if (e != cudaSuccess) return pt_fail(e, "pt_rasterize_tracks: memset");

@@ -38,12 +38,16 @@ def rescale_tracks(trajectory_json: Dict[str, Sequence[Sequence[float]]], size: 
 
 
 def rasterize_tracks(tracks, num_frames: int, height: int, width: int, device=None, output: str = "f32",
-                     start: int = 0) -> torch.Tensor:
+                     start: int = 0, style: str = "inference") -> torch.Tensor:
     """tracks: K lists (or an int tensor [K, >= start+num_frames, 2]) of (x, y) pixel coordinates.
 
     Returns the `num_frames` conditioning maps: output "f32" -> [F, 3, H, W] float32 in [-1, 1] (what the pipeline
     feeds the ControlNet), "u8" -> [F, H, W, 3] uint8 RGB (the PIL images of the reference).  Frame k draws the motion
-    k -> k+1; the last frame is black."""
+    k -> k+1; the last frame is black.  style "dataset" reproduces utils/dataset.py:741-766, whose BGR->RGB conversion
+    sits inside the track loop (the channels swap once per track; that variant also has no black padding frame in the
+    reference, the caller drops it)."""
+    if style not in ("inference", "dataset"):
+        raise ValueError("style must be 'inference' or 'dataset'")
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
@@ -73,6 +77,7 @@ def rasterize_tracks(tracks, num_frames: int, height: int, width: int, device=No
     a.order = order.data_ptr()
     a.out_f32 = out.data_ptr() if output == "f32" else None
     a.out_u8 = out.data_ptr() if output == "u8" else None
+    a.swap_per_track = 1 if style == "dataset" else 0
     with torch.cuda.device(device):
         _lib.check(lib.pt_rasterize_tracks(C.addressof(a), torch.cuda.current_stream().cuda_stream), "pt_rasterize_tracks")
     return out

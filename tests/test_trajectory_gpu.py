@@ -68,3 +68,15 @@ def test_idempotent_and_deterministic(cuda_dev):
     a = rasterize_tracks(tracks, 14, 64, 96, cuda_dev, output="u8")
     b = rasterize_tracks(tracks, 14, 64, 96, cuda_dev, output="u8")
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("K", [1, 2, 7])
+def test_dataset_variant_channel_swaps(cuda_dev, K):
+    """utils/dataset.py:762: cvtColor inside the track loop — colours depend on the number of tracks drawn afterwards."""
+    from oracle.trajectory import trajectory_maps_cv2_dataset
+    from posetraj_b200.trajectory import rasterize_tracks
+    rng = random.Random(K)
+    tracks = [[[rng.randint(0, 95), rng.randint(0, 63)] for _ in range(6)] for _ in range(K)]
+    want = trajectory_maps_cv2_dataset(tracks, 6, 64, 96)
+    got = rasterize_tracks(tracks, 6, 64, 96, cuda_dev, output="u8", style="dataset").cpu().numpy()
+    assert np.array_equal(got, want)
