@@ -40,7 +40,9 @@ PT_DEVICE float rcp_approx(float x) {
   return y;
 }
 
-PT_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU ex2 / rcp (relative error ~2e-7): the IEEE division of x / (1 + exp(-x)) costs ~10
+// instructions and the GroupNorm+SiLU pass is issue-bound with it (profiles/r1g_groupnorm.md)
+PT_DEVICE float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
 // exact (erf) GELU, as diffusers' GEGLU uses F.gelu(gate) with approximate="none"
 PT_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
