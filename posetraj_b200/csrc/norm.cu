@@ -320,91 +320,118 @@ constexpr int kLnMaxVec = 8;  // vectors per lane: 8 x 8 channels x 32 lanes = 2
 template <int G, int V>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   constexpr int kRowsPerWarp = 32 / G;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int l = lane % G;
-  int row = gwarp * kRowsPerWarp + lane / G;
-  const bool live = row < p.rows;
-  if (!live) row = p.rows - 1;  // keep the lanes in the shuffles; they just do not store
   const int nvec = p.C >> 3;
-  const bf16* src = p.x + (size_t)row * p.ld;
-  const float* av = nullptr;
-  if (p.addvec != nullptr) av = p.addvec + (size_t)((row / p.hw) % p.F) * p.C;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int n_groups = (p.rows + kRowsPerWarp - 1) / kRowsPerWarp;
+  int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (grp >= n_groups) return;
+  // persistent warps: the loads of the NEXT row group are in flight while the current one is reduced and stored
+  auto row_of = [&](int g) {
+    const int r = g * kRowsPerWarp + lane / G;
+    return r < p.rows ? r : p.rows - 1;  // keep the lanes in the shuffles; they just do not store
+  };
   uint4 raw[V];
+  {
+    const bf16* src = p.x + (size_t)row_of(grp) * p.ld;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int vi = l + i * G;
-    raw[i] = (vi < nvec) ? ldg_nc_u4(src + vi * 8) : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < V; ++i) {
+      const int vi = l + i * G;
+      raw[i] = (vi < nvec) ? ldg_nc_u4(src + vi * 8) : make_uint4(0, 0, 0, 0);
+    }
   }
-  float v[V][8];
-  float s = 0.f;
+  for (; grp < n_groups; grp += warps_total) {
+    const int row = row_of(grp);
+    const bool live = grp * kRowsPerWarp + lane / G < p.rows;
+    const float* av = nullptr;
+    if (p.addvec != nullptr) av = p.addvec + (size_t)((row / p.hw) % p.F) * p.C;
+    float v[V][8];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int vi = l + i * G;
-    if (vi < nvec) {
-      const float2 a = unpack_bf16x2(raw[i].x), b = unpack_bf16x2(raw[i].y), c = unpack_bf16x2(raw[i].z), d = unpack_bf16x2(raw[i].w);
-      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
-      v[i][4] = c.x; v[i][5] = c.y; v[i][6] = d.x; v[i][7] = d.y;
-      if (av != nullptr) {
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8) + 1);
-        v[i][0] += e0.x; v[i][1] += e0.y; v[i][2] += e0.z; v[i][3] += e0.w;
-        v[i][4] += e1.x; v[i][5] += e1.y; v[i][6] += e1.z; v[i][7] += e1.w;
-        if (p.sum_out != nullptr) {
-          uint4 o;
-          o.x = pack_bf16x2(v[i][0], v[i][1]);
-          o.y = pack_bf16x2(v[i][2], v[i][3]);
-          o.z = pack_bf16x2(v[i][4], v[i][5]);
-          o.w = pack_bf16x2(v[i][6], v[i][7]);
-          if (live) stg_u4(p.sum_out + (size_t)row * p.out_ld + vi * 8, o);
-          // normalise exactly what the consumer of sum_out will see (bf16-rounded), like the reference does
-          const float2 ra = unpack_bf16x2(o.x), rb = unpack_bf16x2(o.y), rc = unpack_bf16x2(o.z), rd = unpack_bf16x2(o.w);
-          v[i][0] = ra.x; v[i][1] = ra.y; v[i][2] = rb.x; v[i][3] = rb.y;
-          v[i][4] = rc.x; v[i][5] = rc.y; v[i][6] = rd.x; v[i][7] = rd.y;
+    for (int i = 0; i < V; ++i) {
+      const int vi = l + i * G;
+      if (vi < nvec) {
+        const float2 a = unpack_bf16x2(raw[i].x), b = unpack_bf16x2(raw[i].y), c = unpack_bf16x2(raw[i].z), d = unpack_bf16x2(raw[i].w);
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
+        v[i][4] = c.x; v[i][5] = c.y; v[i][6] = d.x; v[i][7] = d.y;
+      }
+    }
+    // prefetch the next row group of this warp
+    if (grp + warps_total < n_groups) {
+      const bf16* nsrc = p.x + (size_t)row_of(grp + warps_total) * p.ld;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int vi = l + i * G;
+        raw[i] = (vi < nvec) ? ldg_nc_u4(nsrc + vi * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int vi = l + i * G;
+      if (vi < nvec) {
+        if (av != nullptr) {
+          const float4 e0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
+          const float4 e1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8) + 1);
+          v[i][0] += e0.x; v[i][1] += e0.y; v[i][2] += e0.z; v[i][3] += e0.w;
+          v[i][4] += e1.x; v[i][5] += e1.y; v[i][6] += e1.z; v[i][7] += e1.w;
+          if (p.sum_out != nullptr) {
+            uint4 o;
+            o.x = pack_bf16x2(v[i][0], v[i][1]);
+            o.y = pack_bf16x2(v[i][2], v[i][3]);
+            o.z = pack_bf16x2(v[i][4], v[i][5]);
+            o.w = pack_bf16x2(v[i][6], v[i][7]);
+            if (live) stg_u4(p.sum_out + (size_t)row * p.out_ld + vi * 8, o);
+            // normalise exactly what the consumer of sum_out will see (bf16-rounded), like the reference does
+            const float2 ra = unpack_bf16x2(o.x), rb = unpack_bf16x2(o.y), rc = unpack_bf16x2(o.z), rd = unpack_bf16x2(o.w);
+            v[i][0] = ra.x; v[i][1] = ra.y; v[i][2] = rb.x; v[i][3] = rb.y;
+            v[i][4] = rc.x; v[i][5] = rc.y; v[i][6] = rd.x; v[i][7] = rd.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)p.C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int vi = l + i * G;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          sq = fmaf(d, d, sq);
         }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
     }
-  }
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)p.C;
-  float sq = 0.f;
+    for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)p.C + p.eps);
+    if (live) {
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int vi = l + i * G;
-    if (vi < nvec) {
+      for (int i = 0; i < V; ++i) {
+        const int vi = l + i * G;
+        if (vi < nvec) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8) + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8) + 1);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        sq = fmaf(d, d, sq);
+          for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gg[j], bb[j]);
+          uint4 u;
+          u.x = pack_bf16x2(o[0], o[1]);
+          u.y = pack_bf16x2(o[2], o[3]);
+          u.z = pack_bf16x2(o[4], o[5]);
+          u.w = pack_bf16x2(o[6], o[7]);
+          stg_u4(p.out + (size_t)row * p.out_ld + vi * 8, u);
+        }
       }
-    }
-  }
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / (float)p.C + p.eps);
-  if (!live) return;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int vi = l + i * G;
-    if (vi < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8) + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8) + 1);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gg[j], bb[j]);
-      uint4 u;
-      u.x = pack_bf16x2(o[0], o[1]);
-      u.y = pack_bf16x2(o[2], o[3]);
-      u.z = pack_bf16x2(o[4], o[5]);
-      u.w = pack_bf16x2(o[6], o[7]);
-      stg_u4(p.out + (size_t)row * p.out_ld + vi * 8, u);
     }
   }
 }
@@ -517,7 +544,9 @@ extern "C" int pt_layernorm(const PtLayerNormArgs* a, void* stream) {
   if (nvec < 8) G = 8;
   const int V = (nvec + G - 1) / G;
   const int rows_per_block = 8 * (32 / G);
-  const int blocks = (a->rows + rows_per_block - 1) / rows_per_block;
+  int blocks = (a->rows + rows_per_block - 1) / rows_per_block;
+  const int max_blocks = pt_num_sms() * 2;  // persistent: 2 resident CTAs per SM (117 registers), each warp strides over row groups
+  if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t st = (cudaStream_t)stream;
 #define PT_LN_LAUNCH(GG, VV) layernorm_kernel<GG, VV><<<blocks, 256, 0, st>>>(p)
 #define PT_LN_G(GG)                                   \
