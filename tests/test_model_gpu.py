@@ -168,3 +168,26 @@ def test_error_is_at_the_level_of_torch_bf16(small_setup, cuda_dev):
     _record("noise_pred ours vs torch-bf16 (both against the fp32 oracle)", [e_ours, e_torch])
     assert e_ours < TOL
     assert e_ours < 1.5 * e_torch + 1e-3
+
+
+def test_against_committed_golden_vectors(cuda_dev):
+    """The kernels against tests/golden/model_golden.safetensors (oracle outputs minted by gen_model_golden.py)."""
+    from pathlib import Path
+    from safetensors.torch import load_file
+    from posetraj_b200.models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+    g = load_file(str(Path(__file__).parent / "golden" / "model_golden.safetensors"))
+    cfg = small_cfg()
+    o_unet, o_cnet = oracle_pair(cfg, seed=0, cam=True)          # only for the (seeded) weights
+    unet = UNetSpatioTemporalConditionControlNetModel(cfg, o_unet.state_dict(), cuda_dev)
+    cnet = ControlNetSDVModel(cfg, o_cnet.state_dict(), cuda_dev, cam=True)
+    inp = make_small_inputs(cfg)
+    d = to_dev(inp, cuda_dev)
+    x, t = g["sample"].to(cuda_dev), g["timestep"][0].to(cuda_dev)
+    down, mid = cnet(x, t, d["image_embeddings"], d["added_time_ids"], controlnet_cond=d["controlnet_condition"],
+                     camera_cond=d["camera_cond"], conditioning_scale=0.8, return_dict=False)
+    pred = unet(x, t, d["image_embeddings"], down_block_additional_residuals=down, mid_block_additional_residual=mid,
+                added_time_ids=d["added_time_ids"], return_dict=False)[0]
+    torch.cuda.synchronize()
+    assert rel_l2(pred, g["noise_pred"]) < TOL
+    assert rel_l2(mid, g["mid_residual"]) < TOL_RES and rel_l2(down[0], g["down_residual_0"]) < TOL_RES
+    assert rel_l2(down[11], g["down_residual_11"]) < TOL_RES

@@ -271,3 +271,19 @@ def test_product_refuses_cpu():
     cfg = small_cfg()
     with pytest.raises(RuntimeError):
         UNetSpatioTemporalConditionControlNetModel(cfg, {k: torch.zeros(s) for k, s in unet_param_shapes(cfg).items()})
+
+
+def test_oracle_reproduces_committed_model_golden():
+    """tests/golden/model_golden.safetensors (gen_model_golden.py): one denoise step of the small config, cam model."""
+    from safetensors.torch import load_file
+    g = load_file(str(GOLDEN / "model_golden.safetensors"))
+    cfg = small_cfg()
+    o_unet, o_cnet = oracle_pair(cfg, seed=0, cam=True)
+    inp = make_small_inputs(cfg)
+    with torch.no_grad():
+        down, mid = o_cnet(g["sample"], g["timestep"][0], inp["image_embeddings"], inp["added_time_ids"],
+                           controlnet_cond=inp["controlnet_condition"], camera_cond=inp["camera_cond"], conditioning_scale=0.8)
+        pred = o_unet(g["sample"], g["timestep"][0], inp["image_embeddings"], down_block_additional_residuals=down,
+                      mid_block_additional_residual=mid, added_time_ids=inp["added_time_ids"])
+    assert rel_l2(pred, g["noise_pred"]) < 1e-5       # same code, same seeds: only thread-count-dependent summation order
+    assert rel_l2(mid, g["mid_residual"]) < 1e-5 and rel_l2(down[11], g["down_residual_11"]) < 1e-5
