@@ -9,13 +9,15 @@
 //   * temporal (3,1,1) convs of TemporalResnetBlock                               num_taps = 3, shift = +-H*W
 //   * 1x1 shortcut / ControlNet zero-convs                                        num_taps = 1 (+ 2 K sources)
 //
-// Structure (per CTA, one CTA per SM, tiles 128 x block_n, K step 64):
+// Structure (per CTA, one CTA per SM, tiles 128 x block_n — or 256 x block_n shared by a CTA pair, cta_group::2 —
+// K step 64):
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> SWIZZLE_128B smem ring, mbarrier expect_tx)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma kind::f16, accumulators in TMEM, 2 accumulator stages)
-//   warps 2..9    : epilogue       (tcgen05.ld -> bias / row-vector / residual / blend / GEGLU -> global)
+//   warps 2..9/13 : epilogue       (tcgen05.ld -> smem transpose -> bias / row-vector / residual / blend / GEGLU ->
+//                                   coalesced global stores; 8 warps, 12 for GEGLU)
 // The three pipelines (smem full/empty, TMEM full/empty, static persistent tile schedule) follow the
-// canonical Blackwell GEMM anatomy; block_n, stage count and tap table are runtime values so the single
-// instantiation covers all shapes.
+// canonical Blackwell GEMM anatomy; block_n, stage count and tap table are runtime values, the epilogue flavour
+// (generic / GEGLU / 8 lean variants) and the pair mode are template parameters.
 #include "common.cuh"
 #include "launch.h"
 #include "../../include/posetraj_b200.h"
@@ -26,10 +28,13 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 // warp 0 TMA, warp 1 MMA, then the epilogue warps: 8 for the memory-bound epilogues, 12 for GEGLU whose 128 x block_n/2
 // erf evaluations per tile are ALU work that more resident warps hide better (4 schedulers either way)
-constexpr int kEpiGegluId = 1;
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == kEpiGegluId ? 12 : 8; }
+// kEpi selects the epilogue instantiation: 0 generic (every feature, runtime flags), 1 GEGLU, 2 + bits = lean
+// variants for bf16 outputs with n_out % 8 == 0 and no SiLU (bit 0 per-row vector, bit 1 residual operands,
+// bit 2 second output) — the compiler does not if-convert what is not instantiated.
+constexpr int kEpiGeneric = 0, kEpiGeglu = 1, kEpiFast = 2;
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == kEpiGeglu ? 12 : 8; }
 __host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 32 * epi_warps(epi); }
-__host__ __device__ constexpr int stage_warp_bytes(int epi) { return epi == kEpiGegluId ? 32 * 32 * 2 : 32 * 32 * 4; }
+__host__ __device__ constexpr int stage_warp_bytes(int epi) { return epi == kEpiGeglu ? 32 * 32 * 2 : 32 * 32 * 4; }
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr uint32_t kTmemCols = 512;             // 2 accumulator stages x 256 fp32 columns
 constexpr int kMaxStages = 8;
@@ -229,11 +234,6 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
     }
   }
 }
-
-// kEpi selects the epilogue instantiation: 0 generic (every feature, runtime flags), 1 GEGLU, 2 + bits = lean
-// variants for bf16 outputs with n_out % 8 == 0 and no SiLU (bit 0 per-row vector, bit 1 residual operands,
-// bit 2 second output) — the compiler does not if-convert what is not instantiated.
-constexpr int kEpiGeneric = 0, kEpiGeglu = 1, kEpiFast = 2;
 
 // kPair: the kernel runs as clusters of two CTAs (one SM pair) that share one 256 x block_n tile through
 // tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of A and HALF of the B tile, so a k-step costs
@@ -693,7 +693,7 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.geglu = a->geglu ? 1 : 0;
   p.gate_row_offset = a->gate_row_offset;
   p.stage_bytes = kABytes + (a->cta_pair ? a->block_n / 2 : a->block_n) * kBlockK * 2;
-  const int epi_id_for_smem = a->geglu ? kEpiGegluId : 0;
+  const int epi_id_for_smem = a->geglu ? kEpiGeglu : 0;
   const int stage_area = (epi_warps(epi_id_for_smem) * stage_warp_bytes(epi_id_for_smem) + 1023) & ~1023;
   const int smem_limit = 227 * 1024 - kSmemCtl - 1024 - stage_area;
   int stages = smem_limit / p.stage_bytes;
