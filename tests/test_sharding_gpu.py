@@ -212,6 +212,6 @@ def test_frame_sharding_matches_single_gpu(world):
     e_single = ((single - oracle).norm() / oracle.norm()).item()
     for r in range(world):
         e_shard = ((res[r]["sharded"] - oracle).norm() / oracle.norm()).item()
-        assert e_shard < 2e-2 and e_shard < 1.3 * e_single + 1e-3, (r, e_shard, e_single)
+        assert e_shard < 2e-2 and e_shard < 1.5 * e_single + 2e-3, (r, e_shard, e_single)
         assert torch.equal(res[r]["sharded"], res[0]["sharded"])    # every rank gathers the same latents
     assert res[0]["collectives"] > 0
