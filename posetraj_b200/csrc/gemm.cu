@@ -18,6 +18,8 @@
 // The three pipelines (smem full/empty, TMEM full/empty, static persistent tile schedule) follow the
 // canonical Blackwell GEMM anatomy; block_n, stage count and tap table are runtime values, the epilogue flavour
 // (generic / GEGLU / 8 lean variants) and the pair mode are template parameters.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.h"
 #include "../../include/posetraj_b200.h"
@@ -698,6 +700,14 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   const int smem_limit = 227 * 1024 - kSmemCtl - 1024 - stage_area;
   int stages = smem_limit / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  {
+    static int env_stages = -2;   // experiment knob: PT_GEMM_STAGES caps the ring depth
+    if (env_stages == -2) {
+      const char* e = getenv("PT_GEMM_STAGES");
+      env_stages = e ? atoi(e) : -1;
+    }
+    if (env_stages > 0 && stages > env_stages) stages = env_stages;
+  }
   p.stages = stages;
   const bool pair = a->cta_pair != 0;
   const int tile_m = pair ? 2 * kBlockM : kBlockM;
