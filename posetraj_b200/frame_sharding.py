@@ -33,6 +33,36 @@ def pixel_shards(num_pixels: int, world_size: int) -> List[Tuple[int, int]]:
     return frame_shards(num_pixels, world_size)
 
 
+def f2p_tables(B: int, nf: int, HW: int, pix: List[Tuple[int, int]]):
+    """Row-block copy tables that pack an F-layout tensor (rows (b, f_local, hw)) into the send order of the
+    frame->pixel all-to-all of batch row b: [dest rank][f_local][hw in P_dest].  Returns (src_rows, dst_rows, rows)."""
+    src_rows, dst_rows, rows = [], [], []
+    for b in range(B):
+        off = b * nf * HW
+        for q0, nq in pix:
+            for f in range(nf):
+                src_rows.append((b * nf + f) * HW + q0)
+                dst_rows.append(off + f * nq)
+                rows.append(nq)
+            off += nf * nq
+    return src_rows, dst_rows, rows
+
+
+def p2f_tables(B: int, nf: int, HW: int, pix: List[Tuple[int, int]]):
+    """Tables that unpack the receive order of the pixel->frame all-to-all ([source rank][f_local][hw in P_source]
+    per batch row) into the F-layout."""
+    src_rows, dst_rows, rows = [], [], []
+    for b in range(B):
+        off = b * nf * HW
+        for q0, nq in pix:
+            for f in range(nf):
+                src_rows.append(off + f * nq)
+                dst_rows.append((b * nf + f) * HW + q0)
+                rows.append(nq)
+            off += nf * nq
+    return src_rows, dst_rows, rows
+
+
 class _Collective:
     """Base of the torch.distributed steps inside an op list (they run on the current stream)."""
     kind, alg_flops, alg_bytes = "collective", 0.0, 0.0
@@ -97,15 +127,7 @@ class ShardedNetPlan(NetPlan):
         p0, npx = sh[self.rank]
         packed = self.pool.get(B * nf * HW, Cc)
         out = self.pool.get(B * Ft * npx, Cc)
-        src_rows, dst_rows, rows = [], [], []
-        for b in range(B):
-            off = b * nf * HW
-            for d, (q0, nq) in enumerate(sh):
-                for f in range(nf):
-                    src_rows.append((b * nf + f) * HW + q0)
-                    dst_rows.append(off + f * nq)
-                    rows.append(nq)
-                off += nf * nq
+        src_rows, dst_rows, rows = f2p_tables(B, nf, HW, sh)
         self.step_ops.append(ops.RowBlockCopy(x, packed, src_rows, dst_rows, rows, name=name + ".pack"))
         send = [nf * nq for _, nq in sh]
         recv = [cnt * npx for _, cnt in self.fshards]
@@ -127,15 +149,7 @@ class ShardedNetPlan(NetPlan):
         for b in range(B):
             self.step_ops.append(AllToAllRows(y[b * Ft * npx:(b + 1) * Ft * npx], recv_buf[b * nf * HW:(b + 1) * nf * HW],
                                               send, recv, self.group, name=name + ".p2f"))
-        src_rows, dst_rows, rows = [], [], []
-        for b in range(B):
-            off = b * nf * HW
-            for s, (q0, nq) in enumerate(sh):
-                for f in range(nf):
-                    src_rows.append(off + f * nq)
-                    dst_rows.append((b * nf + f) * HW + q0)
-                    rows.append(nq)
-                off += nf * nq
+        src_rows, dst_rows, rows = p2f_tables(B, nf, HW, sh)
         self.step_ops.append(ops.RowBlockCopy(recv_buf, out, src_rows, dst_rows, rows, name=name + ".unpack"))
         self.pool.put(recv_buf)
         return out

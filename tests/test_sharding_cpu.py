@@ -89,3 +89,87 @@ def test_gloo_world2_collectives():
         assert ids == [0, 1, 2, 3, 4]
         assert t == 11.0                     # max over ranks
         assert (m0, m1) == (0.0, 1.0)        # rank r's row lands in slot r
+
+
+def _simulate_exchange(B, F, HW, world, Cc=3):
+    """numpy model of the frame<->pixel re-sharding: F-layout on every rank -> pack tables -> all-to-all (split sizes as
+    in ShardedNetPlan) -> P-layout; then back.  Checks every element lands where the layouts say it should."""
+    import numpy as np
+    from posetraj_b200.frame_sharding import f2p_tables, p2f_tables, pixel_shards
+    from posetraj_b200.sharding import frame_shards
+    fsh, psh = frame_shards(F, world), pixel_shards(HW, world)
+    full = np.arange(B * F * HW * Cc, dtype=np.int64).reshape(B, F, HW, Cc)
+    f_lay = [full[:, f0:f0 + nf].reshape(B * nf * HW, Cc) for f0, nf in fsh]
+    # ---- F -> P
+    packed = []
+    for r, (f0, nf) in enumerate(fsh):
+        src, dst, rows = f2p_tables(B, nf, HW, psh)
+        buf = np.zeros_like(f_lay[r])
+        for s_, d_, n_ in zip(src, dst, rows):
+            buf[d_:d_ + n_] = f_lay[r][s_:s_ + n_]
+        packed.append(buf)
+    p_lay = []
+    for r, (p0, npx) in enumerate(psh):
+        out = np.zeros((B * F * npx, Cc), dtype=np.int64)
+        for b in range(B):
+            pos = b * F * npx
+            for s_rank, (f0, nf) in enumerate(fsh):          # all_to_all_single: chunks arrive ordered by source rank
+                send_off = b * nf * HW + sum(nf * nq for _, nq in psh[:r])
+                n = nf * npx
+                out[pos:pos + n] = packed[s_rank][send_off:send_off + n]
+                pos += n
+        p_lay.append(out)
+        want = full[:, :, p0:p0 + npx].reshape(B * F * npx, Cc)
+        assert np.array_equal(out, want), ("F->P", r)
+    # ---- P -> F
+    for r, (f0, nf) in enumerate(fsh):
+        recv = np.zeros((B * nf * HW, Cc), dtype=np.int64)
+        for b in range(B):
+            pos = b * nf * HW
+            for s_rank, (p0, npx) in enumerate(psh):
+                src_off = b * F * npx + sum(cnt * npx for _, cnt in fsh[:r])      # rank s sends its frames F_r block
+                n = nf * npx
+                recv[pos:pos + n] = p_lay[s_rank][src_off:src_off + n]
+                pos += n
+        src, dst, rows = p2f_tables(B, nf, HW, psh)
+        out = np.zeros_like(recv)
+        for s_, d_, n_ in zip(src, dst, rows):
+            out[d_:d_ + n_] = recv[s_:s_ + n_]
+        assert np.array_equal(out, f_lay[r]), ("P->F", r)
+
+
+def test_frame_pixel_exchange_tables():
+    for B, F, HW, world in [(2, 14, 45, 2), (2, 25, 144, 8), (2, 5, 6, 3), (1, 3, 7, 3), (2, 25, 9216, 4)]:
+        _simulate_exchange(B, F, HW, world)
+
+
+def _a2a_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from posetraj_b200.frame_sharding import AllReduceSum, AllToAllRows
+    send_rows = [2, 3] if rank == 0 else [1, 4]          # ragged: rank0 -> (2 rows to r0, 3 to r1); rank1 -> (1, 4)
+    recv_rows = [2, 1] if rank == 0 else [3, 4]
+    src = torch.arange(sum(send_rows) * 2, dtype=torch.float32).reshape(-1, 2) + 100 * rank
+    dst = torch.zeros(sum(recv_rows), 2)
+    AllToAllRows(src, dst, send_rows, recv_rows, None).launch(0)
+    s = torch.full((4,), float(rank + 1), dtype=torch.float64)
+    AllReduceSum(s, None).launch(0)
+    q.put((rank, dst.tolist(), s.tolist()))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_ragged_all_to_all_rows():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r, (d, s)) for r, d, s in (q.get(timeout=120) for _ in range(2)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # rank 0 receives its own first 2 rows and rank 1's first row; rank 1 receives rank 0's last 3 and its own last 4
+    assert res[0][0] == [[0.0, 1.0], [2.0, 3.0], [100.0, 101.0]]
+    assert res[1][0][:3] == [[4.0, 5.0], [6.0, 7.0], [8.0, 9.0]] and res[1][0][3] == [102.0, 103.0]
+    assert res[0][1] == [3.0] * 4 and res[1][1] == [3.0] * 4
