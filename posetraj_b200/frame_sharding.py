@@ -6,7 +6,7 @@ the conditioning embedding) are independent per frame: rank r runs them on its f
 temporal transformer block: attention over frames) are independent per pixel: rank r runs them on ALL frames of its
 pixel slice P_r ("P-layout": rows (b, f, hw in P_r)).  Between them the activations are re-sharded by an all-to-all
 over NVLink — one each way per SpatioTemporalResBlock and per TransformerSpatioTemporalModel, ~110 per step — with
-one row-block-copy kernel packing (F->P) or unpacking (P->F) the non-contiguous side.  The 5-D GroupNorm statistics
+row-block-copy kernels packing the send order ([dest rank][batch row][...]) and unpacking the receive order.  The 5-D GroupNorm statistics
 span all pixels, i.e. all ranks: statistics kernel -> all-reduce of [B, 32, 2] fp64 sums -> normalisation kernel.
 
 Frames and pixels are split raggedly when the world size does not divide them (25 frames on 8 GPUs:
@@ -34,33 +34,44 @@ def pixel_shards(num_pixels: int, world_size: int) -> List[Tuple[int, int]]:
 
 
 def f2p_tables(B: int, nf: int, HW: int, pix: List[Tuple[int, int]]):
-    """Row-block copy tables that pack an F-layout tensor (rows (b, f_local, hw)) into the send order of the
-    frame->pixel all-to-all of batch row b: [dest rank][f_local][hw in P_dest].  Returns (src_rows, dst_rows, rows)."""
+    """Pack tables, frame -> pixel direction: F-layout rows (b, f_local, hw) -> the all-to-all send order
+    [dest rank][b][f_local][hw in P_dest].  Returns (src_rows, dst_rows, rows)."""
     src_rows, dst_rows, rows = [], [], []
-    for b in range(B):
-        off = b * nf * HW
-        for q0, nq in pix:
+    off = 0
+    for q0, nq in pix:
+        for b in range(B):
             for f in range(nf):
                 src_rows.append((b * nf + f) * HW + q0)
-                dst_rows.append(off + f * nq)
+                dst_rows.append(off + (b * nf + f) * nq)
                 rows.append(nq)
-            off += nf * nq
+        off += B * nf * nq
     return src_rows, dst_rows, rows
+
+
+def f2p_unpack_tables(B: int, Ft: int, npx: int, fsh: List[Tuple[int, int]]):
+    """Unpack tables, frame -> pixel direction: receive order [source rank][b][f in F_source][p_local] -> P-layout
+    rows (b, f, p_local)."""
+    src_rows, dst_rows, rows = [], [], []
+    off = 0
+    for f0, cnt in fsh:
+        for b in range(B):
+            src_rows.append(off + b * cnt * npx)
+            dst_rows.append((b * Ft + f0) * npx)
+            rows.append(cnt * npx)
+        off += B * cnt * npx
+    return src_rows, dst_rows, rows
+
+
+def p2f_pack_tables(B: int, Ft: int, npx: int, fsh: List[Tuple[int, int]]):
+    """Pack tables, pixel -> frame direction: P-layout rows (b, f, p_local) -> send order [dest rank][b][f in F_dest][p_local]."""
+    src, dst, rows = f2p_unpack_tables(B, Ft, npx, fsh)
+    return dst, src, rows
 
 
 def p2f_tables(B: int, nf: int, HW: int, pix: List[Tuple[int, int]]):
-    """Tables that unpack the receive order of the pixel->frame all-to-all ([source rank][f_local][hw in P_source]
-    per batch row) into the F-layout."""
-    src_rows, dst_rows, rows = [], [], []
-    for b in range(B):
-        off = b * nf * HW
-        for q0, nq in pix:
-            for f in range(nf):
-                src_rows.append(off + f * nq)
-                dst_rows.append((b * nf + f) * HW + q0)
-                rows.append(nq)
-            off += nf * nq
-    return src_rows, dst_rows, rows
+    """Unpack tables, pixel -> frame direction: receive order [source rank][b][f_local][hw in P_source] -> F-layout."""
+    src, dst, rows = f2p_tables(B, nf, HW, pix)
+    return dst, src, rows
 
 
 class _Collective:
@@ -121,37 +132,33 @@ class ShardedNetPlan(NetPlan):
         return sh
 
     def to_pixel_layout(self, x: torch.Tensor, HW: int, name: str) -> torch.Tensor:
-        """F-layout [B*nf*HW, C] -> P-layout [B*F*np, C]."""
+        """F-layout [B*nf*HW, C] -> P-layout [B*F*np, C]: pack -> ONE all-to-all (both batch rows) -> unpack."""
         B, nf, Ft, Cc = self.B, self.nf, self.F_total, x.shape[1]
         sh = self._pix(HW)
-        p0, npx = sh[self.rank]
-        packed = self.pool.get(B * nf * HW, Cc)
+        npx = sh[self.rank][1]
+        send_buf = self.pool.get(B * nf * HW, Cc)
+        recv_buf = self.pool.get(B * Ft * npx, Cc)
+        self.step_ops.append(ops.RowBlockCopy(x, send_buf, *f2p_tables(B, nf, HW, sh), name=name + ".pack"))
+        self.step_ops.append(AllToAllRows(send_buf, recv_buf, [B * nf * nq for _, nq in sh],
+                                          [B * cnt * npx for _, cnt in self.fshards], self.group, name=name + ".f2p"))
         out = self.pool.get(B * Ft * npx, Cc)
-        src_rows, dst_rows, rows = f2p_tables(B, nf, HW, sh)
-        self.step_ops.append(ops.RowBlockCopy(x, packed, src_rows, dst_rows, rows, name=name + ".pack"))
-        send = [nf * nq for _, nq in sh]
-        recv = [cnt * npx for _, cnt in self.fshards]
-        for b in range(B):
-            self.step_ops.append(AllToAllRows(packed[b * nf * HW:(b + 1) * nf * HW], out[b * Ft * npx:(b + 1) * Ft * npx],
-                                              send, recv, self.group, name=name + ".f2p"))
-        self.pool.put(packed)
+        self.step_ops.append(ops.RowBlockCopy(recv_buf, out, *f2p_unpack_tables(B, Ft, npx, self.fshards), name=name + ".unpack"))
+        self.pool.put(send_buf, recv_buf)
         return out
 
     def to_frame_layout(self, y: torch.Tensor, HW: int, name: str) -> torch.Tensor:
         """P-layout [B*F*np, C] -> F-layout [B*nf*HW, C]."""
         B, nf, Ft, Cc = self.B, self.nf, self.F_total, y.shape[1]
         sh = self._pix(HW)
-        p0, npx = sh[self.rank]
+        npx = sh[self.rank][1]
+        send_buf = self.pool.get(B * Ft * npx, Cc)
         recv_buf = self.pool.get(B * nf * HW, Cc)
+        self.step_ops.append(ops.RowBlockCopy(y, send_buf, *p2f_pack_tables(B, Ft, npx, self.fshards), name=name + ".pack"))
+        self.step_ops.append(AllToAllRows(send_buf, recv_buf, [B * cnt * npx for _, cnt in self.fshards],
+                                          [B * nf * nq for _, nq in sh], self.group, name=name + ".p2f"))
         out = self.pool.get(B * nf * HW, Cc)
-        send = [cnt * npx for _, cnt in self.fshards]
-        recv = [nf * nq for _, nq in sh]
-        for b in range(B):
-            self.step_ops.append(AllToAllRows(y[b * Ft * npx:(b + 1) * Ft * npx], recv_buf[b * nf * HW:(b + 1) * nf * HW],
-                                              send, recv, self.group, name=name + ".p2f"))
-        src_rows, dst_rows, rows = p2f_tables(B, nf, HW, sh)
-        self.step_ops.append(ops.RowBlockCopy(recv_buf, out, src_rows, dst_rows, rows, name=name + ".unpack"))
-        self.pool.put(recv_buf)
+        self.step_ops.append(ops.RowBlockCopy(recv_buf, out, *p2f_tables(B, nf, HW, sh), name=name + ".unpack"))
+        self.pool.put(send_buf, recv_buf)
         return out
 
     def _gn_temporal(self, x: torch.Tensor, key: str, HW: int, npx: int, eps: float) -> torch.Tensor:

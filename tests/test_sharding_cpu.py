@@ -92,49 +92,44 @@ def test_gloo_world2_collectives():
 
 
 def _simulate_exchange(B, F, HW, world, Cc=3):
-    """numpy model of the frame<->pixel re-sharding: F-layout on every rank -> pack tables -> all-to-all (split sizes as
-    in ShardedNetPlan) -> P-layout; then back.  Checks every element lands where the layouts say it should."""
+    """numpy model of the frame<->pixel re-sharding: F-layout on every rank -> pack -> all-to-all (split sizes as in
+    ShardedNetPlan) -> unpack -> P-layout; then back.  Checks every element lands where the layouts say it should."""
     import numpy as np
-    from posetraj_b200.frame_sharding import f2p_tables, p2f_tables, pixel_shards
+    from posetraj_b200.frame_sharding import f2p_tables, f2p_unpack_tables, p2f_pack_tables, p2f_tables, pixel_shards
     from posetraj_b200.sharding import frame_shards
     fsh, psh = frame_shards(F, world), pixel_shards(HW, world)
     full = np.arange(B * F * HW * Cc, dtype=np.int64).reshape(B, F, HW, Cc)
+
+    def copy(src_t, tables, n_rows):
+        out = np.full((n_rows, Cc), -1, dtype=np.int64)
+        for s_, d_, n_ in zip(*tables):
+            out[d_:d_ + n_] = src_t[s_:s_ + n_]
+        return out
+
+    def all_to_all(send_bufs, send_rows):      # send_rows[r][d]; chunks arrive ordered by source rank
+        outs = []
+        for r in range(world):
+            parts = []
+            for s_rank in range(world):
+                off = sum(send_rows[s_rank][:r])
+                parts.append(send_bufs[s_rank][off:off + send_rows[s_rank][r]])
+            outs.append(np.concatenate(parts, 0))
+        return outs
+
     f_lay = [full[:, f0:f0 + nf].reshape(B * nf * HW, Cc) for f0, nf in fsh]
     # ---- F -> P
-    packed = []
-    for r, (f0, nf) in enumerate(fsh):
-        src, dst, rows = f2p_tables(B, nf, HW, psh)
-        buf = np.zeros_like(f_lay[r])
-        for s_, d_, n_ in zip(src, dst, rows):
-            buf[d_:d_ + n_] = f_lay[r][s_:s_ + n_]
-        packed.append(buf)
+    send = [copy(f_lay[r], f2p_tables(B, nf, HW, psh), B * nf * HW) for r, (f0, nf) in enumerate(fsh)]
+    recv = all_to_all(send, [[B * nf * nq for _, nq in psh] for _, nf in fsh])
     p_lay = []
     for r, (p0, npx) in enumerate(psh):
-        out = np.zeros((B * F * npx, Cc), dtype=np.int64)
-        for b in range(B):
-            pos = b * F * npx
-            for s_rank, (f0, nf) in enumerate(fsh):          # all_to_all_single: chunks arrive ordered by source rank
-                send_off = b * nf * HW + sum(nf * nq for _, nq in psh[:r])
-                n = nf * npx
-                out[pos:pos + n] = packed[s_rank][send_off:send_off + n]
-                pos += n
+        out = copy(recv[r], f2p_unpack_tables(B, F, npx, fsh), B * F * npx)
+        assert np.array_equal(out, full[:, :, p0:p0 + npx].reshape(B * F * npx, Cc)), ("F->P", r)
         p_lay.append(out)
-        want = full[:, :, p0:p0 + npx].reshape(B * F * npx, Cc)
-        assert np.array_equal(out, want), ("F->P", r)
     # ---- P -> F
+    send = [copy(p_lay[r], p2f_pack_tables(B, F, npx, fsh), B * F * npx) for r, (p0, npx) in enumerate(psh)]
+    recv = all_to_all(send, [[B * cnt * npx for _, cnt in fsh] for _, npx in psh])
     for r, (f0, nf) in enumerate(fsh):
-        recv = np.zeros((B * nf * HW, Cc), dtype=np.int64)
-        for b in range(B):
-            pos = b * nf * HW
-            for s_rank, (p0, npx) in enumerate(psh):
-                src_off = b * F * npx + sum(cnt * npx for _, cnt in fsh[:r])      # rank s sends its frames F_r block
-                n = nf * npx
-                recv[pos:pos + n] = p_lay[s_rank][src_off:src_off + n]
-                pos += n
-        src, dst, rows = p2f_tables(B, nf, HW, psh)
-        out = np.zeros_like(recv)
-        for s_, d_, n_ in zip(src, dst, rows):
-            out[d_:d_ + n_] = recv[s_:s_ + n_]
+        out = copy(recv[r], p2f_tables(B, nf, HW, psh), B * nf * HW)
         assert np.array_equal(out, f_lay[r]), ("P->F", r)
 
 
