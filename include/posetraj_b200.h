@@ -30,6 +30,8 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------ */
 const char* pt_last_error(void);
 int pt_version(void);
+/* 1 when kernels are launched with programmatic dependent launch (opt-in: PT_PDL=1 in the environment) */
+int pt_pdl(void);
 /* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
 int64_t pt_launch_count(void);
 /* sizeof() of a struct declared in this header, by name (-1 if unknown): ABI self-check for bindings */

@@ -140,6 +140,7 @@ PT_DT_F32 = 1
 _SIGNATURES = {
     "pt_last_error": (C.c_char_p, []),
     "pt_version": (C.c_int, []),
+    "pt_pdl": (C.c_int, []),
     "pt_launch_count": (C.c_int64, []),
     "pt_sizeof": (C.c_int, [C.c_char_p]),
     "pt_tensormap_encode_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64),

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "launch.h"
 #include "../../include/posetraj_b200.h"
@@ -36,6 +37,16 @@ int pt_num_sms() {
   return sms;
 }
 
+bool pt_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PT_PDL");
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured slower inside the captured step (profiles/r1h): opt-in
+  }
+  return on != 0;
+}
+
+extern "C" int pt_pdl(void) { return pt_pdl_enabled() ? 1 : 0; }
 extern "C" const char* pt_last_error(void) { return g_err; }
 extern "C" int pt_version(void) { return 100; }
 extern "C" int64_t pt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -85,6 +85,9 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: everything above is private to this CTA; the qkv rows are the previous kernel's output
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -324,7 +327,7 @@ static int launch_attn(const PtAttnSpatialArgs* a, const AttnParams& p, cudaStre
   AttnTmap tm;
   memcpy(&tm, a->tmap_qkv, sizeof(tm));
   dim3 grid((a->S + kQTile * NQ - 1) / (kQTile * NQ), a->heads, a->n_img);
-  attn_spatial_kernel<NQ><<<grid, 64 + 128 * NQ, smem_bytes, st>>>(tm, p);
+  pt_launch(attn_spatial_kernel<NQ>, dim3(grid), dim3(64 + 128 * NQ), smem_bytes, (void*)st, 1, tm, p);
   return pt_launched("pt_attention_spatial");
 }
 

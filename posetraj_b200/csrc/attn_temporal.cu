@@ -41,6 +41,8 @@ PT_DEVICE uint32_t ld_2rows(const bf16* p0, bool ok0, const bf16* p1, bool ok1) 
 // MT = number of 16-row query tiles (F <= 16*MT); keys are padded to 16*MT as well.
 template <int MT>
 __global__ void __launch_bounds__(256) attn_temporal_kernel(const TAttnParams p) {
+  griddep_launch();
+  griddep_wait();
   constexpr int NT = 2 * MT;  // 8-key tiles
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,8 +186,8 @@ extern "C" int pt_attention_temporal(const PtAttnTemporalArgs* a, void* stream) 
   const long long warps = (long long)a->B * a->HW * a->heads;
   const int blocks = (int)((warps + 7) / 8);
   if (a->F <= 16)
-    attn_temporal_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    pt_launch(attn_temporal_kernel<1>, dim3(blocks), dim3(256), 0, stream, 1, p);
   else
-    attn_temporal_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    pt_launch(attn_temporal_kernel<2>, dim3(blocks), dim3(256), 0, stream, 1, p);
   return pt_launched("pt_attention_temporal");
 }

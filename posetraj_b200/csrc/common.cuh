@@ -22,6 +22,12 @@ PT_DEVICE uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (see launch.h).  `griddep_wait` returns once every grid this one depends on has
+// completed and its memory is visible; `griddep_launch` lets the next grid in the stream start being scheduled.
+// Both are no-ops for a grid launched without the attribute.
+PT_DEVICE void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PT_DEVICE void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 PT_DEVICE uint32_t lane_id() {
   uint32_t l;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));

@@ -299,6 +299,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
   __syncthreads();  // (also in pair mode: the CTA-level barrier is what race checkers track for the smem handshake)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: barrier init, TMEM allocation and descriptor prefetch above overlap the tail of the previous kernel;
+  // operands, residuals and output buffers are only touched after its completion
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -785,23 +789,11 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   memcpy(&tb, a->tmap_b, sizeof(TmapParam));
   if (pair) {
     const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(gemm_threads(epi));
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[1][epi], ta0, ta1, tb, p);
+    cudaError_t e = pt_launch(kernels[1][epi], dim3(2 * clusters), dim3(gemm_threads(epi)), smem_bytes, stream, 2, ta0, ta1, tb, p);
     if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cluster launch");
   } else {
     const int grid = (int)(tiles < sms ? tiles : sms);
-    kernels[0][epi]<<<grid, gemm_threads(epi), smem_bytes, (cudaStream_t)stream>>>(ta0, ta1, tb, p);
+    pt_launch(kernels[0][epi], dim3(grid), dim3(gemm_threads(epi)), smem_bytes, stream, 1, ta0, ta1, tb, p);
   }
   return pt_launched("pt_gemm");
 }

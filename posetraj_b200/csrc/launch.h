@@ -14,3 +14,38 @@ int pt_num_sms();
   do {                                                            \
     if (!(cond)) return pt_fail(cudaErrorInvalidValue, msg);      \
   } while (0)
+
+// Programmatic dependent launch (PDL), opt-in with PT_PDL=1: kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a grid may be scheduled while its predecessor in the
+// stream is still draining; each kernel runs its private prologue (barrier init, TMEM allocation, descriptor
+// prefetch, parameter fetch), then `griddepcontrol.wait`s before touching anything another kernel produced.
+// Off by default: inside the captured denoise step it measured 1 % SLOWER than plain graph edges
+// (profiles/r1h_pdl_gn.md); the device-side waits are no-ops for grids launched without the attribute.
+bool pt_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t pt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, int cluster_x,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pt_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

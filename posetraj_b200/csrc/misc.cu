@@ -29,6 +29,8 @@ struct SmallLinearParams {
 };
 
 __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearParams p) {
+  griddep_launch();
+  griddep_wait();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= p.N) return;
@@ -95,6 +97,8 @@ struct SinCosParams {
 };
 
 __global__ void sincos_kernel(const SinCosParams p) {
+  griddep_launch();
+  griddep_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = p.dim >> 1;
   if (idx >= p.M * half) return;
@@ -122,6 +126,8 @@ struct UpsampleParams {
 };
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p) {
+  griddep_launch();
+  griddep_wait();
   const int cvec = p.C >> 3;
   const int sc = p.scale;
   const int oW = sc * p.W + (p.halo ? 1 : 0), oH = sc * p.H + (p.halo ? 1 : 0);
@@ -160,6 +166,8 @@ __global__ void __launch_bounds__(128) conv3x3_direct_kernel(const ConvDirectPar
   const int wcount = 9 * p.Cin * COUT;
   for (int i = threadIdx.x; i < wcount; i += blockDim.x) s_w[i] = p.w[i];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_w[wcount + i] = p.bias[i];
+  griddep_launch();
+  griddep_wait();  // the weights above are constants; the activations below are not
   __syncthreads();
   const int oH = (p.H + p.stride - 1) / p.stride, oW = (p.W + p.stride - 1) / p.stride;
   const long long total = (long long)p.n * oH * oW;
@@ -224,6 +232,8 @@ struct LayoutParams {
 
 // 32 pixels x 32 channels transposed through smem; block (32, 8)
 __global__ void nchw_to_tokens_kernel(const LayoutParams p) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float tile[32][33];
   const int HW = p.H * p.W;
   const int img = blockIdx.z;
@@ -254,6 +264,8 @@ __global__ void nchw_to_tokens_kernel(const LayoutParams p) {
 }
 
 __global__ void tokens_to_nchw_kernel(const LayoutParams p) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float tile[32][33];
   const int HW = p.H * p.W;
   const int img = blockIdx.z;
@@ -301,6 +313,8 @@ struct RowBlockCopyParams {
 
 // grid (x: slices of a block, y: block); each thread moves 16 bytes at a time
 __global__ void __launch_bounds__(256) row_block_copy_kernel(const RowBlockCopyParams p) {
+  griddep_launch();
+  griddep_wait();
   const int blk = blockIdx.y;
   const long long total = (long long)p.rows[blk] * p.cvec;
   const bf16* s = p.src + (size_t)p.src_row[blk] * p.src_ld;
@@ -321,6 +335,8 @@ struct AxpyParams {
 };
 
 __global__ void __launch_bounds__(256) axpy_bf16_kernel(const AxpyParams p) {
+  griddep_launch();
+  griddep_wait();
   const long long total = (long long)p.rows * p.cvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / p.cvec;
@@ -354,7 +370,7 @@ extern "C" int pt_row_block_copy(const PtRowBlockCopyArgs* a, void* stream) {
   if (slices < 1) slices = 1;
   if (slices > 64) slices = 64;
   dim3 grid(slices, a->n_blocks);
-  row_block_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  pt_launch(row_block_copy_kernel, dim3(grid), dim3(256), 0, (void*)stream, 1, p);
   return pt_launched("pt_row_block_copy");
 }
 
@@ -372,7 +388,7 @@ extern "C" int pt_axpy_bf16(const PtAxpyArgs* a, void* stream) {
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)pt_num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  axpy_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  pt_launch(axpy_bf16_kernel, dim3((int)blocks), dim3(256), 0, (void*)stream, 1, p);
   return pt_launched("pt_axpy_bf16");
 }
 
@@ -388,7 +404,7 @@ extern "C" int pt_small_linear(const PtSmallLinearArgs* a, void* stream) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.act_in_silu = a->act_in_silu; p.act_out_silu = a->act_out_silu; p.accumulate = a->accumulate;
   const int blocks = (a->N + 7) / 8;
-  small_linear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  pt_launch(small_linear_kernel, dim3(blocks), dim3(256), 0, (void*)stream, 1, p);
   return pt_launched("pt_small_linear");
 }
 
@@ -400,7 +416,7 @@ extern "C" int pt_timestep_sincos(const PtSinCosArgs* a, void* stream) {
   p.t = a->t; p.sigmas = a->sigmas; p.step_index = a->step_index;
   p.out = a->out; p.out_ld = a->out_ld; p.M = a->M; p.dim = a->dim;
   const int total = a->M * (a->dim / 2);
-  sincos_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  pt_launch(sincos_kernel, dim3((total + 127) / 128), dim3(128), 0, (void*)stream, 1, p);
   return pt_launched("pt_timestep_sincos");
 }
 
@@ -416,7 +432,7 @@ extern "C" int pt_upsample2x(const PtUpsampleArgs* a, void* stream) {
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)pt_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  upsample2x_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  pt_launch(upsample2x_kernel, dim3((int)blocks), dim3(256), 0, (void*)stream, 1, p);
   return pt_launched("pt_upsample2x");
 }
 
@@ -437,9 +453,9 @@ extern "C" int pt_conv3x3_direct(const PtConvDirectArgs* a, void* stream) {
   if (blocks > cap) blocks = cap;
   const size_t smem = sizeof(float) * (9 * (size_t)a->Cin * a->Cout + a->Cout);
   if (a->Cout == 16)
-    conv3x3_direct_kernel<16><<<(int)blocks, 128, smem, (cudaStream_t)stream>>>(p);
+    pt_launch(conv3x3_direct_kernel<16>, dim3((int)blocks), dim3(128), smem, (void*)stream, 1, p);
   else
-    conv3x3_direct_kernel<32><<<(int)blocks, 128, smem, (cudaStream_t)stream>>>(p);
+    pt_launch(conv3x3_direct_kernel<32>, dim3((int)blocks), dim3(128), smem, (void*)stream, 1, p);
   return pt_launched("pt_conv3x3_direct");
 }
 
@@ -454,9 +470,9 @@ static int layout_common(const PtLayoutArgs* a, void* stream, bool to_tokens) {
   dim3 grid((a->H * a->W + 31) / 32, (a->C + 31) / 32, a->n);
   dim3 block(32, 8);
   if (to_tokens)
-    nchw_to_tokens_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    pt_launch(nchw_to_tokens_kernel, dim3(grid), dim3(block), 0, (void*)stream, 1, p);
   else
-    tokens_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    pt_launch(tokens_to_nchw_kernel, dim3(grid), dim3(block), 0, (void*)stream, 1, p);
   return pt_launched(to_tokens ? "pt_nchw_to_tokens" : "pt_tokens_to_nchw");
 }
 

@@ -9,7 +9,10 @@
 //   * LayerNorm optionally adds the per-frame position embedding first and also emits that sum
 //     (`hidden_states_mix = hidden_states + emb`, models/modified_svd.py:196-197).
 // Algorithmic bytes: GN stats pass reads numel*2 B, apply pass reads numel*2 B and writes numel*2 B (the second
-// read normally hits the 126 MB L2); LayerNorm reads and writes numel*2 B.
+// read is served from shared memory for the rows the CTA could keep resident and from the 126 MB L2 for the rest);
+// LayerNorm reads and writes numel*2 B.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.h"
 #include "../../include/posetraj_b200.h"
@@ -20,7 +23,9 @@ namespace pt {
 // GroupNorm (+SiLU) in ONE launch: every CTA reduces its slab of rows to per-group partial sums, publishes them,
 // waits until the other CTAs of the same statistics group have published theirs (the grid is sized to be fully
 // co-resident, so the wait cannot deadlock), folds all partials in a fixed order and normalises the slab it has just
-// read — the second read hits the L2.  HBM traffic: numel*2 B in + out rows*C*2 B out.
+// read.  The first `res_slots` rows of every thread are fetched with cp.async into shared memory (all of them in
+// flight at once: ~90 KB per CTA without a register held) and stay there for the second pass; the rows that do not
+// fit are streamed through registers and re-read from the L2.  HBM traffic: numel*2 B in + out rows*C*2 B out.
 // Deterministic on purpose: no floating-point atomics, every reduction in a fixed order, so two runs of the same
 // step are bit-identical (a 1-ulp wobble in a mean flips bf16 roundings downstream and decorrelates whole runs).
 // Workspace: uint32 arrive[1024] | uint32 depart[1024] (zero before the first launch; the kernel re-arms them)
@@ -47,10 +52,24 @@ struct GnParams {
   int mode;       // 0 fused, 1 statistics only (-> sums), 2 normalise only (<- sums, count)
   double* sums;   // [num_stat, 32, 2]
   double count;   // mode 2: elements per (statistics, norm) group over ALL ranks
+  int res_slots;  // rows per thread kept resident in shared memory between the two passes
+  int res_off;    // byte offset of the resident area in dynamic shared memory
 };
 
+PT_DEVICE void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+PT_DEVICE void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+PT_DEVICE uint4 lds_u4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  return u;
+}
+
 __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
-  extern __shared__ float s_red[];  // [rpar][C] sums, [rpar][C] squares, then [C] + [C] per-channel totals
+  extern __shared__ __align__(16) float s_red[];  // [rpar][C] sums, [rpar][C] squares, then [C] + [C] per-channel totals; then resident rows
   __shared__ float s_mean[32], s_rstd[32];
   const int C = p.c0 + p.c1;
   const int cvec = C >> 3;            // threads along channels (8 channels each)
@@ -80,13 +99,24 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c) + 1);
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + c));
   const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + c) + 1);
+  // PDL: the activations are the previous kernel's output.  The NEXT grid may only be released once every CTA of
+  // this one is resident (they wait for each other below): after the rendezvous, or at once when there is none.
+  griddep_wait();
+  if (p.mode == 2) griddep_launch();
 
   // ---------------- phase 1: partial statistics of this CTA's rows ----------------
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  // resident rows: slot i of this thread holds row r_begin + tr + i*rpar (a thread only ever reads its own slots, so
+  // cp.async.wait_group is all the synchronisation needed)
+  const int n_my = (r_end - r_begin - tr + rpar - 1) / rpar;  // rows of this thread (<= 0: none)
+  const int n_res = p.mode == 0 ? min(n_my, p.res_slots) : 0;
+  const uint32_t res_u32 = smem_u32(reinterpret_cast<uint8_t*>(s_red) + p.res_off) + threadIdx.x * 16u;
+  const uint32_t res_stride = blockDim.x * 16u;
+  for (int i = 0; i < n_res; ++i) cp_async_16(res_u32 + (uint32_t)i * res_stride, base + (size_t)(r_begin + tr + i * rpar) * ld);
   if (p.mode != 2) {
-    int r = r_begin + tr;
+    int r = r_begin + tr + n_res * rpar;
     for (; r + 3 * rpar < r_end; r += 4 * rpar) {  // 4 independent 16-byte loads in flight per thread
       uint4 u[4];
 #pragma unroll
@@ -110,6 +140,19 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
       for (int j = 0; j < 8; ++j) {
         sum[j] += v[j];
         sq[j] = fmaf(v[j], v[j], sq[j]);
+      }
+    }
+    if (n_res > 0) {
+      cp_async_wait_all();
+      for (int i = 0; i < n_res; ++i) {
+        const uint4 u = lds_u4(res_u32 + (uint32_t)i * res_stride);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sum[j] += v[j];
+          sq[j] = fmaf(v[j], v[j], sq[j]);
+        }
       }
     }
   }
@@ -158,6 +201,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
     __threadfence();
   }
   __syncthreads();
+  griddep_launch();
 
   // ---------------- fixed-order fp64 fold of all partials (identical in every CTA of the group) ----------------
   double* s_part = reinterpret_cast<double*>(s_red);  // [nsl][64], reuses the reduction scratch (>= 4 KiB)
@@ -247,7 +291,8 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
     x = rem - y * p.W;
   }
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  for (; r < r_end; r += 4 * rpar) {
+  int slot = 0;  // index of row r among this thread's rows
+  for (; r < r_end; r += 4 * rpar, slot += 4) {
     uint4 u[4];
     bool live[4];
     size_t orow[4];
@@ -266,7 +311,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
         while (x >= p.W) { x -= p.W; ++y; }
         while (y >= p.H) { y -= p.H; ++img; }
       }
-      u[k] = live[k] ? ldg_u4(base + (size_t)rk * ld) : zero4;
+      u[k] = !live[k] ? zero4 : (slot + k < n_res ? lds_u4(res_u32 + (uint32_t)(slot + k) * res_stride) : ldg_u4(base + (size_t)rk * ld));
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -326,6 +371,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int n_groups = (p.rows + kRowsPerWarp - 1) / kRowsPerWarp;
   int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  griddep_launch();
+  griddep_wait();
   if (grp >= n_groups) return;
   // persistent warps: the loads of the NEXT row group are in flight while the current one is reduced and stored
   auto row_of = [&](int g) {
@@ -447,7 +494,7 @@ static int gn_block_threads(int C) {
   return cvec * rpar;
 }
 
-static int gn_smem_bytes(int C) {
+static int gn_red_bytes(int C) {
   const int threads = gn_block_threads(C);
   const int rpar = threads / (C / 8);
   size_t b = sizeof(float) * ((size_t)2 * rpar * C + 2 * C);
@@ -456,10 +503,11 @@ static int gn_smem_bytes(int C) {
 }
 
 // CTAs per statistics group.  The whole grid must be co-resident (the CTAs of a group wait for each other), so it
-// is capped by what the occupancy calculator says fits on the device at once.
-static int gn_splits(int num_stat, int rows_per_stat, int C) {
+// is capped by what the occupancy calculator says fits on the device at once (registers / threads; the shared
+// memory left over is then divided between the resident CTAs, see gn_res_slots).
+static int gn_ctas_per_sm(int C) {
   const int threads = gn_block_threads(C);
-  const int smem = gn_smem_bytes(C);
+  const int smem = gn_red_bytes(C);
   static int cached_threads = 0, cached_smem = 0, cached_blocks = 0;
   if (cached_threads != threads || cached_smem != smem) {
     int nb = 0;
@@ -468,7 +516,30 @@ static int gn_splits(int num_stat, int rows_per_stat, int C) {
     cached_smem = smem;
     cached_blocks = nb;
   }
-  int per_sm = cached_blocks < 4 ? cached_blocks : 4;
+  return cached_blocks < 4 ? cached_blocks : 4;
+}
+
+constexpr int kGnSmemPerSm = 216 * 1024;  // of 228 KB: 1 KB per CTA is reserved by the system, static smem, margin
+
+// rows per thread that can stay in shared memory between the statistics and the normalisation pass
+static int gn_res_slots(int C, int per_sm, int rows_per_split) {
+  static int env_res = -2;  // experiment knob: PT_GN_RESIDENT=0 disables the resident rows
+  if (env_res == -2) {
+    const char* e = getenv("PT_GN_RESIDENT");
+    env_res = e ? atoi(e) : -1;
+  }
+  if (env_res == 0) return 0;
+  const int threads = gn_block_threads(C);
+  const int rpar = threads / (C / 8);
+  const int avail = kGnSmemPerSm / per_sm - gn_red_bytes(C);
+  int slots = avail > 0 ? avail / (threads * 16) : 0;
+  const int need = (rows_per_split + rpar - 1) / rpar;
+  return slots < need ? slots : need;
+}
+
+static int gn_splits(int num_stat, int rows_per_stat, int C) {
+  const int threads = gn_block_threads(C);
+  const int per_sm = gn_ctas_per_sm(C);
   const int capacity = pt_num_sms() * per_sm;
   int splits = capacity / num_stat;
   const int rpar = threads / (C / 8);
@@ -517,7 +588,17 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   PT_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "pt_groupnorm: mode must be 0, 1 or 2");
   PT_CHECK_ARG(a->mode == 0 || a->sums != nullptr, "pt_groupnorm: modes 1/2 need `sums`");
   PT_CHECK_ARG(a->mode != 2 || a->count > 0, "pt_groupnorm: mode 2 needs `count`");
-  gn_fused_kernel<<<a->num_stat * splits, threads, gn_smem_bytes(C), (cudaStream_t)stream>>>(p);
+  const int rows_per_split = (a->rows_per_stat + splits - 1) / splits;
+  p.res_slots = a->mode == 0 ? gn_res_slots(C, gn_ctas_per_sm(C), rows_per_split) : 0;
+  p.res_off = gn_red_bytes(C);
+  const size_t smem_bytes = (size_t)p.res_off + (size_t)p.res_slots * threads * 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemPerSm);
+    if (e != cudaSuccess) return pt_fail(e, "pt_groupnorm: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  pt_launch(gn_fused_kernel, dim3(a->num_stat * splits), dim3(threads), smem_bytes, (void*)stream, 1, p);
   return pt_launched("pt_groupnorm");
 }
 
@@ -548,7 +629,7 @@ extern "C" int pt_layernorm(const PtLayerNormArgs* a, void* stream) {
   const int max_blocks = pt_num_sms() * 2;  // persistent: 2 resident CTAs per SM (117 registers), each warp strides over row groups
   if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t st = (cudaStream_t)stream;
-#define PT_LN_LAUNCH(GG, VV) layernorm_kernel<GG, VV><<<blocks, 256, 0, st>>>(p)
+#define PT_LN_LAUNCH(GG, VV) pt_launch(layernorm_kernel<GG, VV>, dim3(blocks), dim3(256), 0, (void*)st, 1, p)
 #define PT_LN_G(GG)                                   \
   switch (V) {                                        \
     case 1: PT_LN_LAUNCH(GG, 1); break;               \

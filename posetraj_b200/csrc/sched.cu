@@ -27,6 +27,8 @@ struct CfgEulerParams {
 
 // one thread per (f, y, x); C (= 4) channels handled in a short loop
 __global__ void __launch_bounds__(256) cfg_euler_kernel(const CfgEulerParams p) {
+  griddep_launch();
+  griddep_wait();
   const int HW = p.H * p.W;
   const int total = p.F * HW;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,7 +91,11 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const CfgEulerParams p) 
   }
 }
 
-__global__ void step_advance_kernel(int* step_index) { *step_index += 1; }
+__global__ void step_advance_kernel(int* step_index) {
+  griddep_launch();
+  griddep_wait();
+  *step_index += 1;
+}
 
 }  // namespace pt
 
@@ -121,12 +127,12 @@ extern "C" int pt_cfg_euler_step(const PtCfgEulerArgs* a, void* stream) {
   p.row_count = a->row_count > 0 ? a->row_count : 2;
   PT_CHECK_ARG(p.row_begin >= 0 && p.row_begin + p.row_count <= 2, "pt_cfg_euler_step: row window must lie inside the CFG pair");
   const int total = a->F * a->H * a->W;
-  cfg_euler_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  pt_launch(cfg_euler_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, 1, p);
   return pt_launched("pt_cfg_euler_step");
 }
 
 extern "C" int pt_step_advance(int32_t* step_index, void* stream) {
   PT_CHECK_ARG(step_index != nullptr, "pt_step_advance: null");
-  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_index);
+  pt_launch(step_advance_kernel, dim3(1), dim3(1), 0, stream, 1, step_index);
   return pt_launched("pt_step_advance");
 }
