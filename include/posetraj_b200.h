@@ -309,6 +309,32 @@ typedef struct PtAxpyArgs {
 int pt_axpy_bf16(const PtAxpyArgs* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* VAE (pipeline/pipeline_stable_video_diffusion_controlnet.py:174-195     */
+/* `_encode_vae_image`, :225-251 `decode_latents`): diffusers AutoencoderKLTemporalDecoder.     */
+/* Its convolutions, norms and linears run on pt_gemm / pt_groupnorm; these two are the rest.  */
+/* ------------------------------------------------------------------------------------------ */
+/* out[r, :cols] = softmax(in[r, :cols]) — fp32 logits of the single-head (head_dim = C) mid-block attention,
+ * bf16 probabilities (the A operand of the P V GEMM); columns >= cols are left untouched */
+typedef struct PtSoftmaxArgs {
+  const float* in;
+  void* out;                /* bf16 */
+  int32_t rows, cols, ld_in, ld_out;
+} PtSoftmaxArgs;
+int pt_softmax_rows(const PtSoftmaxArgs* a, void* stream);
+
+/* TemporalDecoder.time_conv_out: Conv3d(C, C, (3,1,1), padding (1,0,0)) over the frames of each video, on the
+ * token-major fp32 output of conv_out, written as the caller's NCHW fp32 frames [B*F, C, H, W] */
+typedef struct PtTimeConvArgs {
+  const float* in;          /* [B*F*HW, ld] */
+  int32_t ld;
+  const float* w;           /* [C, C, 3] */
+  const float* bias;        /* [C] */
+  float* out;               /* [B*F, C, H*W] */
+  int32_t B, F, HW, C;
+} PtTimeConvArgs;
+int pt_time_conv3(const PtTimeConvArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* R1: trajectory maps (scripts/run_inference_vipseg_json_repro.py:438-449, utils/dataset.py:  */
 /* 741-766): per frame transition k a black canvas with, per track in order, cv2.line(p_k,     */
 /* p_k+1, BGR (0,0,255), thickness 3) and cv2.circle(p_k+1, 3, BGR (0,255,0), filled); then    */

@@ -129,6 +129,12 @@ PtAxpyArgs = _st("PtAxpyArgs", [
     ("x", vp), ("y", vp), ("out", vp), ("ld_x", i32), ("ld_y", i32), ("ld_out", i32), ("rows", i32), ("cols", i32),
     ("scale", f32)])
 
+PtSoftmaxArgs = _st("PtSoftmaxArgs", [
+    ("in_", vp), ("out", vp), ("rows", i32), ("cols", i32), ("ld_in", i32), ("ld_out", i32)])
+
+PtTimeConvArgs = _st("PtTimeConvArgs", [
+    ("in_", vp), ("ld", i32), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("F", i32), ("HW", i32), ("C", i32)])
+
 PtRasterArgs = _st("PtRasterArgs", [
     ("tracks", vp), ("K", i32), ("F", i32), ("H", i32), ("W", i32), ("order", vp), ("out_f32", vp), ("out_u8", vp),
     ("swap_per_track", i32)])
@@ -163,6 +169,8 @@ _SIGNATURES = {
     "pt_row_block_copy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_axpy_bf16": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_rasterize_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "pt_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_time_conv3": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

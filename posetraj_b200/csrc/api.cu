@@ -120,5 +120,7 @@ extern "C" int pt_sizeof(const char* name) {
   if (!strcmp(name, "PtRasterArgs")) return (int)sizeof(PtRasterArgs);
   if (!strcmp(name, "PtRowBlockCopyArgs")) return (int)sizeof(PtRowBlockCopyArgs);
   if (!strcmp(name, "PtAxpyArgs")) return (int)sizeof(PtAxpyArgs);
+  if (!strcmp(name, "PtSoftmaxArgs")) return (int)sizeof(PtSoftmaxArgs);
+  if (!strcmp(name, "PtTimeConvArgs")) return (int)sizeof(PtTimeConvArgs);
   return -1;
 }

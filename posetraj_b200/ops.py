@@ -527,6 +527,38 @@ class Axpy(_Op):
         self._finish(a, (x, y, out), name)
 
 
+class SoftmaxRows(_Op):
+    """bf16 out[r, :cols] = softmax(fp32 x[r, :cols]) (VAE mid-block attention)."""
+    fn_name = "pt_softmax_rows"
+    kind = "vae_misc"
+
+    def __init__(self, x, out, cols: int, name=None):
+        a = _lib.PtSoftmaxArgs()
+        assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and x.shape[0] == out.shape[0]
+        assert x.stride(1) == 1 and out.stride(1) == 1 and cols <= x.shape[1] and cols <= out.shape[1]
+        a.in_, a.out = x.data_ptr(), out.data_ptr()
+        a.rows, a.cols, a.ld_in, a.ld_out = x.shape[0], cols, x.stride(0), out.stride(0)
+        self.alg_bytes = x.shape[0] * cols * 6.0
+        self._finish(a, (x, out), name)
+
+
+class TimeConv3(_Op):
+    """TemporalDecoder.time_conv_out on token-major fp32 rows -> NCHW fp32 frames."""
+    fn_name = "pt_time_conv3"
+    kind = "vae_misc"
+
+    def __init__(self, x, w, bias, out, *, batch: int, frames: int, hw: int, name=None):
+        a = _lib.PtTimeConvArgs()
+        Cc = out.shape[1]
+        assert x.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous() and x.stride(1) == 1
+        assert w.dtype == torch.float32 and w.is_contiguous() and w.numel() == Cc * Cc * 3 and bias.numel() == Cc
+        assert x.shape[0] == batch * frames * hw and out.shape[0] == batch * frames and out[0, 0].numel() == hw
+        a.in_, a.ld, a.w, a.bias, a.out = x.data_ptr(), x.stride(0), w.data_ptr(), bias.data_ptr(), out.data_ptr()
+        a.B, a.F, a.HW, a.C = batch, frames, hw, Cc
+        self.alg_bytes = x.shape[0] * Cc * 8.0
+        self._finish(a, (x, w, bias, out), name)
+
+
 class TorchOp:
     """A tiny torch-side op inside an op list that is replayed OUTSIDE the per-step graph (embedding staging)."""
     kind, alg_flops, alg_bytes = "misc", 0.0, 0.0

@@ -11,9 +11,11 @@ What runs where
     needs host control between steps.
   * once per call: Karras sigma table (host float64, like the reference), ControlNet conditioning embedding,
     the 1-token cross-attention vectors.
-  * CLIP image encoding and the VAE are outside the hot path: pass `image_encoder` /
-    `vae` modules to use them, or hand the pipeline `image_embeddings=` / `image_latents=` directly
-    (then `image` may be None and only output_type="latent" is available).
+  * the VAE on either side of the loop is posetraj_b200.vae.AutoencoderKLTemporalDecoder on
+    the same kernel library: `_encode_vae_image` (:174-195) for the conditioning image, `decode_latents` (:225-251)
+    + `tensor2vid` (:70-82) for output_type "pt" / "np" / "pil".  `image_latents=` may be passed instead of a VAE.
+  * CLIP image encoding is not on this library yet: hand the pipeline `image_embeddings=`
+    (or construct it with an `image_encoder` module exposing `.image_embeds`, as the reference does).
 """
 from __future__ import annotations
 
@@ -31,6 +33,77 @@ from .scheduler import EulerDiscreteScheduler
 @dataclass
 class StableVideoDiffusionPipelineOutput:
     frames: Union[List, torch.Tensor]
+
+
+class VaeImageProcessor:
+    """The two calls the reference pipeline makes on diffusers' VaeImageProcessor (pipeline...controlnet.py:143,
+    450, 500, 78): `preprocess` (PIL / numpy / tensor -> [N, 3, height, width] fp32 in [-1, 1]) and `postprocess`
+    ([N, 3, H, W] in [-1, 1] -> "pt" | "np" | "pil").  Host-side image formatting, not arithmetic of the path."""
+
+    def __init__(self, vae_scale_factor: int = 8):
+        self.vae_scale_factor = vae_scale_factor
+
+    @staticmethod
+    def _pil_to_pt(images, height, width):
+        import numpy as np
+        import PIL.Image
+        out = []
+        for im in images:
+            if height is not None and width is not None and im.size != (width, height):
+                im = im.resize((width, height), resample=PIL.Image.LANCZOS)
+            out.append(np.asarray(im.convert("RGB"), dtype=np.float32) / 255.0)
+        return torch.from_numpy(np.stack(out, 0)).permute(0, 3, 1, 2)
+
+    def preprocess(self, image, height: Optional[int] = None, width: Optional[int] = None) -> torch.Tensor:
+        import numpy as np
+        try:
+            import PIL.Image
+            pil_t = PIL.Image.Image
+        except ImportError:  # pragma: no cover
+            pil_t = ()
+        if isinstance(image, pil_t):
+            image = [image]
+        if isinstance(image, (list, tuple)) and len(image) and isinstance(image[0], pil_t):
+            x = self._pil_to_pt(image, height, width)
+        elif isinstance(image, np.ndarray) or (isinstance(image, (list, tuple)) and isinstance(image[0], np.ndarray)):
+            arr = np.stack(image, 0) if isinstance(image, (list, tuple)) else image
+            if arr.ndim == 3:
+                arr = arr[None]
+            x = torch.from_numpy(arr.astype(np.float32)).permute(0, 3, 1, 2)
+        elif torch.is_tensor(image) or (isinstance(image, (list, tuple)) and torch.is_tensor(image[0])):
+            x = torch.stack(list(image), 0) if isinstance(image, (list, tuple)) else image
+            if x.dim() == 3:
+                x = x[None]
+            x = x.to(F32)
+            if x.min() < 0:      # already in [-1, 1] (diffusers warns and skips the normalisation)
+                if height is not None and tuple(x.shape[-2:]) != (height, width):
+                    x = torch.nn.functional.interpolate(x, size=(height, width))
+                return x
+        else:
+            raise ValueError("image must be a PIL image, numpy array, tensor, or a list of those")
+        if height is not None and tuple(x.shape[-2:]) != (height, width):
+            x = torch.nn.functional.interpolate(x, size=(height, width))
+        return 2.0 * x - 1.0
+
+    def postprocess(self, image: torch.Tensor, output_type: str = "pil"):
+        if output_type not in ("pt", "np", "pil"):
+            raise ValueError(f"output_type must be one of 'latent', 'pt', 'np', 'pil', got {output_type!r}")
+        image = (image / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return image
+        arr = image.cpu().permute(0, 2, 3, 1).float().numpy()
+        if output_type == "np":
+            return arr
+        import PIL.Image
+        return [PIL.Image.fromarray(a) for a in (arr * 255).round().astype("uint8")]
+
+
+def tensor2vid(video: torch.Tensor, processor: VaeImageProcessor, output_type: str = "np"):
+    """pipeline...controlnet.py:70-82: [B, C, F, H, W] -> per video, the post-processed frames."""
+    outputs = []
+    for b in range(video.shape[0]):
+        outputs.append(processor.postprocess(video[b].permute(1, 0, 2, 3), output_type))
+    return outputs
 
 
 def _get_add_time_ids(noise_aug_strength, dtype, batch_size, fps=4, motion_bucket_id=128, unet=None):
@@ -170,7 +243,8 @@ class StableVideoDiffusionPipelineControlNet:
         self.vae, self.image_encoder, self.unet, self.controlnet = vae, image_encoder, unet, controlnet
         self.scheduler = scheduler or EulerDiscreteScheduler()
         self.feature_extractor = feature_extractor
-        self.vae_scale_factor = 8
+        self.vae_scale_factor = 8 if vae is None else 2 ** (len(vae.config.block_out_channels) - 1)
+        self.image_processor = VaeImageProcessor(vae_scale_factor=self.vae_scale_factor)
         self._engines: Dict[tuple, DenoiseEngine] = {}
         self._guidance_scale = None
         self._num_timesteps = 0
@@ -265,12 +339,19 @@ class StableVideoDiffusionPipelineControlNet:
         h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
 
         # 3./4. image conditioning (outside the hot path)
-        if image_embeddings is None or image_latents is None:
-            if self.image_encoder is None or self.vae is None:
-                raise ValueError("pass image_embeddings= and image_latents= (or construct the pipeline with "
-                                 "image_encoder and vae modules)")
-            image_embeddings, image_latents = self._encode_conditioning(image, height, width, noise_aug_strength,
-                                                                        generator, device)
+        if image_embeddings is None:
+            if self.image_encoder is None:
+                raise ValueError("pass image_embeddings= (or construct the pipeline with an image_encoder module)")
+            image_embeddings = self._encode_image(image, device, num_videos_per_prompt, True)
+        if image_latents is None:
+            if self.vae is None:
+                raise ValueError("pass image_latents= (or construct the pipeline with a vae module)")
+            # 4. encode the (noise-augmented) conditioning image (:449-461)
+            img = self.image_processor.preprocess(image, height=height, width=width).to(device)
+            gdev = generator.device if isinstance(generator, torch.Generator) else device
+            noise = torch.randn(img.shape, generator=generator, device=gdev, dtype=img.dtype).to(device)
+            img = img + noise_aug_strength * noise
+            image_latents = self._encode_vae_image(img, device, num_videos_per_prompt, True)
         image_embeddings = image_embeddings.to(device=device, dtype=F32)
         image_latents = image_latents.to(device=device, dtype=F32)
         if image_latents.dim() == 4:  # [2, C, h, w] -> repeat per frame (:466)
@@ -332,15 +413,43 @@ class StableVideoDiffusionPipelineControlNet:
             if self.vae is None:
                 raise ValueError("output_type other than 'latent' needs a VAE (SURVEY.md §8f row 2)")
             frames = self.decode_latents(latents, num_frames, decode_chunk_size or num_frames)
+            frames = tensor2vid(frames, self.image_processor, output_type=output_type)
         else:
             frames = latents
         if not return_dict:
             return frames
         return StableVideoDiffusionPipelineOutput(frames=frames)
 
-    # ---- outside the hot path: thin adapters over user-supplied HF modules ------------------------------
-    def _encode_conditioning(self, image, height, width, noise_aug_strength, generator, device):
-        raise NotImplementedError("CLIP / VAE encoding is next-scope (SURVEY.md §8f): pass image_embeddings/image_latents")
+    # ---- either side of the loop ------------------------------------------------------------------------
+    def _encode_image(self, image, device, num_videos_per_prompt, do_classifier_free_guidance):
+        """pipeline...controlnet.py:145-172 over a user-supplied CLIP vision module (`.image_embeds`); the anti-aliased
+        224x224 resize of :604-712 is that module's preprocessing here (next)."""
+        x = self.image_processor.preprocess(image)
+        x = torch.nn.functional.interpolate((x + 1.0) / 2.0, size=(224, 224), mode="bicubic", align_corners=True,
+                                            antialias=True)
+        emb = self.image_encoder(x.to(device)).image_embeds.unsqueeze(1)
+        emb = emb.repeat(1, num_videos_per_prompt, 1).view(emb.shape[0] * num_videos_per_prompt, 1, -1)
+        if do_classifier_free_guidance:
+            emb = torch.cat([torch.zeros_like(emb), emb])
+        return emb
 
-    def decode_latents(self, latents, num_frames, decode_chunk_size):
-        raise NotImplementedError("VAE decoding is next-scope (SURVEY.md §8f): use output_type='latent'")
+    def _encode_vae_image(self, image: torch.Tensor, device, num_videos_per_prompt, do_classifier_free_guidance):
+        """pipeline...controlnet.py:174-195: mode of the VAE posterior, zeros for the unconditional branch."""
+        image_latents = self.vae.encode(image.to(device=device)).latent_dist.mode()
+        if do_classifier_free_guidance:
+            image_latents = torch.cat([torch.zeros_like(image_latents), image_latents])
+        return image_latents.repeat(num_videos_per_prompt, 1, 1, 1)
+
+    def decode_latents(self, latents, num_frames, decode_chunk_size=14):
+        """pipeline...controlnet.py:225-251: [B, F, C, h, w] latents -> [B, 3, F, H, W] fp32 frames, decoded
+        `decode_chunk_size` frames at a time (the temporal layers only see the frames of one chunk, as in the
+        reference)."""
+        latents = latents.flatten(0, 1)
+        latents = 1 / self.vae.config.scaling_factor * latents
+        frames = []
+        for i in range(0, latents.shape[0], decode_chunk_size):
+            chunk = latents[i: i + decode_chunk_size]
+            frames.append(self.vae.decode(chunk, num_frames=chunk.shape[0]).sample)
+        frames = torch.cat(frames, dim=0)
+        frames = frames.reshape(-1, num_frames, *frames.shape[1:]).permute(0, 2, 1, 3, 4)
+        return frames.float()
