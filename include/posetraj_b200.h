@@ -131,8 +131,9 @@ typedef struct PtGemmArgs {
   int32_t out_halo;           /* map_mode 1 only: write the zero-haloed layout of the (strided) output image instead
                                * of the compact one: orow = (img*(oH+1) + y/ostride)*(oW+1) + x/ostride; halo rows
                                * are never written (the caller zeroes the buffer once) */
-  int32_t act_silu;           /* apply SiLU after acc_scale and before the residual terms (cond-embedding convs,
-                               * models/controlnet_sdv.py:103-109) */
+  int32_t act_silu;           /* activation after acc_scale and before the residual terms: 0 none, 1 SiLU (cond-embedding
+                               * convs, models/controlnet_sdv.py:103-109), 2 GELU (exact erf; CLIP ViT-H MLP),
+                               * 3 quick-GELU x*sigmoid(1.702x) (CLIP ViT-L style configs) */
   int32_t cta_pair;           /* 1: run as clusters of two CTAs sharing 256 x block_n tiles (tcgen05 cta_group::2);
                                * tmap_b's box is block_n/2 rows in both modes */
   int32_t rv_mod, rv_off;     /* see rowvec_mode 2 */
@@ -333,6 +334,43 @@ typedef struct PtTimeConvArgs {
   int32_t B, F, HW, C;
 } PtTimeConvArgs;
 int pt_time_conv3(const PtTimeConvArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Image-conditioning branch (pipeline/pipeline_stable_video_diffusion_     */
+/* controlnet.py:145-172 `_encode_image`, :602-712 `_resize_with_antialiasing`).               */
+/* ------------------------------------------------------------------------------------------ */
+/* One pass of the separable Gaussian pre-filter with reflect padding (`_gaussian_blur2d` / `_filter2d`, :652-712):
+ * out[p, y, x] = sum_i w[i] * in[p, y, x + i - (k-1)/2]  (axis 0)   or the same along y (axis 1) */
+typedef struct PtBlurArgs {
+  const float* in;          /* [planes, H, W] fp32 */
+  float* out;               /* [planes, H, W] fp32 */
+  const float* w;           /* device [k] */
+  int32_t planes, H, W, k, axis;
+} PtBlurArgs;
+int pt_blur_reflect(const PtBlurArgs* a, void* stream);
+
+/* torch.nn.functional.interpolate(mode="bicubic", align_corners=True) (:631) of one image's planes to S x S, written as
+ * fp32 planes [C, S, S] (out_f32, optional) and/or as the bf16 im2col rows of CLIP's patch embedding (out_patches,
+ * optional): row = patch (py * S/P + px), column = c*P*P + ky*P + kx, columns C*P*P .. ld-1 untouched (zero them once) */
+typedef struct PtBicubicArgs {
+  const float* in;          /* [C, H, W] fp32 */
+  int32_t C, H, W, S, P;
+  float* out_f32;
+  void* out_patches;        /* bf16 [ (S/P)^2, ld ] */
+  int32_t ld;
+} PtBicubicArgs;
+int pt_bicubic_resize(const PtBicubicArgs* a, void* stream);
+
+/* Multi-head self-attention for short sequences and any head_dim <= 128 (CLIP vision tower: 257 tokens, 16 heads of
+ * 80): qkv rows are [q | k | v] of width 3C, head h owns columns h*hd .. (h+1)*hd of each third; fp32 softmax */
+typedef struct PtAttnSmallArgs {
+  const void* qkv;          /* bf16 [S, 3C] */
+  int32_t ld;
+  void* out;                /* bf16 [S, C] */
+  int32_t out_ld;
+  int32_t S, heads, head_dim;
+} PtAttnSmallArgs;
+int pt_attention_small(const PtAttnSmallArgs* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* R1: trajectory maps (scripts/run_inference_vipseg_json_repro.py:438-449, utils/dataset.py:  */

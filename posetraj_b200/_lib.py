@@ -135,6 +135,16 @@ PtSoftmaxArgs = _st("PtSoftmaxArgs", [
 PtTimeConvArgs = _st("PtTimeConvArgs", [
     ("in_", vp), ("ld", i32), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("F", i32), ("HW", i32), ("C", i32)])
 
+PtBlurArgs = _st("PtBlurArgs", [
+    ("in_", vp), ("out", vp), ("w", vp), ("planes", i32), ("H", i32), ("W", i32), ("k", i32), ("axis", i32)])
+
+PtBicubicArgs = _st("PtBicubicArgs", [
+    ("in_", vp), ("C", i32), ("H", i32), ("W", i32), ("S", i32), ("P", i32), ("out_f32", vp), ("out_patches", vp),
+    ("ld", i32)])
+
+PtAttnSmallArgs = _st("PtAttnSmallArgs", [
+    ("qkv", vp), ("ld", i32), ("out", vp), ("out_ld", i32), ("S", i32), ("heads", i32), ("head_dim", i32)])
+
 PtRasterArgs = _st("PtRasterArgs", [
     ("tracks", vp), ("K", i32), ("F", i32), ("H", i32), ("W", i32), ("order", vp), ("out_f32", vp), ("out_u8", vp),
     ("swap_per_track", i32)])
@@ -170,6 +180,9 @@ _SIGNATURES = {
     "pt_axpy_bf16": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_rasterize_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "pt_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_blur_reflect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_bicubic_resize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_attention_small": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_time_conv3": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 

@@ -121,6 +121,9 @@ extern "C" int pt_sizeof(const char* name) {
   if (!strcmp(name, "PtRowBlockCopyArgs")) return (int)sizeof(PtRowBlockCopyArgs);
   if (!strcmp(name, "PtAxpyArgs")) return (int)sizeof(PtAxpyArgs);
   if (!strcmp(name, "PtSoftmaxArgs")) return (int)sizeof(PtSoftmaxArgs);
+  if (!strcmp(name, "PtBlurArgs")) return (int)sizeof(PtBlurArgs);
+  if (!strcmp(name, "PtBicubicArgs")) return (int)sizeof(PtBicubicArgs);
+  if (!strcmp(name, "PtAttnSmallArgs")) return (int)sizeof(PtAttnSmallArgs);
   if (!strcmp(name, "PtTimeConvArgs")) return (int)sizeof(PtTimeConvArgs);
   return -1;
 }

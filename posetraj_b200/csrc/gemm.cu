@@ -109,6 +109,13 @@ PT_DEVICE float geglu_gate(float value, float g) {
   return value * g * phi;
 }
 
+// activation codes of PtGemmArgs.act_silu: 1 SiLU, 2 GELU (exact erf), 3 quick-GELU x*sigmoid(1.702 x)
+PT_DEVICE float apply_act(int act, float v) {
+  if (act == 1) return silu_f(v);
+  if (act == 2) return gelu_erf_f(v);
+  return v * rcp_approx(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * v));
+}
+
 // slow path of the store side: fewer than 8 valid columns in this lane's segment (only conv_out: n_out = 4)
 __device__ __noinline__ void epilogue_tail(const GemmParams& p, const float* acc, const float* sb_seg, int ncol,
                                            int nvalid, long long orow, int grp) {
@@ -116,7 +123,7 @@ __device__ __noinline__ void epilogue_tail(const GemmParams& p, const float* acc
     float v = acc[j] + sb_seg[j];
     if (p.rowvec_mode != 0) v += __ldg(p.rowvec + (size_t)grp * p.rowvec_ld + ncol + j);
     v *= p.acc_scale;
-    if (p.act_silu) v = silu_f(v);
+    if (p.act_silu) v = apply_act(p.act_silu, v);
     if (p.res1 != nullptr) v = fmaf(p.res1_scale, __bfloat162float(p.res1[(size_t)orow * p.res_ld + ncol + j]), v);
     if (p.res2 != nullptr) v = fmaf(p.res2_scale, __bfloat162float(p.res2[(size_t)orow * p.res_ld + ncol + j]), v);
     const size_t off = (size_t)orow * p.out_ld + ncol + j;
@@ -603,7 +610,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             for (int j = 0; j < 8; ++j) f[j] *= p.acc_scale;
             if (p.act_silu) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+              for (int j = 0; j < 8; ++j) f[j] = apply_act(p.act_silu, f[j]);
             }
             if (p.res1 != nullptr) {
               float r[8];

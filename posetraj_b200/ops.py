@@ -120,7 +120,7 @@ class Gemm:
                  res2: Optional[torch.Tensor] = None, res2_scale: float = 1.0,
                  out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_scale: float = 0.0,
                  halo: Optional[tuple] = None, ostride: int = 1, out_halo: bool = False,
-                 act_silu: bool = False, name: str = "gemm", alg_k: Optional[int] = None,
+                 act_silu=False, name: str = "gemm", alg_k: Optional[int] = None,
                  cta_pair: Optional[bool] = None):
         assert a0.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
         assert a0.dim() == 2 and w.dim() == 2 and a0.stride(1) == 1 and w.stride(1) == 1
@@ -224,7 +224,7 @@ class Gemm:
         else:
             a.map_mode = 0
             assert out_rows == rows_total
-        a.act_silu = 1 if act_silu else 0
+        a.act_silu = int(act_silu)   # 0 none, 1 / True SiLU, 2 GELU (erf), 3 quick-GELU
         a.cta_pair = 1 if cta_pair else 0
         # algorithmic FLOPs (bench.py roofline): true output pixels x true (un-padded) K
         valid_rows = out_rows if not (halo is not None and out_halo) else n_img * a.oH * a.oW
@@ -557,6 +557,59 @@ class TimeConv3(_Op):
         a.B, a.F, a.HW, a.C = batch, frames, hw, Cc
         self.alg_bytes = x.shape[0] * Cc * 8.0
         self._finish(a, (x, w, bias, out), name)
+
+
+class BlurReflect(_Op):
+    """One pass of the reference's separable Gaussian pre-filter (reflect padding) on fp32 planes."""
+    fn_name = "pt_blur_reflect"
+    kind = "clip_misc"
+
+    def __init__(self, x, out, w, *, axis: int, name=None):
+        a = _lib.PtBlurArgs()
+        assert x.dtype == torch.float32 and out.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+        assert x.shape == out.shape and x.dim() == 3 and w.dtype == torch.float32 and w.is_contiguous()
+        a.in_, a.out, a.w = x.data_ptr(), out.data_ptr(), w.data_ptr()
+        a.planes, a.H, a.W = x.shape
+        a.k, a.axis = w.numel(), axis
+        self.alg_bytes = x.numel() * 8.0
+        self._finish(a, (x, out, w), name)
+
+
+class BicubicResize(_Op):
+    """bicubic, align_corners=True, to S x S: fp32 planes and/or bf16 patch-embedding rows."""
+    fn_name = "pt_bicubic_resize"
+    kind = "clip_misc"
+
+    def __init__(self, x, *, size: int, out_f32=None, out_patches=None, patch: int = 1, name=None):
+        a = _lib.PtBicubicArgs()
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+        a.in_ = x.data_ptr()
+        a.C, a.H, a.W = x.shape
+        a.S, a.P = size, patch
+        if out_f32 is not None:
+            assert out_f32.dtype == torch.float32 and out_f32.is_contiguous() and out_f32.numel() == a.C * size * size
+            a.out_f32 = out_f32.data_ptr()
+        if out_patches is not None:
+            assert out_patches.dtype == torch.bfloat16 and out_patches.stride(1) == 1
+            assert out_patches.shape[0] == (size // patch) ** 2
+            a.out_patches, a.ld = out_patches.data_ptr(), out_patches.stride(0)
+        self._finish(a, (x, out_f32, out_patches), name)
+
+
+class AttnSmall(_Op):
+    """Self-attention for short sequences / any head_dim <= 128 (CLIP vision tower)."""
+    fn_name = "pt_attention_small"
+    kind = "clip_attn"
+
+    def __init__(self, qkv, out, *, heads: int, name=None):
+        a = _lib.PtAttnSmallArgs()
+        S, c3 = qkv.shape
+        assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and out.shape == (S, c3 // 3)
+        assert qkv.stride(1) == 1 and out.stride(1) == 1 and (c3 // 3) % heads == 0
+        a.qkv, a.ld, a.out, a.out_ld = qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0)
+        a.S, a.heads, a.head_dim = S, heads, c3 // 3 // heads
+        self.alg_flops = 4.0 * S * S * (c3 // 3)
+        self._finish(a, (qkv, out), name)
 
 
 class TorchOp:

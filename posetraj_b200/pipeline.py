@@ -14,8 +14,9 @@ What runs where
   * the VAE on either side of the loop is posetraj_b200.vae.AutoencoderKLTemporalDecoder on
     the same kernel library: `_encode_vae_image` (:174-195) for the conditioning image, `decode_latents` (:225-251)
     + `tensor2vid` (:70-82) for output_type "pt" / "np" / "pil".  `image_latents=` may be passed instead of a VAE.
-  * CLIP image encoding is not on this library yet: hand the pipeline `image_embeddings=`
-    (or construct it with an `image_encoder` module exposing `.image_embeds`, as the reference does).
+  * the image-conditioning branch is posetraj_b200.clip: the reference's anti-aliased resize
+    (:602-712) and the CLIP ViT-H/14 vision tower on the same library (`_encode_image`, :145-172);
+    `image_embeddings=` may be passed instead of an image_encoder.
 """
 from __future__ import annotations
 
@@ -422,12 +423,20 @@ class StableVideoDiffusionPipelineControlNet:
 
     # ---- either side of the loop ------------------------------------------------------------------------
     def _encode_image(self, image, device, num_videos_per_prompt, do_classifier_free_guidance):
-        """pipeline...controlnet.py:145-172 over a user-supplied CLIP vision module (`.image_embeds`); the anti-aliased
-        224x224 resize of :604-712 is that module's preprocessing here (next)."""
-        x = self.image_processor.preprocess(image)
-        x = torch.nn.functional.interpolate((x + 1.0) / 2.0, size=(224, 224), mode="bicubic", align_corners=True,
-                                            antialias=True)
-        emb = self.image_encoder(x.to(device)).image_embeds.unsqueeze(1)
+        """pipeline...controlnet.py:145-172: PIL / numpy images become [0, 1] tensors (`pil_to_numpy` + `numpy_to_pt`;
+        tensors are taken as they are), `_resize_with_antialiasing` to 224x224 (:602-712), CLIP `image_embeds`.  Like the
+        reference, neither the [-1, 1] mapping nor CLIP's mean/std normalisation is applied here.  With
+        posetraj_b200.clip.CLIPVisionModelWithProjection the resize writes the patch rows of the tower directly."""
+        from .clip import resize_with_antialiasing
+        if torch.is_tensor(image):
+            x = image if image.dim() == 4 else image.unsqueeze(0)
+        else:
+            x = (self.image_processor.preprocess(image) + 1.0) / 2.0   # == numpy_to_pt(pil_to_numpy(image))
+        x = x.to(device=device, dtype=F32)
+        if hasattr(self.image_encoder, "encode_image"):
+            emb = self.image_encoder.encode_image(x)
+        else:
+            emb = self.image_encoder(resize_with_antialiasing(x, (224, 224))).image_embeds.unsqueeze(1)
         emb = emb.repeat(1, num_videos_per_prompt, 1).view(emb.shape[0] * num_videos_per_prompt, 1, -1)
         if do_classifier_free_guidance:
             emb = torch.cat([torch.zeros_like(emb), emb])
