@@ -216,6 +216,57 @@ def _synthetic_tracks(frames):
              for k in range(frames)]]
 
 
+def full_pipeline_leg(unet, cnet, tracks, dev):
+    """Extra (not the contract's metric): one whole video through the public API on this library's kernels only — host
+    uint8 image + host tracks -> R1 rasteriser, anti-aliased resize + CLIP ViT-H/14, VAE encode, 25 denoise steps, VAE
+    temporal decode -> 14 x 320 x 576 frames on the host (SURVEY.md §8f rows 2-3 next to the hot path)."""
+    import numpy as np
+    import torch
+    from posetraj_b200.clip import CLIPVisionConfig, CLIPVisionModelWithProjection
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    from posetraj_b200.trajectory import rasterize_tracks
+    from posetraj_b200.vae import AutoencoderKLTemporalDecoder, VaeConfig
+    try:
+        vae = AutoencoderKLTemporalDecoder.from_random(VaeConfig(), dev, seed=0)
+        clip = CLIPVisionModelWithProjection.from_random(CLIPVisionConfig(), dev, seed=0)
+        pipe = StableVideoDiffusionPipelineControlNet(vae=vae, image_encoder=clip, unet=unet, controlnet=cnet)
+        H, W = LAT_H * 8, LAT_W * 8
+        image = np.random.default_rng(7).integers(0, 256, size=(H, W, 3), dtype=np.uint8).astype(np.float32) / 255.0
+
+        def call():
+            cond = rasterize_tracks(tracks, FRAMES, H, W, dev, output="f32")
+            out = pipe(image, cond, height=H, width=W, num_frames=FRAMES, num_inference_steps=SAMPLING_STEPS,
+                       generator=torch.Generator().manual_seed(0), output_type="np")
+            return out.frames[0]
+
+        frames = call()
+        if frames.shape != (FRAMES, H, W, 3) or not np.isfinite(frames).all():
+            return {"error": f"bad frames {frames.shape}"}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 2
+        for _ in range(n):
+            call()
+        torch.cuda.synchronize()
+        s_per_video = (time.perf_counter() - t0) / n
+        # stage split with CUDA events (device time of each stage, inputs already on the device)
+        def dev_ms(fn):
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            return round(e0.elapsed_time(e1), 3)
+        img_d = torch.from_numpy(image).permute(2, 0, 1)[None].to(dev)
+        lat = torch.randn(FRAMES, 4, LAT_H, LAT_W, device=dev)
+        stages = {"resize_clip_ms": dev_ms(lambda: clip.encode_image(img_d)),
+                  "vae_encode_ms": dev_ms(lambda: vae.encode(img_d * 2 - 1)),
+                  "vae_decode_ms": dev_ms(lambda: vae.decode(lat, num_frames=FRAMES))}
+        return {"s_per_video": round(s_per_video, 4), "videos_per_min": round(60.0 / s_per_video, 2), "stages": stages,
+                "api": "StableVideoDiffusionPipelineControlNet.__call__(host image, tracks -> rasterize_tracks, output_type='np'): "
+                       "CLIP ViT-H/14 632M + VAE 97.7M random-init, 25 steps, frames [14,320,576,3] returned on the host"}
+    except Exception as e:  # the extra must never take the contract line down with it
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def run_own(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -364,6 +415,8 @@ def run_own(args):
             "kernel_classes": per_class,
             "lib_launch_count": int(_lib.lib().pt_launch_count()),
         }
+        if world == 1:
+            line["full_pipeline"] = full_pipeline_leg(unet, cnet, tracks, dev)
         if world == 1 and not args.no_cpu_baseline:
             v, t_step, cores, sample = cpu_oracle_steps_per_sec(1, 1, budget_s=40.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
