@@ -137,6 +137,23 @@ typedef struct PtGemmArgs {
   int32_t cta_pair;           /* 1: run as clusters of two CTAs sharing 256 x block_n tiles (tcgen05 cta_group::2);
                                * tmap_b's box is block_n/2 rows in both modes */
   int32_t rv_mod, rv_off;     /* see rowvec_mode 2 */
+  /* Fused all-to-all of the frame-sharded plan (SURVEY.md 8e "Frames"): instead of writing `out`, the epilogue
+   * scatters every finished output row straight into the buffer of the rank that owns it in the OTHER sharding
+   * (frames <-> pixels), over NVLink peer memory — the GEMM and the exchange are one kernel, no pack / NCCL / unpack.
+   * The local output row is r = (b*sc_J + j)*sc_S + s; rank q owns [sc_start[q], sc_start[q] + sc_count[q]) of the
+   * split axis.
+   *   1: split the INNER axis s (frame layout -> pixel layout):
+   *        row on q = (b*sc_kept_total + sc_kept_off + j)*sc_count[q] + (s - sc_start[q])
+   *   2: split the MIDDLE axis j (pixel layout -> frame layout):
+   *        row on q = (b*sc_count[q] + (j - sc_start[q]))*sc_kept_total + sc_kept_off + s
+   * sc_peer[q] is the (peer-mapped) base of rank q's destination, row stride out_ld; bf16 outputs with n_out % 8 == 0
+   * only; `out` / `out2` are ignored.  The caller orders consumers behind a cross-rank barrier. */
+  int32_t scatter_mode;
+  int32_t sc_world;           /* <= 8 */
+  int32_t sc_J, sc_S;
+  int32_t sc_kept_off, sc_kept_total;
+  int32_t sc_start[8], sc_count[8];
+  void* sc_peer[8];
 } PtGemmArgs;
 int pt_gemm(const PtGemmArgs* a, void* stream);
 

@@ -73,6 +73,9 @@ class PtGemmArgs(C.Structure):
         ("pW1", C.c_int32), ("pH1", C.c_int32), ("ostride", C.c_int32), ("oW", C.c_int32), ("oH", C.c_int32),
         ("out_halo", C.c_int32), ("act_silu", C.c_int32), ("cta_pair", C.c_int32),
         ("rv_mod", C.c_int32), ("rv_off", C.c_int32),
+        ("scatter_mode", C.c_int32), ("sc_world", C.c_int32), ("sc_J", C.c_int32), ("sc_S", C.c_int32),
+        ("sc_kept_off", C.c_int32), ("sc_kept_total", C.c_int32),
+        ("sc_start", C.c_int32 * 8), ("sc_count", C.c_int32 * 8), ("sc_peer", C.c_void_p * 8),
     ]
 
 

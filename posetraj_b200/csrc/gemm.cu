@@ -63,6 +63,10 @@ struct GemmParams {
   const bf16* aux;
   float aux_scale;
   int map_mode, pW1, pH1, ostride, oW, oH, out_halo, act_silu;
+  // fused all-to-all (PtGemmArgs.scatter_mode): rows leave through NVLink peer memory
+  int scatter_mode, sc_world, sc_J, sc_S, sc_kept_off, sc_kept_total;
+  int sc_start[8], sc_count[8];
+  bf16* sc_peer[8];
 };
 
 struct alignas(64) TmapParam {
@@ -138,7 +142,8 @@ __device__ __noinline__ void epilogue_tail(const GemmParams& p, const float* acc
 }
 
 struct EpiRows {
-  long long out_off[4];  // element offset of the 4 output rows this lane finishes
+  bf16* out_ptr[4];      // first element of the 4 output rows this lane finishes (local, or a peer's in scatter mode)
+  long long out_off[4];  // their element offset in the local row space (aux / out2)
   long long res_off[4];
   int grp[4];
   uint32_t vmask;
@@ -151,7 +156,6 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
                              int chunks, int hsel, int lane, const ArriveFn& arrive_drained) {
   const int sub_row = lane >> 2;
   const int seg = lane & 3;
-  bf16* out = reinterpret_cast<bf16*>(p.out);
   bf16* out2 = reinterpret_cast<bf16*>(p.out2);
   const bool has_res2 = kRes && p.res2 != nullptr;
   const bool has_res1 = kRes && p.res1 != nullptr;
@@ -232,7 +236,7 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
           for (int j = 0; j < 8; ++j) f[j] = fmaf(p.res2_scale, r[j], f[j]);
         }
       }
-      stg_u4(out + R.out_off[i] + ncol, pack8(f));
+      stg_u4(R.out_ptr[i] + ncol, pack8(f));
       if constexpr (kOut2) {
         float r[8];
         unpack8(ax[i], r);
@@ -459,6 +463,23 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
           R.out_off[i] = (long long)orow4[i] * p.out_ld;
           R.res_off[i] = (long long)orow4[i] * p.res_ld;
           R.grp[i] = grp4[i];
+          if (p.scatter_mode == 0) {
+            R.out_ptr[i] = reinterpret_cast<bf16*>(p.out) + R.out_off[i];
+          } else {
+            // (b, j, s) of the local row, owner q of its split-axis index, row in q's layout (see PtGemmArgs)
+            const int per_b = p.sc_J * p.sc_S;
+            const int b = orow4[i] / per_b;
+            const int rem = orow4[i] - b * per_b;
+            const int j = rem / p.sc_S;
+            const int s = rem - j * p.sc_S;
+            const int u = p.scatter_mode == 1 ? s : j;
+            int q = 0;
+            while (q + 1 < p.sc_world && u >= p.sc_start[q] + p.sc_count[q]) ++q;
+            const long long drow = p.scatter_mode == 1
+                ? ((long long)b * p.sc_kept_total + p.sc_kept_off + j) * p.sc_count[q] + (s - p.sc_start[q])
+                : ((long long)b * p.sc_count[q] + (j - p.sc_start[q])) * p.sc_kept_total + p.sc_kept_off + s;
+            R.out_ptr[i] = p.sc_peer[q] + drow * p.out_ld;
+          }
         }
         R.vmask = vmask;
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -690,6 +711,16 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: out2 without aux");
   if (a->geglu && (a->rowvec_mode != 0 || a->res1 != nullptr || a->res2 != nullptr || a->out2 != nullptr || a->acc_scale != 1.0f))
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: GEGLU tiles support a bias-only epilogue");
+  if (a->scatter_mode != 0) {
+    if (a->scatter_mode < 0 || a->scatter_mode > 2 || a->sc_world < 1 || a->sc_world > 8 || a->sc_J < 1 || a->sc_S < 1 ||
+        a->sc_kept_total < 1 || a->sc_kept_off < 0)
+      return pt_fail(cudaErrorInvalidValue, "pt_gemm: bad scatter geometry");
+    for (int q = 0; q < a->sc_world; ++q)
+      if (a->sc_peer[q] == nullptr || a->sc_count[q] < 1 || (reinterpret_cast<uintptr_t>(a->sc_peer[q]) & 15u) != 0)
+        return pt_fail(cudaErrorInvalidValue, "pt_gemm: scatter needs a 16-byte aligned peer buffer and >= 1 item per rank");
+    if (a->geglu || a->out2 != nullptr || a->out_dtype != PT_DT_BF16 || (a->n_out % 8) != 0 || a->act_silu || a->out_halo)
+      return pt_fail(cudaErrorInvalidValue, "pt_gemm: scatter supports plain bf16 outputs with n_out % 8 == 0 only");
+  }
   if (a->geglu && (a->out_dtype != PT_DT_BF16 || (a->n_out % 8) != 0 || (a->out_ld % 8) != 0 ||
                    (reinterpret_cast<uintptr_t>(a->out) & 15u) != 0))
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: GEGLU output must be bf16, 16-byte aligned, with n_out and out_ld multiples of 8");
@@ -755,6 +786,14 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.oH = a->oH;
   p.out_halo = a->out_halo;
   p.act_silu = a->act_silu;
+  p.scatter_mode = a->scatter_mode;
+  p.sc_world = a->sc_world; p.sc_J = a->sc_J > 0 ? a->sc_J : 1; p.sc_S = a->sc_S > 0 ? a->sc_S : 1;
+  p.sc_kept_off = a->sc_kept_off; p.sc_kept_total = a->sc_kept_total;
+  for (int q = 0; q < 8; ++q) {
+    p.sc_start[q] = a->sc_start[q];
+    p.sc_count[q] = a->sc_count[q];
+    p.sc_peer[q] = reinterpret_cast<bf16*>(a->sc_peer[q]);
+  }
 
   const size_t smem_bytes = (size_t)kSmemCtl + (size_t)stage_area + (size_t)p.stages * p.stage_bytes + 1024;
   typedef void (*KernelFn)(TmapParam, TmapParam, TmapParam, GemmParams);
@@ -787,6 +826,8 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     epi = kEpiFast + (p.rowvec_mode != 0 ? 1 : 0) + ((p.res1 != nullptr || p.res2 != nullptr) ? 2 : 0) +
           (p.out2 != nullptr ? 4 : 0);
   }
+  if (p.scatter_mode != 0 && epi < kEpiFast)
+    return pt_fail(cudaErrorInvalidValue, "pt_gemm: scatter needs 16-byte aligned operands and strides (lean epilogue)");
   const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
   const int sms = pt_num_sms();
 

@@ -127,7 +127,7 @@ class Pool:
 
     def put(self, *ts) -> None:
         for t in ts:
-            if t is not None:
+            if t is not None and not getattr(t, "_pt_no_pool", False):   # peer-mapped exchange buffers are dedicated
                 self.free[(t.shape[0], t.shape[1], t.dtype)].append(t)
 
 

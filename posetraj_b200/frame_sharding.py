@@ -16,9 +16,19 @@ the GEMM epilogue (PtGemmArgs.rv_mod / rv_off) so the quirk is reproduced exactl
 
 The CFG + Euler update is elementwise, so every rank updates only its own frames' latents; the final latents are
 all-gathered once per call.  With NCCL the whole step — kernels and collectives — is captured into one CUDA graph.
+
+Fused exchange (default on NCCL groups, PT_P2P=0 disables): all four tensors that cross the sharding boundary are
+GEMM outputs consumed only by the exchange (spatial conv2 / spatial ff.out going to the pixel layout, temporal conv2 /
+temporal ff.out+mix coming back), so the GEMM's epilogue scatters each finished row straight into the owning rank's
+buffer over NVLink peer memory (PtGemmArgs.scatter_mode; buffers from torch symmetric memory): pack kernel, NCCL
+all-to-all and unpack kernel become ZERO extra kernels, and one device-side barrier per exchange orders the consumers.
+Every exchange owns a dedicated destination buffer, so a buffer is only rewritten one whole step later, after >= 100
+barriers that its readers have passed: no second ("ready to receive") barrier is needed.  gloo groups (test rigs with
+several ranks on one GPU) keep the pack / all-to-all / unpack path.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -111,6 +121,59 @@ class AllReduceSum(_Collective):
             self.t.copy_(h)
 
 
+class SymmArena:
+    """Peer-mapped exchange buffers: chunks of torch symmetric memory, sub-allocated identically on every rank (all
+    ranks build the same plan and ask for the same worst-case sizes in the same order, so offsets agree)."""
+    CHUNK = 256 << 20
+
+    def __init__(self, device, group):
+        import torch.distributed as dist
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.chunks = []     # [buffer (uint8), handle, used bytes]
+        self.bytes = 0
+
+    def _new_chunk(self, nbytes: int) -> None:
+        import torch.distributed._symmetric_memory as sm
+        size = max(self.CHUNK, (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20))
+        buf = sm.empty(size, dtype=torch.uint8, device=self.device)
+        hdl = sm.rendezvous(buf, self.group)
+        buf.zero_()
+        self.chunks.append([buf, hdl, 0])
+        self.bytes += size
+
+    def take(self, nbytes: int) -> Tuple[int, int]:
+        nbytes = (nbytes + 255) // 256 * 256
+        if not self.chunks or self.chunks[-1][2] + nbytes > self.chunks[-1][0].numel():
+            self._new_chunk(nbytes)
+        c = self.chunks[-1]
+        off = c[2]
+        c[2] += nbytes
+        return len(self.chunks) - 1, off
+
+    def view(self, slot: Tuple[int, int], rows: int, cols: int) -> torch.Tensor:
+        buf = self.chunks[slot[0]][0]
+        t = buf[slot[1]: slot[1] + rows * cols * 2].view(BF16).view(rows, cols)
+        t._pt_no_pool = True
+        return t
+
+    def peer_ptrs(self, slot: Tuple[int, int]) -> List[int]:
+        return [int(p) + slot[1] for p in self.chunks[slot[0]][1].buffer_ptrs]
+
+    def barrier(self) -> None:
+        self.chunks[0][1].barrier(channel=0)
+
+
+class SymmBarrier(_Collective):
+    """Device-side barrier over the symmetric-memory signal pads (no NCCL): every rank's scattered rows have landed."""
+
+    def __init__(self, arena: SymmArena, name="barrier"):
+        self.arena, self.name = arena, name
+
+    def launch(self, stream_ptr: int) -> None:
+        self.arena.barrier()
+
+
 class ShardedNetPlan(NetPlan):
     """NetPlan of one rank: spatial geometry = this rank's frames, temporal geometry = this rank's pixel slices."""
 
@@ -122,6 +185,12 @@ class ShardedNetPlan(NetPlan):
         if self.nf < 1:
             raise ValueError("more ranks than frames")
         self._sums = []
+        import torch.distributed as dist
+        self.arena: Optional[SymmArena] = kw.pop("arena", None)
+        self.p2p = (world > 1 and os.environ.get("PT_P2P", "1") != "0" and dist.is_initialized()
+                    and dist.get_backend(group) == "nccl")
+        if self.p2p and self.arena is None:
+            self.arena = SymmArena(device, group)
         super().__init__(kind, cfg, weights, batch=batch, frames=self.nf, height=height, width=width, device=device, **kw)
 
     # ---- layout exchange ------------------------------------------------------------------------------------
@@ -161,6 +230,32 @@ class ShardedNetPlan(NetPlan):
         self.pool.put(send_buf, recv_buf)
         return out
 
+    def _gemm_exchange(self, direction: str, HW: int, a0, wt, n_cols: int, *, name: str, **kw) -> torch.Tensor:
+        """A GEMM whose output only exists to change sharding: 'f2p' (frame layout -> pixel layout) or 'p2f'.
+        P2P: the epilogue scatters the rows into the owners' buffers (one kernel) + one barrier.  Otherwise: GEMM into a
+        local tensor, then pack / all-to-all / unpack."""
+        B, nf, Ft = self.B, self.nf, self.F_total
+        sh = self._pix(HW)
+        p0, npx = sh[self.rank]
+        if not self.p2p:
+            tmp = self._gemm(a0, wt, n_cols, name=name, **kw)
+            out = (self.to_pixel_layout if direction == "f2p" else self.to_frame_layout)(tmp, HW, name)
+            self.pool.put(tmp)
+            return out
+        if direction == "f2p":
+            slot = self.arena.take(B * Ft * max(c for _, c in sh) * n_cols * 2)
+            local = self.arena.view(slot, B * Ft * npx, n_cols)
+            spec = dict(mode=1, B=B, J=nf, S=HW, kept_off=self.f0, kept_total=Ft, starts=[s for s, _ in sh],
+                        counts=[c for _, c in sh], peers=self.arena.peer_ptrs(slot))
+        else:
+            slot = self.arena.take(B * max(c for _, c in self.fshards) * HW * n_cols * 2)
+            local = self.arena.view(slot, B * nf * HW, n_cols)
+            spec = dict(mode=2, B=B, J=Ft, S=npx, kept_off=p0, kept_total=HW, starts=[s for s, _ in self.fshards],
+                        counts=[c for _, c in self.fshards], peers=self.arena.peer_ptrs(slot))
+        self._gemm(a0, wt, n_cols, out=local, scatter=spec, name=name + "+" + direction, **kw)
+        self.step_ops.append(SymmBarrier(self.arena, name=name + ".barrier"))
+        return local
+
     def _gn_temporal(self, x: torch.Tensor, key: str, HW: int, npx: int, eps: float) -> torch.Tensor:
         """5-D GroupNorm of a pixel-sharded tensor: statistics span all ranks."""
         Cc = x.shape[1]
@@ -196,15 +291,14 @@ class ShardedNetPlan(NetPlan):
                             name=s + "conv_shortcut")
         else:
             sc = x0
-        xs = self._gemm(g2, w.conv3(s + "conv2.weight"), cout, taps=taps, bias=w.f32(s + "conv2.bias"), res1=sc,
-                        halo=hw, out_rows=rows, name=s + "conv2")
+        # the spatial block's output goes straight to the pixel layout (fused into the conv2 epilogue with P2P)
+        xs_p = self._gemm_exchange("f2p", HW, g2, w.conv3(s + "conv2.weight"), cout, taps=taps, bias=w.f32(s + "conv2.bias"),
+                                   res1=sc, halo=hw, out_rows=rows, name=s + "conv2")
         self.pool.put(g2)
         if sc is not x0:
             self.pool.put(sc)
         # TemporalResnetBlock on all frames of this rank's pixel slice
         npx = self._pix(HW)[self.rank][1]
-        xs_p = self.to_pixel_layout(xs, HW, prefix + "temporal")
-        self.pool.put(xs)
         t1 = self._gn_temporal(xs_p, t + "norm1", HW, npx, eps)
         t2 = self._gemm(t1, w.tconv(t + "conv1.weight"), cout, batches=B, taps=(-npx, 0, npx), bias=w.f32(t + "conv1.bias"),
                         rowvec=self._tvec(t, cout), rowvec_mode=1, rv=(Ft * npx, 1, 1), name=t + "conv1")
@@ -212,11 +306,9 @@ class ShardedNetPlan(NetPlan):
         t3 = self._gn_temporal(t2, t + "norm2", HW, npx, eps)
         self.pool.put(t2)
         alpha = w.alpha(prefix + "time_mixer.mix_factor")
-        out_p = self._gemm(t3, w.tconv(t + "conv2.weight"), cout, batches=B, taps=(-npx, 0, npx), bias=w.f32(t + "conv2.bias"),
-                           acc_scale=1.0 - alpha, res1=xs_p, name=t + "conv2")
+        out = self._gemm_exchange("p2f", HW, t3, w.tconv(t + "conv2.weight"), cout, batches=B, taps=(-npx, 0, npx),
+                                  bias=w.f32(t + "conv2.bias"), acc_scale=1.0 - alpha, res1=xs_p, name=t + "conv2")
         self.pool.put(t3, xs_p)
-        out = self.to_frame_layout(out_p, HW, prefix + "temporal")
-        self.pool.put(out_p)
         # the residual extras live in the frame layout: mid residual (res2) and ControlNet skip injection (out2/aux)
         if res2 is not None:
             self.step_ops.append(ops.Axpy(out, res2, out, 1.0, name=prefix + "res2"))
@@ -257,12 +349,11 @@ class ShardedNetPlan(NetPlan):
         f1 = self._gemm(l3, w.linear(sb + "ff.net.0.proj.weight"), 4 * Cc, geglu=True, bias=w.f32(sb + "ff.net.0.proj.bias"),
                         name=sb + "ff.geglu")
         self.pool.put(l3)
-        h3 = self._gemm(f1, w.linear(sb + "ff.net.2.weight"), Cc, bias=w.f32(sb + "ff.net.2.bias"), res1=h2, name=sb + "ff.out")
+        h3_p = self._gemm_exchange("f2p", HW, f1, w.linear(sb + "ff.net.2.weight"), Cc, bias=w.f32(sb + "ff.net.2.bias"),
+                                   res1=h2, name=sb + "ff.out")
         self.pool.put(f1, h2)
         # --- TemporalBasicTransformerBlock on all frames of this rank's pixel slice
         p0, npx = self._pix(HW)[self.rank]
-        h3_p = self.to_pixel_layout(h3, HW, prefix + "temporal")
-        self.pool.put(h3)
         rows_p = h3_p.shape[0]
         ht = self.pool.get(rows_p, Cc)
         l_in = self._ln(h3_p, tb + "norm_in", addvec=pos, hw=npx, frames=Ft, sum_out=ht)
@@ -288,11 +379,10 @@ class ShardedNetPlan(NetPlan):
                         name=tb + "ff.geglu")
         self.pool.put(l3t)
         alpha = w.alpha(prefix + "time_mixer.mix_factor")
-        hb_p = self._gemm(f2, w.linear(tb + "ff.net.2.weight"), Cc, bias=w.f32(tb + "ff.net.2.bias"), acc_scale=1.0 - alpha,
-                          res1=t2, res1_scale=1.0 - alpha, res2=h3_p, res2_scale=alpha, name=tb + "ff.out+mix")
+        hb = self._gemm_exchange("p2f", HW, f2, w.linear(tb + "ff.net.2.weight"), Cc, bias=w.f32(tb + "ff.net.2.bias"),
+                                 acc_scale=1.0 - alpha, res1=t2, res1_scale=1.0 - alpha, res2=h3_p, res2_scale=alpha,
+                                 name=tb + "ff.out+mix")
         self.pool.put(f2, t2, h3_p)
-        hb = self.to_frame_layout(hb_p, HW, prefix + "temporal")
-        self.pool.put(hb_p)
         out = self._gemm(hb, w.linear(prefix + "proj_out.weight"), Cc, bias=w.f32(prefix + "proj_out.bias"), res1=x,
                          out2=out2, aux=aux, aux_scale=aux_scale, name=prefix + "proj_out")
         self.pool.put(hb)
@@ -315,8 +405,12 @@ class FrameShardedEngine:
         self.guidance = torch.ones(self.nf, device=device, dtype=F32)
         self.step_index = torch.zeros(1, device=device, dtype=torch.int32)
         self.sigmas = torch.zeros(1024, device=device, dtype=F32)
+        import torch.distributed as dist
+        self.arena = None
+        if world > 1 and os.environ.get("PT_P2P", "1") != "0" and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            self.arena = SymmArena(device, group)    # one set of peer-mapped exchange buffers for both networks
         common = dict(batch=2, frames_total=frames, world=world, rank=rank, group=group, height=h, width=w, device=device,
-                      sigmas=self.sigmas, step_index=self.step_index)
+                      sigmas=self.sigmas, step_index=self.step_index, arena=self.arena)
         self.cplan = ShardedNetPlan("controlnet", controlnet.cfg, controlnet.weights, cond_hw=cond_hw, **controlnet.flags, **common)
         self.uplan = ShardedNetPlan("unet", unet.cfg, unet.weights, x_in=self.cplan.x_in, residual_bufs=self.cplan.res, **common)
         kw = dict(latents=self.latents, guidance=self.guidance, sigmas=self.sigmas, step_index=self.step_index,

@@ -121,7 +121,7 @@ class Gemm:
                  out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_scale: float = 0.0,
                  halo: Optional[tuple] = None, ostride: int = 1, out_halo: bool = False,
                  act_silu=False, name: str = "gemm", alg_k: Optional[int] = None,
-                 cta_pair: Optional[bool] = None):
+                 cta_pair: Optional[bool] = None, scatter: Optional[dict] = None):
         assert a0.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
         assert a0.dim() == 2 and w.dim() == 2 and a0.stride(1) == 1 and w.stride(1) == 1
         self.name = name
@@ -186,6 +186,10 @@ class Gemm:
                 a.rv_mod, a.rv_off = rv[3], rv[4]
         a.acc_scale = acc_scale
         out_rows = out.shape[0]
+        if scatter is not None:
+            # fused all-to-all: `out` is this rank's destination buffer in the OTHER sharding; the rows this GEMM
+            # produces (and its residual operands) live in the source layout of B * J * S rows
+            out_rows = scatter["B"] * scatter["J"] * scatter["S"]
         for r in (res1, res2):
             if r is not None:
                 assert r.dtype == torch.bfloat16 and r.stride(1) == 1 and r.shape[0] == out_rows
@@ -224,6 +228,15 @@ class Gemm:
         else:
             a.map_mode = 0
             assert out_rows == rows_total
+        if scatter is not None:
+            assert out2 is None and out.dtype == torch.bfloat16 and not out_halo
+            starts, counts, peers = scatter["starts"], scatter["counts"], scatter["peers"]
+            assert len(starts) == len(counts) == len(peers) <= 8 and scatter["mode"] in (1, 2)
+            a.scatter_mode, a.sc_world = scatter["mode"], len(peers)
+            a.sc_J, a.sc_S = scatter["J"], scatter["S"]
+            a.sc_kept_off, a.sc_kept_total = scatter["kept_off"], scatter["kept_total"]
+            for q in range(len(peers)):
+                a.sc_start[q], a.sc_count[q], a.sc_peer[q] = starts[q], counts[q], peers[q]
         a.act_silu = int(act_silu)   # 0 none, 1 / True SiLU, 2 GELU (erf), 3 quick-GELU
         a.cta_pair = 1 if cta_pair else 0
         # algorithmic FLOPs (bench.py roofline): true output pixels x true (un-padded) K
