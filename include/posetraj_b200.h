@@ -187,6 +187,11 @@ typedef struct PtGroupNormArgs {
   int32_t mode;
   double* sums;
   double count;
+  /* mode 2 without an all-reduce: when n_peers > 0 the statistics are the sum, in rank order (identical bits on every
+   * rank), of the n_peers (<= 8) per-rank `sums` arrays sums_peers[q] — peer-mapped memory read over NVLink; the caller
+   * puts a cross-rank barrier between the mode-1 launches and this one */
+  int32_t n_peers;
+  const double* sums_peers[8];
 } PtGroupNormArgs;
 int pt_groupnorm(const PtGroupNormArgs* a, void* stream);
 /* bytes of PtGroupNormArgs.stats needed for this problem (-1 on bad arguments) */

@@ -90,7 +90,7 @@ PtGroupNormArgs = _st("PtGroupNormArgs", [
     ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32),
     ("rows_per_stat", i32), ("num_stat", i32), ("stats", vp), ("gamma", vp), ("beta", vp),
     ("eps", f32), ("silu", i32), ("out", vp), ("out_ld", i32), ("halo", i32), ("H", i32), ("W", i32),
-    ("mode", i32), ("sums", vp), ("count", C.c_double)])
+    ("mode", i32), ("sums", vp), ("count", C.c_double), ("n_peers", i32), ("sums_peers", C.c_void_p * 8)])
 
 PtLayerNormArgs = _st("PtLayerNormArgs", [
     ("x", vp), ("ld", i32), ("gamma", vp), ("beta", vp), ("eps", f32), ("out", vp), ("out_ld", i32),

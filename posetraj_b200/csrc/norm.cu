@@ -52,6 +52,8 @@ struct GnParams {
   int mode;       // 0 fused, 1 statistics only (-> sums), 2 normalise only (<- sums, count)
   double* sums;   // [num_stat, 32, 2]
   double count;   // mode 2: elements per (statistics, norm) group over ALL ranks
+  int n_peers;    // mode 2: > 0 = sum the per-rank sums of these peers (rank order) instead of reading `sums`
+  const double* sums_peers[8];
   int res_slots;  // rows per thread kept resident in shared memory between the two passes
   int res_off;    // byte offset of the resident area in dynamic shared memory
 };
@@ -254,8 +256,16 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   } else {
     // normalise only: statistics were reduced across ranks by the caller
     if (threadIdx.x < 32) {
-      const double a = p.sums[((size_t)stat * 32 + threadIdx.x) * 2];
-      const double b = p.sums[((size_t)stat * 32 + threadIdx.x) * 2 + 1];
+      double a = 0.0, b = 0.0;
+      if (p.n_peers > 0) {
+        for (int q = 0; q < p.n_peers; ++q) {   // fixed order: every rank computes bit-identical statistics
+          a += __ldcg(p.sums_peers[q] + ((size_t)stat * 32 + threadIdx.x) * 2);       // L1 bypass: peer memory
+          b += __ldcg(p.sums_peers[q] + ((size_t)stat * 32 + threadIdx.x) * 2 + 1);
+        }
+      } else {
+        a = p.sums[((size_t)stat * 32 + threadIdx.x) * 2];
+        b = p.sums[((size_t)stat * 32 + threadIdx.x) * 2 + 1];
+      }
       const double m = a / p.count;
       double var = b / p.count - m * m;
       if (var < 0) var = 0;
@@ -585,8 +595,12 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   p.out_ld = a->out_ld;
   p.halo = a->halo; p.H = a->H > 0 ? a->H : 1; p.W = a->W > 0 ? a->W : 1;
   p.mode = a->mode; p.sums = a->sums; p.count = a->count;
+  p.n_peers = a->mode == 2 ? a->n_peers : 0;
+  PT_CHECK_ARG(p.n_peers >= 0 && p.n_peers <= 8, "pt_groupnorm: at most 8 peers");
+  for (int q = 0; q < 8; ++q) p.sums_peers[q] = q < p.n_peers ? a->sums_peers[q] : nullptr;
+  for (int q = 0; q < p.n_peers; ++q) PT_CHECK_ARG(a->sums_peers[q] != nullptr, "pt_groupnorm: null peer sums");
   PT_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "pt_groupnorm: mode must be 0, 1 or 2");
-  PT_CHECK_ARG(a->mode == 0 || a->sums != nullptr, "pt_groupnorm: modes 1/2 need `sums`");
+  PT_CHECK_ARG(a->mode == 0 || a->sums != nullptr || (a->mode == 2 && a->n_peers > 0), "pt_groupnorm: modes 1/2 need `sums`");
   PT_CHECK_ARG(a->mode != 2 || a->count > 0, "pt_groupnorm: mode 2 needs `count`");
   const int rows_per_split = (a->rows_per_stat + splits - 1) / splits;
   p.res_slots = a->mode == 0 ? gn_res_slots(C, gn_ctas_per_sm(C), rows_per_split) : 0;

@@ -260,13 +260,25 @@ class ShardedNetPlan(NetPlan):
         """5-D GroupNorm of a pixel-sharded tensor: statistics span all ranks."""
         Cc = x.shape[1]
         out = self.pool.get(x.shape[0], Cc)
-        sums = torch.zeros(self.B * 64, device=self.device, dtype=torch.float64)
-        self._sums.append(sums)
         gam, bet = self.w.f32(key + ".weight"), self.w.f32(key + ".bias")
         common = dict(rows_per_stat=self.F_total * npx, eps=eps, silu=True)
+        count = float(Cc // 32) * self.F_total * HW
+        if self.p2p:
+            # every rank publishes its sums in peer-mapped memory; after one barrier the apply kernel adds the ranks'
+            # sums itself, in rank order (no NCCL all-reduce; a dedicated slot per norm, rewritten one step later)
+            slot = self.arena.take(self.B * 64 * 8)
+            buf = self.arena.chunks[slot[0]][0]
+            sums = buf[slot[1]: slot[1] + self.B * 64 * 8].view(torch.float64)
+            self._sums.append(sums)
+            self.step_ops.append(ops.GroupNorm(x, out, gam, bet, self.stats, mode=1, sums=sums, name=key + ".stats", **common))
+            self.step_ops.append(SymmBarrier(self.arena, name=key + ".barrier"))
+            self.step_ops.append(ops.GroupNorm(x, out, gam, bet, self.stats, mode=2, sums=sums, count=count,
+                                               sums_peers=self.arena.peer_ptrs(slot), name=key + ".apply", **common))
+            return out
+        sums = torch.zeros(self.B * 64, device=self.device, dtype=torch.float64)
+        self._sums.append(sums)
         self.step_ops.append(ops.GroupNorm(x, out, gam, bet, self.stats, mode=1, sums=sums, name=key + ".stats", **common))
         self.step_ops.append(AllReduceSum(sums, self.group, name=key + ".allreduce"))
-        count = float(Cc // 32) * self.F_total * HW
         self.step_ops.append(ops.GroupNorm(x, out, gam, bet, self.stats, mode=2, sums=sums, count=count, name=key + ".apply", **common))
         return out
 

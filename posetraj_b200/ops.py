@@ -324,9 +324,14 @@ class GroupNorm(_Op):
 
     def __init__(self, x0, out, gamma, beta, stats, *, rows_per_stat, eps, silu=True, x1=None,
                  halo: Optional[tuple] = None, name=None, mode: int = 0, sums: Optional[torch.Tensor] = None,
-                 count: float = 0.0):
+                 count: float = 0.0, sums_peers: Optional[Sequence[int]] = None):
         a = _lib.PtGroupNormArgs()
         a.mode = mode
+        if sums_peers is not None:
+            assert mode == 2 and 1 <= len(sums_peers) <= 8
+            a.n_peers = len(sums_peers)
+            for q, ptr in enumerate(sums_peers):
+                a.sums_peers[q] = ptr
         if mode != 0:
             assert sums is not None and sums.dtype == torch.float64 and sums.is_contiguous()
             a.sums, a.count = sums.data_ptr(), float(count)
