@@ -87,6 +87,28 @@ def test_encode_parity(vae_pair, cuda_dev, n, H, W):
     assert dist.sample(generator=torch.Generator(device=cuda_dev).manual_seed(0)).shape == ref.shape
 
 
+def test_chunked_decode_and_from_pretrained(vae_pair, cuda_dev, tmp_path):
+    """`decode_latents` decodes `decode_chunk_size` frames at a time (pipeline...controlnet.py:238-246): the temporal
+    layers only see one chunk; and a checkpoint written in the diffusers directory layout loads back."""
+    from posetraj_b200.checkpoint import save_pretrained
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    from posetraj_b200.vae import AutoencoderKLTemporalDecoder
+    o, v = vae_pair
+    save_pretrained(v.state_dict(), v.cfg, str(tmp_path / "vae"), "AutoencoderKLTemporalDecoder")
+    v2 = AutoencoderKLTemporalDecoder.from_pretrained(str(tmp_path), subfolder="vae", device=cuda_dev)
+    assert v2.cfg == v.cfg and v2.config.scaling_factor == 0.18215
+    pipe = StableVideoDiffusionPipelineControlNet(vae=v2)
+    lat = torch.randn(1, 5, 4, 8, 8, generator=torch.Generator().manual_seed(21))
+    out = pipe.decode_latents(lat.to(cuda_dev), 5, decode_chunk_size=2)          # chunks of 2, 2, 1 frames
+    assert out.shape == (1, 3, 5, 64, 64) and out.dtype == torch.float32
+    z = lat[0] / 0.18215
+    with torch.no_grad():
+        ref = torch.cat([o.decode(z[0:2], 2), o.decode(z[2:4], 2), o.decode(z[4:5], 1)])
+    err = rel_l2(out[0].permute(1, 0, 2, 3), ref)
+    _record("vae_chunked_decode", err)
+    assert err <= TOL, err
+
+
 def test_argument_errors(vae_pair, cuda_dev):
     _, v = vae_pair
     with pytest.raises(ValueError):
