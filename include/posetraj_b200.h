@@ -30,7 +30,8 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------ */
 const char* pt_last_error(void);
 int pt_version(void);
-/* 1 when kernels are launched with programmatic dependent launch (opt-in: PT_PDL=1 in the environment) */
+/* 1 when kernels are launched with programmatic dependent launch (opt-in: library built with -DPT_ENABLE_PDL and
+ * PT_PDL=1 in the environment; 0 in the default build) */
 int pt_pdl(void);
 /* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
 int64_t pt_launch_count(void);

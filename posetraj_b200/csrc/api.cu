@@ -38,6 +38,9 @@ int pt_num_sms() {
 }
 
 bool pt_pdl_enabled() {
+#ifndef PT_ENABLE_PDL
+  return false;   // the device-side griddepcontrol instructions are compiled out: the attribute must stay off
+#endif
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("PT_PDL");

@@ -25,8 +25,15 @@ PT_DEVICE uint32_t smem_u32(const void* p) {
 // Programmatic dependent launch (see launch.h).  `griddep_wait` returns once every grid this one depends on has
 // completed and its memory is visible; `griddep_launch` lets the next grid in the stream start being scheduled.
 // Both are no-ops for a grid launched without the attribute.
+// Compiled in only with -DPT_ENABLE_PDL (measured slower inside the captured step, profiles/r1h_pdl_gn.md, and the
+// instructions are not free even without the launch attribute: PREEXIT shows up in GroupNorm's stall samples).
+#ifdef PT_ENABLE_PDL
 PT_DEVICE void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 PT_DEVICE void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+PT_DEVICE void griddep_wait() {}
+PT_DEVICE void griddep_launch() {}
+#endif
 
 PT_DEVICE uint32_t lane_id() {
   uint32_t l;

@@ -15,7 +15,7 @@ int pt_num_sms();
     if (!(cond)) return pt_fail(cudaErrorInvalidValue, msg);      \
   } while (0)
 
-// Programmatic dependent launch (PDL), opt-in with PT_PDL=1: kernels are launched with
+// Programmatic dependent launch (PDL), opt-in: build with -DPT_ENABLE_PDL and run with PT_PDL=1; kernels are then launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so a grid may be scheduled while its predecessor in the
 // stream is still draining; each kernel runs its private prologue (barrier init, TMEM allocation, descriptor
 // prefetch, parameter fetch), then `griddepcontrol.wait`s before touching anything another kernel produced.

@@ -119,12 +119,12 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   for (int i = 0; i < n_res; ++i) cp_async_16(res_u32 + (uint32_t)i * res_stride, base + (size_t)(r_begin + tr + i * rpar) * ld);
   if (p.mode != 2) {
     int r = r_begin + tr + n_res * rpar;
-    for (; r + 3 * rpar < r_end; r += 4 * rpar) {  // 4 independent 16-byte loads in flight per thread
-      uint4 u[4];
+    for (; r + 7 * rpar < r_end; r += 8 * rpar) {  // 8 independent 16-byte loads in flight per thread
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = ldg_u4(base + (size_t)(r + k * rpar) * ld);
+      for (int k = 0; k < 8; ++k) u[k] = ldg_u4(base + (size_t)(r + k * rpar) * ld);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), cc = unpack_bf16x2(u[k].z), d = unpack_bf16x2(u[k].w);
         const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
 #pragma unroll
@@ -180,14 +180,16 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    double a = 0.0, b = 0.0;
+    // this CTA's channels of a group in fp32 (a few thousand elements), fp64 only across CTAs: a chain of cg fp64 adds
+    // on 32 threads was ~1 us of pure latency on the 1/64-rate fp64 pipe
+    float a = 0.f, b = 0.f;
     for (int i = 0; i < cg; ++i) {
-      a += (double)c_sum[threadIdx.x * cg + i];
-      b += (double)c_sq[threadIdx.x * cg + i];
+      a += c_sum[threadIdx.x * cg + i];
+      b += c_sq[threadIdx.x * cg + i];
     }
     double* dst = p.partials + (((size_t)stat * p.splits + split) * 32 + threadIdx.x) * 2;
-    dst[0] = a;
-    dst[1] = b;
+    dst[0] = (double)a;
+    dst[1] = (double)b;
     __threadfence();
   }
   __syncthreads();

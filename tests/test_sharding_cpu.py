@@ -168,3 +168,31 @@ def test_gloo_world2_ragged_all_to_all_rows():
     assert res[0][0] == [[0.0, 1.0], [2.0, 3.0], [100.0, 101.0]]
     assert res[1][0][:3] == [[4.0, 5.0], [6.0, 7.0], [8.0, 9.0]] and res[1][0][3] == [102.0, 103.0]
     assert res[0][1] == [3.0] * 4 and res[1][1] == [3.0] * 4
+
+
+def test_symm_arena_suballocation_is_rank_independent(monkeypatch):
+    """The peer-mapped exchange buffers are sub-allocated from symmetric-memory chunks; every rank must arrive at the
+    same (chunk, offset) for the same request sequence, or a scattered row would land in the wrong exchange."""
+    from posetraj_b200.frame_sharding import SymmArena
+
+    def fake_chunk(self, nbytes):
+        size = max(self.CHUNK, (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20))
+        self.chunks.append([torch.zeros(0).new_empty(size, dtype=torch.uint8), None, 0])
+        self.bytes += size
+
+    monkeypatch.setattr(SymmArena, "_new_chunk", fake_chunk)
+    monkeypatch.setattr(SymmArena, "CHUNK", 1 << 20)
+    reqs = [300_000, 512, 700_001, 1 << 21, 64, 999_999, 5]
+    arenas = [SymmArena.__new__(SymmArena) for _ in range(3)]
+    for a in arenas:
+        a.device, a.group, a.chunks, a.bytes = "cpu", None, [], 0
+    slots = [[a.take(n) for n in reqs] for a in arenas]
+    assert slots[0] == slots[1] == slots[2]
+    seen = {}
+    for (c, off), n in zip(slots[0], reqs):
+        assert off % 256 == 0 and off + n <= arenas[0].chunks[c][0].numel()
+        for (c2, off2, n2) in seen.get(c, []):
+            assert off >= off2 + n2 or off2 >= off + n      # no overlap inside a chunk
+        seen.setdefault(c, []).append((c, off, n))
+    v = arenas[0].view(slots[0][0], 100, 64)
+    assert v.shape == (100, 64) and v.dtype == torch.bfloat16 and getattr(v, "_pt_no_pool", False)
