@@ -67,6 +67,7 @@ struct GemmParams {
   int scatter_mode, sc_world, sc_J, sc_S, sc_kept_off, sc_kept_total;
   int sc_start[8], sc_count[8];
   bf16* sc_peer[8];
+  int epi_depth;  // chunks of operand lookahead in the lean epilogue (1 or 2)
 };
 
 struct alignas(64) TmapParam {
@@ -159,39 +160,41 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
   bf16* out2 = reinterpret_cast<bf16*>(p.out2);
   const bool has_res2 = kRes && p.res2 != nullptr;
   const bool has_res1 = kRes && p.res1 != nullptr;
-  // Operands are fetched one chunk AHEAD (double-buffered in registers): the global-load latency of chunk c+2
-  // overlaps the TMEM read, transpose and math of chunk c.  (res2 — rare — is fetched in the chunk that uses it.)
-  uint4 r1n[4], axn[4];
-  float4 b0n = make_float4(0.f, 0.f, 0.f, 0.f), b1n = b0n;
-  auto fetch = [&](int c, uint4 (&r1x)[4], uint4 (&axx)[4], float4& b0x, float4& b1x) {
+  // Operands (bias, residual, aux) are fetched one chunk AHEAD of the chunk that uses them, in rotating register
+  // sets: the global-load latency of chunk c+2 overlaps the TMEM read, transpose and math of chunk c.  A second chunk
+  // of lookahead (PT_EPI_DEPTH=2) measured no gain (profiles/r1e_experiments.md).  (res2 — rare — is fetched in the
+  // chunk that uses it.)
+  struct Pre {
+    uint4 r1[4], ax[4];
+    float4 b0, b1;
+  };
+  auto fetch = [&](int c, Pre& P) {
     const int ncol = n0 + c * 32 + seg * 8;
+    P.b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    P.b1 = P.b0;
     if (c < chunks && ncol < p.n_out) {
       if (p.bias != nullptr) {
-        b0x = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
-        b1x = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + 1);
+        P.b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
+        P.b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + 1);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if constexpr (kRes) r1x[i] = has_res1 ? ldg_nc_u4(p.res1 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
-        if constexpr (kOut2) axx[i] = ldg_nc_u4(p.aux + R.out_off[i] + ncol);
+        if constexpr (kRes) P.r1[i] = has_res1 ? ldg_nc_u4(p.res1 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
+        if constexpr (kOut2) P.ax[i] = ldg_nc_u4(p.aux + R.out_off[i] + ncol);
       }
     }
   };
-  fetch(hsel, r1n, axn, b0n, b1n);
-  for (int c = hsel; c < chunks; c += 2) {
+  // one 32-column chunk: TMEM -> registers -> swizzled smem transpose -> 4 coalesced row segments per lane
+  auto process = [&](int c, const Pre& P) {
     const int ncol = n0 + c * 32 + seg * 8;
     const bool act = ncol < p.n_out;  // n_out % 8 == 0 on this path: a segment is full or empty
     uint32_t v[32];
     tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
-    uint4 r1[4], r2[4], ax[4];
-    const float4 b0 = b0n, b1 = b1n;
+    uint4 r2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if constexpr (kRes) r1[i] = r1n[i];
-      if constexpr (kOut2) ax[i] = axn[i];
       if constexpr (kRes) r2[i] = (act && has_res2) ? ldg_nc_u4(p.res2 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
     }
-    fetch(c + 2, r1n, axn, b0n, b1n);
     tmem_wait_ld();
     if (c + 2 >= chunks) {
       tc_fence_before();
@@ -206,6 +209,7 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
                    "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
     }
     __syncwarp();
+    const float4 b0 = P.b0, b1 = P.b1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int rr = i * 8 + sub_row;
@@ -227,7 +231,7 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
       for (int j = 0; j < 8; ++j) f[j] *= p.acc_scale;
       if constexpr (kRes) {
         float r[8];
-        unpack8(r1[i], r);
+        unpack8(P.r1[i], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaf(p.res1_scale, r[j], f[j]);
         if (has_res2) {
@@ -239,11 +243,42 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
       stg_u4(R.out_ptr[i] + ncol, pack8(f));
       if constexpr (kOut2) {
         float r[8];
-        unpack8(ax[i], r);
+        unpack8(P.ax[i], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaf(p.aux_scale, r[j], f[j]);
         stg_u4(out2 + R.out_off[i] + ncol, pack8(f));
       }
+    }
+  };
+  Pre P0, P1;
+  fetch(hsel, P0);
+  // optional second chunk of lookahead (three register sets; not for the second-output variants, which already
+  // carry 16 more registers per set)
+  if constexpr ((kRes || kOut2) && !(kRes && kOut2)) {
+    if (p.epi_depth >= 2) {
+      Pre P2;
+      fetch(hsel + 2, P1);
+      for (int c = hsel; c < chunks; c += 6) {
+        fetch(c + 4, P2);
+        process(c, P0);
+        if (c + 2 < chunks) {
+          fetch(c + 6, P0);
+          process(c + 2, P1);
+        }
+        if (c + 4 < chunks) {
+          fetch(c + 8, P1);
+          process(c + 4, P2);
+        }
+      }
+      return;
+    }
+  }
+  for (int c = hsel; c < chunks; c += 4) {
+    fetch(c + 2, P1);
+    process(c, P0);
+    if (c + 2 < chunks) {
+      fetch(c + 4, P0);
+      process(c + 2, P1);
     }
   }
 }
@@ -786,6 +821,14 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.oH = a->oH;
   p.out_halo = a->out_halo;
   p.act_silu = a->act_silu;
+  {
+    static int env_depth = -2;   // experiment knob: PT_EPI_DEPTH=2 = two chunks of operand lookahead (no gain: r1e)
+    if (env_depth == -2) {
+      const char* e = getenv("PT_EPI_DEPTH");
+      env_depth = e ? atoi(e) : -1;
+    }
+    p.epi_depth = env_depth > 0 ? env_depth : 1;
+  }
   p.scatter_mode = a->scatter_mode;
   p.sc_world = a->sc_world; p.sc_J = a->sc_J > 0 ? a->sc_J : 1; p.sc_S = a->sc_S > 0 ? a->sc_S : 1;
   p.sc_kept_off = a->sc_kept_off; p.sc_kept_total = a->sc_kept_total;
