@@ -4,3 +4,5 @@ from .config import SVDConfig  # noqa: F401
 from .models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel  # noqa: F401
 from .pipeline import StableVideoDiffusionPipelineControlNet  # noqa: F401
 from .scheduler import EulerDiscreteScheduler  # noqa: F401
+from .vae import AutoencoderKLTemporalDecoder  # noqa: F401
+from .clip import CLIPVisionModelWithProjection, resize_with_antialiasing  # noqa: F401
