@@ -196,3 +196,50 @@ def test_symm_arena_suballocation_is_rank_independent(monkeypatch):
         seen.setdefault(c, []).append((c, off, n))
     v = arenas[0].view(slots[0][0], 100, 64)
     assert v.shape == (100, 64) and v.dtype == torch.bfloat16 and getattr(v, "_pt_no_pool", False)
+
+
+@pytest.mark.parametrize("B,Ft,HW,world", [(2, 5, 45, 3), (2, 25, 144, 8), (1, 14, 45, 2), (2, 3, 7, 3)])
+def test_scatter_epilogue_row_formulas(B, Ft, HW, world):
+    """The fused exchange (PtGemmArgs.scatter_mode 1 / 2): the destination row each rank's GEMM epilogue computes must
+    be a bijection onto the owner's layout and carry the right (batch, frame, pixel) — simulated on the host with the
+    same integer formulas as csrc/gemm.cu, for ragged frame and pixel shards."""
+    from posetraj_b200.frame_sharding import pixel_shards
+    from posetraj_b200.sharding import frame_shards
+    fsh, pix = frame_shards(Ft, world), pixel_shards(HW, world)
+
+    def owner(u, shards):
+        q = 0
+        while q + 1 < len(shards) and u >= shards[q][0] + shards[q][1]:
+            q += 1
+        return q
+
+    # mode 1: frame layout (b, j in F_r, s) -> pixel layout of the owner of s
+    dest = [dict() for _ in range(world)]
+    for r, (f0, nf) in enumerate(fsh):
+        J, S, kept_off, kept_total = nf, HW, f0, Ft
+        for row in range(B * J * S):
+            b, rem = divmod(row, J * S)
+            j, s = divmod(rem, S)
+            q = owner(s, pix)
+            drow = (b * kept_total + kept_off + j) * pix[q][1] + (s - pix[q][0])
+            assert drow not in dest[q]
+            dest[q][drow] = (b, f0 + j, s)
+    for q, (p0, npx) in enumerate(pix):
+        assert sorted(dest[q]) == list(range(B * Ft * npx))
+        for drow, (b, f, s) in dest[q].items():
+            assert drow == (b * Ft + f) * npx + (s - p0)
+    # mode 2: pixel layout (b, f, p in P_r) -> frame layout of the owner of f
+    dest = [dict() for _ in range(world)]
+    for r, (p0, npx) in enumerate(pix):
+        J, S, kept_off, kept_total = Ft, npx, p0, HW
+        for row in range(B * J * S):
+            b, rem = divmod(row, J * S)
+            j, s = divmod(rem, S)
+            q = owner(j, fsh)
+            drow = (b * fsh[q][1] + (j - fsh[q][0])) * kept_total + kept_off + s
+            assert drow not in dest[q]
+            dest[q][drow] = (b, j, p0 + s)
+    for q, (f0, nf) in enumerate(fsh):
+        assert sorted(dest[q]) == list(range(B * nf * HW))
+        for drow, (b, f, s) in dest[q].items():
+            assert drow == (b * nf + (f - f0)) * HW + s
