@@ -136,8 +136,13 @@ class SymmArena:
     def _new_chunk(self, nbytes: int) -> None:
         import torch.distributed._symmetric_memory as sm
         size = max(self.CHUNK, (nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20))
-        buf = sm.empty(size, dtype=torch.uint8, device=self.device)
-        hdl = sm.rendezvous(buf, self.group)
+        try:
+            buf = sm.empty(size, dtype=torch.uint8, device=self.device)
+            hdl = sm.rendezvous(buf, self.group)
+        except Exception as e:  # noqa: BLE001 - say what to do instead of a bare driver error
+            raise RuntimeError("posetraj_b200: peer-mapped exchange buffers (torch symmetric memory) are unavailable for "
+                               "this process group — all ranks must sit in one NVLink/NVSwitch domain with peer access; "
+                               "set PT_P2P=0 to use the NCCL all-to-all exchange instead") from e
         buf.zero_()
         self.chunks.append([buf, hdl, 0])
         self.bytes += size
@@ -189,6 +194,9 @@ class ShardedNetPlan(NetPlan):
         self.arena: Optional[SymmArena] = kw.pop("arena", None)
         self.p2p = (world > 1 and os.environ.get("PT_P2P", "1") != "0" and dist.is_initialized()
                     and dist.get_backend(group) == "nccl")
+        if self.p2p and world > 8:
+            raise ValueError("posetraj_b200: the fused peer-memory exchange addresses at most 8 ranks (one NVSwitch "
+                             "domain); set PT_P2P=0 for the NCCL exchange on larger groups")
         if self.p2p and self.arena is None:
             self.arena = SymmArena(device, group)
         super().__init__(kind, cfg, weights, batch=batch, frames=self.nf, height=height, width=width, device=device, **kw)
