@@ -291,6 +291,23 @@ class StableVideoDiffusionPipelineControlNet:
             latents = latents.to(device)
         return latents * self.scheduler.init_noise_sigma
 
+    def prepare_controlnet_condition(self, controlnet_condition, height: int, width: int) -> torch.Tensor:
+        """pipeline...controlnet.py:500-503: the trajectory maps — a list of PIL images / numpy arrays as the reference
+        scripts pass them (`control_images[:14]`), or an already pre-processed [F, 3, H, W] / [1|2, F, 3, H, W] tensor in
+        [-1, 1] (e.g. from posetraj_b200.trajectory.rasterize_tracks) — become [2, F, 3, H, W] for the CFG pair."""
+        cond = controlnet_condition
+        if cond is None:
+            raise ValueError("controlnet_condition is required")
+        if not torch.is_tensor(cond):
+            cond = self.image_processor.preprocess(cond, height=height, width=width)
+        if cond.dim() == 4:
+            cond = cond.unsqueeze(0)
+        if cond.dim() != 5 or cond.shape[2] != 3:
+            raise ValueError(f"controlnet_condition must be [F, 3, H, W] or [B, F, 3, H, W], got {tuple(cond.shape)}")
+        if cond.shape[0] == 1:
+            cond = torch.cat([cond] * 2)
+        return cond
+
     def enable_frame_sharding(self, rank: int, world: int, group=None) -> None:
         """Shard ONE video over `world` GPUs by frames (spatial layers) / pixels (temporal layers) with an all-to-all
         around every temporal sub-block (posetraj_b200/frame_sharding.py)."""
@@ -364,14 +381,7 @@ class StableVideoDiffusionPipelineControlNet:
         latents = self.prepare_latents(1, num_frames, self.unet.config.in_channels, height, width, F32, device,
                                        generator, latents)
         # controlnet condition: [F, 3, H, W] in [-1, 1] -> duplicated for the CFG pair (:500-503)
-        cond = controlnet_condition
-        if cond is None:
-            raise ValueError("controlnet_condition is required")
-        cond = cond.to(device=device, dtype=F32)
-        if cond.dim() == 4:
-            cond = cond.unsqueeze(0)
-        if cond.shape[0] == 1:
-            cond = torch.cat([cond] * 2)
+        cond = self.prepare_controlnet_condition(controlnet_condition, height, width).to(device=device, dtype=F32)
         cam = None
         if camera_cond is not None:
             cam = torch.as_tensor(camera_cond).to(device=device, dtype=F32)

@@ -79,3 +79,24 @@ def test_vae_refuses_cpu():
     from posetraj_b200.vae import AutoencoderKLTemporalDecoder, VaeConfig
     with pytest.raises(RuntimeError):
         AutoencoderKLTemporalDecoder(VaeConfig(), {}, device="cpu")
+
+
+def test_controlnet_condition_from_pil_list():
+    """The reference scripts hand the pipeline a list of PIL trajectory maps (run_inference_vipseg_json_repro.py:451);
+    `preprocess` (pipeline...controlnet.py:500-503) turns them into [2, F, 3, H, W] in [-1, 1]."""
+    import PIL.Image
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    pipe = StableVideoDiffusionPipelineControlNet()
+    rng = np.random.default_rng(1)
+    imgs = [PIL.Image.fromarray(rng.integers(0, 256, size=(32, 48, 3), dtype=np.uint8)) for _ in range(3)]
+    cond = pipe.prepare_controlnet_condition(imgs, 32, 48)
+    assert cond.shape == (2, 3, 3, 32, 48) and cond.min() >= -1 and cond.max() <= 1
+    assert torch.equal(cond[0], cond[1])
+    want = torch.from_numpy(np.asarray(imgs[1], dtype=np.float32) / 255.0).permute(2, 0, 1) * 2 - 1
+    assert torch.allclose(cond[0, 1], want)
+    t = torch.rand(3, 3, 32, 48) * 2 - 1
+    assert torch.equal(pipe.prepare_controlnet_condition(t, 32, 48)[1], t)
+    with pytest.raises(ValueError):
+        pipe.prepare_controlnet_condition(None, 32, 48)
+    with pytest.raises(ValueError):
+        pipe.prepare_controlnet_condition(torch.zeros(3, 4, 32, 48), 32, 48)
