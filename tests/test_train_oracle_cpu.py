@@ -175,3 +175,32 @@ def test_data_parallel_gradient_average_world2():
         assert torch.allclose(res[r][0], mean[::step], rtol=1e-3, atol=1e-6)
         assert res[r][1] == pytest.approx(float(mean.norm()), rel=1e-3)
     assert torch.equal(res[0][0], res[1][0])
+
+
+def test_oracle_reproduces_committed_training_golden():
+    """tests/golden/train_golden.safetensors (losses, prediction, ControlNet gradient norms and a few full gradients of
+    one training step, minted by tests/golden/gen_train_golden.py) is what the backward kernels will be checked against;
+    here: the oracle still produces it."""
+    import importlib.util
+    from safetensors.torch import load_file
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location("gen_train_golden", os.path.join(here, "golden", "gen_train_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    threads = torch.get_num_threads()
+    try:
+        res, names = mod.run()
+    finally:
+        torch.set_num_threads(threads)
+    gold = load_file(os.path.join(here, "golden", "train_golden.safetensors"))
+    assert set(gold) == set(res) and len(names) == gold["grad_norms"].numel()
+    for k in ("loss", "loss_main", "loss_spatial"):
+        assert torch.allclose(res[k], gold[k], rtol=1e-4), k
+    assert torch.allclose(res["model_pred"], gold["model_pred"], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(res["grad_norms"], gold["grad_norms"], rtol=2e-3, atol=1e-7)
+    for k in gold:
+        if k.startswith("grad."):
+            rel = (res[k] - gold[k]).norm() / gold[k].norm().clamp_min(1e-12)
+            assert rel < 2e-3, (k, float(rel))
+    # every ControlNet parameter gets a gradient, and the mix factors (scalars) are among them
+    assert float(gold["grad_norms"].min()) >= 0 and float((gold["grad_norms"] > 0).float().mean()) > 0.95
