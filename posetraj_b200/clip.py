@@ -180,6 +180,37 @@ class ClipPlan:
         self.ops.append(ops.Gemm(pooled, w.linear("visual_projection.weight"), self.embeds, name="visual_projection"))
 
 
+def load_clip_checkpoint(path: str, subfolder: Optional[str] = None, variant: Optional[str] = None, **overrides):
+    """(CLIPVisionConfig, state dict) from a Hugging Face `CLIPVisionModelWithProjection` directory (`config.json` +
+    `model[.variant].safetensors` or `pytorch_model[.variant].bin`), the layout of SVD's `image_encoder/` subfolder the
+    reference loads (scripts/run_inference_vipseg_json_repro.py:335-339).  Host only; no transformers import."""
+    import json
+    import os
+    from dataclasses import fields
+    from .checkpoint import resolve_dir
+    d = resolve_dir(path, subfolder)
+    known = {f.name for f in fields(CLIPVisionConfig)}
+    ckw: Dict = {}
+    cp = os.path.join(d, "config.json")
+    if os.path.exists(cp):
+        with open(cp) as f:
+            for k, v in json.load(f).items():
+                if k in known and v is not None:
+                    ckw[k] = v
+    ckw.update({k: v for k, v in overrides.items() if k in known})
+    v = f".{variant}" if variant else ""
+    for name in (f"model{v}.safetensors", f"pytorch_model{v}.bin"):
+        fp = os.path.join(d, name)
+        if os.path.exists(fp):
+            if fp.endswith(".safetensors"):
+                from safetensors.torch import load_file
+                sd = load_file(fp, device="cpu")
+            else:
+                sd = torch.load(fp, map_location="cpu", weights_only=True)
+            return CLIPVisionConfig(**ckw), sd
+    raise FileNotFoundError(f"no model{v}.safetensors / pytorch_model{v}.bin in {d}")
+
+
 @dataclass
 class CLIPVisionModelOutput:
     image_embeds: torch.Tensor
@@ -243,31 +274,8 @@ class CLIPVisionModelWithProjection(torch.nn.Module):
 
     @classmethod
     def from_pretrained(cls, path: str, subfolder: Optional[str] = None, variant: Optional[str] = None, device=None, **kw):
-        import json
-        import os
-        from dataclasses import fields
-        from .checkpoint import resolve_dir
-        d = resolve_dir(path, subfolder)
-        known = {f.name for f in fields(CLIPVisionConfig)}
-        ckw: Dict = {}
-        cp = os.path.join(d, "config.json")
-        if os.path.exists(cp):
-            with open(cp) as f:
-                for k, v in json.load(f).items():
-                    if k in known and v is not None:
-                        ckw[k] = v
-        ckw.update({k: v for k, v in kw.items() if k in known})
-        v = f".{variant}" if variant else ""
-        for name in (f"model{v}.safetensors", f"pytorch_model{v}.bin"):
-            fp = os.path.join(d, name)
-            if os.path.exists(fp):
-                if fp.endswith(".safetensors"):
-                    from safetensors.torch import load_file
-                    sd = load_file(fp, device="cpu")
-                else:
-                    sd = torch.load(fp, map_location="cpu", weights_only=True)
-                return cls(CLIPVisionConfig(**ckw), sd, device)
-        raise FileNotFoundError(f"no model{v}.safetensors / pytorch_model{v}.bin in {d}")
+        cfg, sd = load_clip_checkpoint(path, subfolder, variant, **kw)
+        return cls(cfg, sd, device)
 
     def _plan_for(self) -> ClipPlan:
         if self._plan is None:

@@ -62,3 +62,29 @@ def test_clip_refuses_cpu():
         CLIPVisionModelWithProjection(CLIPVisionConfig(), {}, device="cpu")
     with pytest.raises(RuntimeError):
         resize_with_antialiasing(torch.zeros(1, 3, 32, 32))
+
+
+def test_load_hf_checkpoint_directory(tmp_path):
+    """`from_pretrained` reads the Hugging Face layout of SVD's image_encoder/ (config.json + model.safetensors, or
+    pytorch_model.bin), ignoring keys the mirror does not use (e.g. `position_ids` buffers, `_name_or_path`)."""
+    import json
+    from safetensors.torch import save_file
+    from oracle.clip import CLIPVisionModelWithProjection as Oracle
+    from posetraj_b200.clip import clip_param_shapes, load_clip_checkpoint
+    kw = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, image_size=56,
+              patch_size=14, projection_dim=64, hidden_act="quick_gelu")
+    sd = {k: v.detach().clone() for k, v in Oracle(**kw).state_dict().items()}
+    sd["vision_model.embeddings.position_ids"] = torch.arange(17)[None]
+    d = tmp_path / "image_encoder"
+    d.mkdir()
+    json.dump(dict(kw, _name_or_path="x", architectures=["CLIPVisionModelWithProjection"], dropout=0.0), open(d / "config.json", "w"))
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(d / "model.fp16.safetensors"))
+    cfg, loaded = load_clip_checkpoint(str(tmp_path), subfolder="image_encoder", variant="fp16")
+    assert cfg.hidden_act == "quick_gelu" and cfg.hidden_size == 128 and cfg.projection_dim == 64
+    shapes = clip_param_shapes(cfg)
+    assert set(shapes) <= set(loaded) and all(tuple(loaded[k].shape) == tuple(s) for k, s in shapes.items())
+    with pytest.raises(FileNotFoundError):
+        load_clip_checkpoint(str(tmp_path), subfolder="image_encoder")        # no un-suffixed weight file
+    torch.save(sd, str(d / "pytorch_model.bin"))
+    cfg2, loaded2 = load_clip_checkpoint(str(tmp_path), subfolder="image_encoder", num_hidden_layers=2)
+    assert torch.equal(loaded2["visual_projection.weight"], sd["visual_projection.weight"])
