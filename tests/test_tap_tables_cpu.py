@@ -33,16 +33,17 @@ def emulate_gemm(rows, w_kmajor, taps, n, H, W, ostride):
 
 
 def kmajor(weight):
-    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin], K index = (ky*3 + kx)*Cin + ci (WeightStore.conv3)."""
-    co, ci = weight.shape[:2]
-    return weight.permute(0, 2, 3, 1).reshape(co, 9 * ci).numpy()
+    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin], K index = (ky*3 + kx)*Cin + ci — through the product's own WeightStore.conv3
+    (bf16 storage: the weights of these tests are bf16-representable)."""
+    from posetraj_b200.engine import WeightStore
+    return WeightStore({"w": weight}, "cpu").conv3("w").float().numpy()
 
 
 @pytest.mark.parametrize("stride", [1, 2])
 def test_padding1_taps_match_conv2d(stride):
     from posetraj_b200.ops import conv3x3_taps
     g = torch.Generator().manual_seed(0)
-    x, w = torch.randn(2, 5, 6, 8, generator=g), torch.randn(7, 5, 3, 3, generator=g)
+    x, w = torch.randn(2, 5, 6, 8, generator=g), torch.randn(7, 5, 3, 3, generator=g).bfloat16().float()
     got = emulate_gemm(haloed_rows(x), kmajor(w), conv3x3_taps(8), 2, 6, 8, stride)
     want = F.conv2d(x, w, stride=stride, padding=1)
     assert got.shape == want.shape and torch.allclose(got, want, atol=1e-4)
@@ -50,7 +51,7 @@ def test_padding1_taps_match_conv2d(stride):
 
 def test_vae_downsample_taps_match_pad_right_bottom_conv():
     g = torch.Generator().manual_seed(1)
-    x, w = torch.randn(2, 4, 6, 8, generator=g), torch.randn(3, 4, 3, 3, generator=g)
+    x, w = torch.randn(2, 4, 6, 8, generator=g), torch.randn(3, 4, 3, 3, generator=g).bfloat16().float()
     taps = [ky * (8 + 1) + kx for ky in range(3) for kx in range(3)]      # posetraj_b200/vae.py VaeEncodePlan
     got = emulate_gemm(haloed_rows(x), kmajor(w), taps, 2, 6, 8, 2)
     want = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, stride=2, padding=0)
@@ -62,9 +63,10 @@ def test_temporal_taps_match_conv3d():
     BATCH (the A operand is a rank-3 tensor map, rows of another batch are out of bounds)."""
     g = torch.Generator().manual_seed(2)
     B, Fr, C, HW, N = 2, 4, 3, 5, 6
-    x, w = torch.randn(B, C, Fr, HW, 1, generator=g), torch.randn(N, C, 3, 1, 1, generator=g)
+    x, w = torch.randn(B, C, Fr, HW, 1, generator=g), torch.randn(N, C, 3, 1, 1, generator=g).bfloat16().float()
     rows = x[..., 0].permute(0, 2, 3, 1).reshape(B, Fr * HW, C).numpy()
-    wk = w.reshape(N, C, 3).permute(0, 2, 1).reshape(N, 3 * C).numpy()           # WeightStore.tconv: K = kt*C + ci
+    from posetraj_b200.engine import WeightStore
+    wk = WeightStore({"w": w}, "cpu").tconv("w").float().numpy()                 # K = kt*C + ci
     out = np.zeros((B, Fr * HW, N))
     for b in range(B):
         for t, shift in enumerate((-HW, 0, HW)):
