@@ -155,6 +155,10 @@ typedef struct PtGemmArgs {
   int32_t sc_kept_off, sc_kept_total;
   int32_t sc_start[8], sc_count[8];
   void* sc_peer[8];
+  /* optional DEVICE scalar multiplied into acc_scale when the kernel runs (NULL: none).  The ControlNet zero-convs
+   * read `conditioning_scale` (models/controlnet_sdv.py:641-643) through it, so that a captured CUDA graph of the
+   * denoise step picks up the value of the current call at replay instead of the one baked in at capture. */
+  const float* acc_scale_ptr;
 } PtGemmArgs;
 int pt_gemm(const PtGemmArgs* a, void* stream);
 

@@ -1,7 +1,10 @@
 """ORACLE (test infrastructure, never the product path) — CPU restatement of PoseTraj's model wiring.
 
-PARITY UNPINNED for the numerics of the blocks (see oracle/svd_blocks.py); the WIRING restated here follows
-the reference files line by line:
+PARITY UNPINNED for the numerics of the leaf blocks (see oracle/svd_blocks.py).  The WIRING restated here is PINNED:
+tests/golden/wiring_golden.safetensors holds outputs of the reference's own model files executed unmodified with
+`diffusers` shimmed (tests/golden/gen_wiring_golden.py), and tests/test_wiring_golden_cpu.py asserts this module
+reproduces them (plain / camera / bbox variants, 13 residuals + noise prediction, <= 1e-5).  It follows the reference
+files line by line:
   /root/reference/models/controlnet_sdv.py:61-116      ControlNetConditioningEmbeddingSVD
   /root/reference/models/controlnet_sdv.py:299-391     ControlNetSDVModel.__init__
   /root/reference/models/controlnet_sdv.py:516-650     ControlNetSDVModel.forward

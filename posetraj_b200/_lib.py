@@ -76,6 +76,7 @@ class PtGemmArgs(C.Structure):
         ("scatter_mode", C.c_int32), ("sc_world", C.c_int32), ("sc_J", C.c_int32), ("sc_S", C.c_int32),
         ("sc_kept_off", C.c_int32), ("sc_kept_total", C.c_int32),
         ("sc_start", C.c_int32 * 8), ("sc_count", C.c_int32 * 8), ("sc_peer", C.c_void_p * 8),
+        ("acc_scale_ptr", C.c_void_p),
     ]
 
 

@@ -27,14 +27,21 @@ int pt_launched(const char* what) {
   return 0;
 }
 
+int pt_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < PT_MAX_DEVICES ? dev : PT_MAX_DEVICES - 1;
+}
+
 int pt_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  static int sms[PT_MAX_DEVICES] = {0};
+  const int slot = pt_device_slot();
+  if (sms[slot] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot) != cudaSuccess || n <= 0) n = 148;
+    sms[slot] = n;
   }
-  return sms;
+  return sms[slot];
 }
 
 bool pt_pdl_enabled() {

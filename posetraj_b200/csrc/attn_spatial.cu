@@ -318,11 +318,12 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
 template <int NQ>
 static int launch_attn(const PtAttnSpatialArgs* a, const AttnParams& p, cudaStream_t st) {
   const size_t smem_bytes = 1024 + (size_t)kTileBytes * (NQ + 2 * NQ + 2 * kKvStages) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[PT_MAX_DEVICES] = {false};  // cudaFuncSetAttribute is per device
+  const int dev_slot = pt_device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(attn_spatial_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return pt_fail(e, "pt_attention_spatial: cudaFuncSetAttribute");
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   AttnTmap tm;
   memcpy(&tm, a->tmap_qkv, sizeof(tm));

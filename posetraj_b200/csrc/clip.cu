@@ -218,11 +218,12 @@ extern "C" int pt_attention_small(const PtAttnSmallArgs* a, void* stream) {
   p.scale = 1.0f / sqrtf((float)a->head_dim);
   const size_t smem = (size_t)2 * p.hd * p.Sp * 2 + (size_t)8 * p.Sp * 4 + (size_t)8 * p.hd * 4;
   PT_CHECK_ARG(smem <= 200 * 1024, "pt_attention_small: sequence too long for the shared-memory K/V (use pt_attention_spatial)");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[PT_MAX_DEVICES] = {false};  // cudaFuncSetAttribute is per device
+  const int dev_slot = pt_device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return pt_fail(e, "pt_attention_small: cudaFuncSetAttribute");
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   dim3 grid(a->heads, (a->S + kSmallQPerCta - 1) / kSmallQPerCta);
   pt_launch(attn_small_kernel, grid, dim3(256), smem, stream, 1, p);

@@ -34,7 +34,11 @@ constexpr int kBlockK = 64;
 // variants for bf16 outputs with n_out % 8 == 0 and no SiLU (bit 0 per-row vector, bit 1 residual operands,
 // bit 2 second output) — the compiler does not if-convert what is not instantiated.
 constexpr int kEpiGeneric = 0, kEpiGeglu = 1, kEpiFast = 2;
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == kEpiGeglu ? 12 : 8; }
+// kEpi 10..17: the lean variants again, with SIXTEEN epilogue warps and no operand lookahead.  With <= 10 k-steps per
+// tile the tile time is the epilogue's, and 8 warps (2 per scheduler) issue only ~15 % of the time there
+// (profiles/r1j_gemm_full.md): four warps per scheduler hide the dependency latency instead of registers.
+constexpr int kEpiWide = kEpiFast + 8;
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == kEpiGeglu ? 12 : (epi >= kEpiWide ? 16 : 8); }
 __host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 32 * epi_warps(epi); }
 __host__ __device__ constexpr int stage_warp_bytes(int epi) { return epi == kEpiGeglu ? 32 * 32 * 2 : 32 * 32 * 4; }
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
@@ -53,6 +57,7 @@ struct GemmParams {
   const float* rowvec;
   int rowvec_ld, rowvec_mode, rv_a, rv_b, rv_c, rv_mod, rv_off;
   float acc_scale;
+  const float* acc_scale_ptr;  // optional device scalar multiplied into acc_scale (graph-replay safe)
   const bf16* res1;
   const bf16* res2;
   float res1_scale, res2_scale;
@@ -123,11 +128,11 @@ PT_DEVICE float apply_act(int act, float v) {
 
 // slow path of the store side: fewer than 8 valid columns in this lane's segment (only conv_out: n_out = 4)
 __device__ __noinline__ void epilogue_tail(const GemmParams& p, const float* acc, const float* sb_seg, int ncol,
-                                           int nvalid, long long orow, int grp) {
+                                           int nvalid, long long orow, int grp, float acc_scale) {
   for (int j = 0; j < nvalid; ++j) {
     float v = acc[j] + sb_seg[j];
     if (p.rowvec_mode != 0) v += __ldg(p.rowvec + (size_t)grp * p.rowvec_ld + ncol + j);
-    v *= p.acc_scale;
+    v *= acc_scale;
     if (p.act_silu) v = apply_act(p.act_silu, v);
     if (p.res1 != nullptr) v = fmaf(p.res1_scale, __bfloat162float(p.res1[(size_t)orow * p.res_ld + ncol + j]), v);
     if (p.res2 != nullptr) v = fmaf(p.res2_scale, __bfloat162float(p.res2[(size_t)orow * p.res_ld + ncol + j]), v);
@@ -152,9 +157,9 @@ struct EpiRows {
 
 // Lean epilogue of one accumulator tile for bf16 outputs (see kEpiFast).  val = acc_scale*(acc + bias + rowvec) +
 // s1*res1 + s2*res2 ; out = val ; out2 = val + aux_scale*aux.
-template <bool kRowvec, bool kRes, bool kOut2, typename ArriveFn>
+template <bool kRowvec, bool kRes, bool kOut2, int kStride, typename ArriveFn>
 PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_acc, uint32_t stage_u32, int n0,
-                             int chunks, int hsel, int lane, const ArriveFn& arrive_drained) {
+                             int chunks, int hsel, int lane, float acc_scale, const ArriveFn& arrive_drained) {
   const int sub_row = lane >> 2;
   const int seg = lane & 3;
   bf16* out2 = reinterpret_cast<bf16*>(p.out2);
@@ -177,10 +182,12 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
         P.b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
         P.b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol) + 1);
       }
+      if constexpr (kStride != 4) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if constexpr (kRes) P.r1[i] = has_res1 ? ldg_nc_u4(p.res1 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
-        if constexpr (kOut2) P.ax[i] = ldg_nc_u4(p.aux + R.out_off[i] + ncol);
+        for (int i = 0; i < 4; ++i) {
+          if constexpr (kRes) P.r1[i] = has_res1 ? ldg_nc_u4(p.res1 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
+          if constexpr (kOut2) P.ax[i] = ldg_nc_u4(p.aux + R.out_off[i] + ncol);
+        }
       }
     }
   };
@@ -191,12 +198,14 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
     uint32_t v[32];
     tmem_ld_32x32(t_acc + (uint32_t)c * 32u, v);
     uint4 r2[4];
+    if constexpr (kStride != 4) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if constexpr (kRes) r2[i] = (act && has_res2) ? ldg_nc_u4(p.res2 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (kRes) r2[i] = (act && has_res2) ? ldg_nc_u4(p.res2 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
+      }
     }
     tmem_wait_ld();
-    if (c + 2 >= chunks) {
+    if (c + kStride >= chunks) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) arrive_drained();
@@ -219,6 +228,15 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a0));
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(a1));
       if (!act || !((R.vmask >> i) & 1u)) continue;
+      // sixteen-warp flavour: operands are loaded where they are used (96 registers per thread, no lookahead sets)
+      uint4 r1w = make_uint4(0, 0, 0, 0), r2w = r1w, axw = r1w;
+      if constexpr (kStride == 4) {
+        if constexpr (kRes) {
+          if (has_res1) r1w = ldg_nc_u4(p.res1 + R.res_off[i] + ncol);
+          if (has_res2) r2w = ldg_nc_u4(p.res2 + R.res_off[i] + ncol);
+        }
+        if constexpr (kOut2) axw = ldg_nc_u4(p.aux + R.out_off[i] + ncol);
+      }
       f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
       f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
       if constexpr (kRowvec) {
@@ -228,14 +246,14 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
         f[4] += v1.x; f[5] += v1.y; f[6] += v1.z; f[7] += v1.w;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] *= p.acc_scale;
+      for (int j = 0; j < 8; ++j) f[j] *= acc_scale;
       if constexpr (kRes) {
         float r[8];
-        unpack8(P.r1[i], r);
+        unpack8(kStride == 4 ? r1w : P.r1[i], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaf(p.res1_scale, r[j], f[j]);
         if (has_res2) {
-          unpack8(r2[i], r);
+          unpack8(kStride == 4 ? r2w : r2[i], r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = fmaf(p.res2_scale, r[j], f[j]);
         }
@@ -243,7 +261,7 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
       stg_u4(R.out_ptr[i] + ncol, pack8(f));
       if constexpr (kOut2) {
         float r[8];
-        unpack8(P.ax[i], r);
+        unpack8(kStride == 4 ? axw : P.ax[i], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaf(p.aux_scale, r[j], f[j]);
         stg_u4(out2 + R.out_off[i] + ncol, pack8(f));
@@ -251,6 +269,14 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
     }
   };
   Pre P0, P1;
+  if constexpr (kStride == 4) {
+    // sixteen epilogue warps: no lookahead registers, the other three warps of the scheduler cover the load latency
+    for (int c = hsel; c < chunks; c += 4) {
+      fetch(c, P0);
+      process(c, P0);
+    }
+    return;
+  }
   fetch(hsel, P0);
   // optional second chunk of lookahead (three register sets; not for the second-output variants, which already
   // carry 16 more registers per set)
@@ -445,6 +471,8 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
     const int seg = lane & 3;           // which 8 columns of the 32-column chunk
     uint8_t* stage = stage_base + ew * kStageWarpBytes;
     const uint32_t stage_u32 = smem_u32(stage);
+    // conditioning_scale lives in device memory so that a captured graph picks up a new value at replay
+    const float acc_scale = p.acc_scale_ptr != nullptr ? p.acc_scale * __ldg(p.acc_scale_ptr) : p.acc_scale;
     // "accumulator drained" goes to the LEADER's barrier (remote arrive for rank 1 of a pair)
     const uint32_t tempty_addr0 = kPair ? map_to_cta(smem_u32(&tempty_bar[0]), 0u) : smem_u32(&tempty_bar[0]);
     auto arrive_tempty = [&](int acc) {
@@ -526,9 +554,9 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
           __syncwarp();
           if (lane == 0) arrive_tempty(acc);
         }
-        constexpr int kBits = kEpi - kEpiFast;
-        epilogue_fast<(kBits & 1) != 0, (kBits & 2) != 0, (kBits & 4) != 0>(
-            p, R, t_acc_f, stage_u32, n_tile * p.block_n, chunks_f, hsel, lane, [&]() { arrive_tempty(acc); });
+        constexpr int kBits = (kEpi - kEpiFast) & 7;
+        epilogue_fast<(kBits & 1) != 0, (kBits & 2) != 0, (kBits & 4) != 0, kChunkStride>(
+            p, R, t_acc_f, stage_u32, n_tile * p.block_n, chunks_f, hsel, lane, acc_scale, [&]() { arrive_tempty(acc); });
         continue;
       }
 
@@ -651,7 +679,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
               float tmp[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) tmp[j] = f[j];
-              epilogue_tail(p, tmp, sb_seg, ncol, nvalid, orow4[i], grp4[i]);
+              epilogue_tail(p, tmp, sb_seg, ncol, nvalid, orow4[i], grp4[i], acc_scale);
               continue;
             }
             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
@@ -663,7 +691,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
               f[4] += v1.x; f[5] += v1.y; f[6] += v1.z; f[7] += v1.w;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] *= p.acc_scale;
+            for (int j = 0; j < 8; ++j) f[j] *= acc_scale;
             if (p.act_silu) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = apply_act(p.act_silu, f[j]);
@@ -744,7 +772,7 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: rowvec_mode without rowvec");
   if (a->out2 != nullptr && a->aux == nullptr)
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: out2 without aux");
-  if (a->geglu && (a->rowvec_mode != 0 || a->res1 != nullptr || a->res2 != nullptr || a->out2 != nullptr || a->acc_scale != 1.0f))
+  if (a->geglu && (a->rowvec_mode != 0 || a->res1 != nullptr || a->res2 != nullptr || a->out2 != nullptr || a->acc_scale != 1.0f || a->acc_scale_ptr != nullptr))
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: GEGLU tiles support a bias-only epilogue");
   if (a->scatter_mode != 0) {
     if (a->scatter_mode < 0 || a->scatter_mode > 2 || a->sc_world < 1 || a->sc_world > 8 || a->sc_J < 1 || a->sc_S < 1 ||
@@ -772,8 +800,25 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.geglu = a->geglu ? 1 : 0;
   p.gate_row_offset = a->gate_row_offset;
   p.stage_bytes = kABytes + (a->cta_pair ? a->block_n / 2 : a->block_n) * kBlockK * 2;
-  const int epi_id_for_smem = a->geglu ? kEpiGeglu : 0;
-  const int stage_area = (epi_warps(epi_id_for_smem) * stage_warp_bytes(epi_id_for_smem) + 1023) & ~1023;
+  // epilogue flavour (needed for the shared-memory budget below)
+  int epi = kEpiGeneric;
+  if (a->geglu) {
+    epi = kEpiGeglu;
+  } else if (a->out_dtype == PT_DT_BF16 && (a->n_out % 8) == 0 && !a->act_silu && (a->out_ld % 8) == 0 &&
+             (a->res_ld % 8) == 0 && (a->rowvec_mode == 0 || (a->rowvec_ld % 4) == 0) &&
+             ((reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->out2) | reinterpret_cast<uintptr_t>(a->res1) |
+               reinterpret_cast<uintptr_t>(a->res2) | reinterpret_cast<uintptr_t>(a->aux) | reinterpret_cast<uintptr_t>(a->bias) |
+               reinterpret_cast<uintptr_t>(a->rowvec)) & 15u) == 0) {
+    epi = kEpiFast + (a->rowvec_mode != 0 ? 1 : 0) + ((a->res1 != nullptr || a->res2 != nullptr) ? 2 : 0) +
+          (a->out2 != nullptr ? 4 : 0);
+    static int env_wide = -2;   // PT_EPI16: max k-steps per tile for the 16-warp epilogue (0 disables; default 0)
+    if (env_wide == -2) {
+      const char* e = getenv("PT_EPI16");
+      env_wide = e ? atoi(e) : 0;
+    }
+    if (a->num_taps * (a->k0_chunks + a->k1_chunks) <= env_wide) epi += 8;
+  }
+  const int stage_area = (epi_warps(epi) * stage_warp_bytes(epi) + 1023) & ~1023;
   const int smem_limit = 227 * 1024 - kSmemCtl - 1024 - stage_area;
   int stages = smem_limit / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -802,6 +847,7 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   p.rv_mod = a->rv_mod > 0 ? a->rv_mod : p.rv_b;
   p.rv_off = a->rv_off > 0 ? a->rv_off : 0;
   p.acc_scale = a->acc_scale;
+  p.acc_scale_ptr = a->acc_scale_ptr;
   p.res1 = reinterpret_cast<const bf16*>(a->res1);
   p.res2 = reinterpret_cast<const bf16*>(a->res2);
   p.res1_scale = a->res1_scale;
@@ -840,34 +886,24 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
 
   const size_t smem_bytes = (size_t)kSmemCtl + (size_t)stage_area + (size_t)p.stages * p.stage_bytes + 1024;
   typedef void (*KernelFn)(TmapParam, TmapParam, TmapParam, GemmParams);
-  static const KernelFn kernels[2][10] = {
-      {gemm_tcgen05_kernel<0, false>, gemm_tcgen05_kernel<1, false>, gemm_tcgen05_kernel<2, false>,
-       gemm_tcgen05_kernel<3, false>, gemm_tcgen05_kernel<4, false>, gemm_tcgen05_kernel<5, false>,
-       gemm_tcgen05_kernel<6, false>, gemm_tcgen05_kernel<7, false>, gemm_tcgen05_kernel<8, false>,
-       gemm_tcgen05_kernel<9, false>},
-      {gemm_tcgen05_kernel<0, true>, gemm_tcgen05_kernel<1, true>, gemm_tcgen05_kernel<2, true>,
-       gemm_tcgen05_kernel<3, true>, gemm_tcgen05_kernel<4, true>, gemm_tcgen05_kernel<5, true>,
-       gemm_tcgen05_kernel<6, true>, gemm_tcgen05_kernel<7, true>, gemm_tcgen05_kernel<8, true>,
-       gemm_tcgen05_kernel<9, true>}};
-  static bool attr_set = false;
-  if (!attr_set) {
+#define PT_GEMM_ROW(P)                                                                                          \
+  {gemm_tcgen05_kernel<0, P>,  gemm_tcgen05_kernel<1, P>,  gemm_tcgen05_kernel<2, P>,  gemm_tcgen05_kernel<3, P>,  \
+   gemm_tcgen05_kernel<4, P>,  gemm_tcgen05_kernel<5, P>,  gemm_tcgen05_kernel<6, P>,  gemm_tcgen05_kernel<7, P>,  \
+   gemm_tcgen05_kernel<8, P>,  gemm_tcgen05_kernel<9, P>,  gemm_tcgen05_kernel<10, P>, gemm_tcgen05_kernel<11, P>, \
+   gemm_tcgen05_kernel<12, P>, gemm_tcgen05_kernel<13, P>, gemm_tcgen05_kernel<14, P>, gemm_tcgen05_kernel<15, P>, \
+   gemm_tcgen05_kernel<16, P>, gemm_tcgen05_kernel<17, P>}
+  constexpr int kNumEpi = 18;
+  static const KernelFn kernels[2][kNumEpi] = {PT_GEMM_ROW(false), PT_GEMM_ROW(true)};
+#undef PT_GEMM_ROW
+  static bool attr_set[PT_MAX_DEVICES] = {false};  // cudaFuncSetAttribute is per device
+  const int dev_slot = pt_device_slot();
+  if (!attr_set[dev_slot]) {
     for (int m = 0; m < 2; ++m)
-      for (int i = 0; i < 10; ++i) {
+      for (int i = 0; i < kNumEpi; ++i) {
         cudaError_t e = cudaFuncSetAttribute(kernels[m][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return pt_fail(e, "pt_gemm: cudaFuncSetAttribute");
       }
-    attr_set = true;
-  }
-  int epi = kEpiGeneric;
-  if (p.geglu) {
-    epi = kEpiGeglu;
-  } else if (p.out_dtype == PT_DT_BF16 && (p.n_out % 8) == 0 && !p.act_silu && (p.out_ld % 8) == 0 &&
-             (p.res_ld % 8) == 0 && (p.rowvec_mode == 0 || (p.rowvec_ld % 4) == 0) &&
-             ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.out2) | reinterpret_cast<uintptr_t>(p.res1) |
-               reinterpret_cast<uintptr_t>(p.res2) | reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.bias) |
-               reinterpret_cast<uintptr_t>(p.rowvec)) & 15u) == 0) {
-    epi = kEpiFast + (p.rowvec_mode != 0 ? 1 : 0) + ((p.res1 != nullptr || p.res2 != nullptr) ? 2 : 0) +
-          (p.out2 != nullptr ? 4 : 0);
+    attr_set[dev_slot] = true;
   }
   if (p.scatter_mode != 0 && epi < kEpiFast)
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: scatter needs 16-byte aligned operands and strides (lean epilogue)");

@@ -9,6 +9,10 @@ int pt_fail(int code, const char* what);
 // to be called right after a kernel launch: checks cudaGetLastError, counts the launch
 int pt_launched(const char* what);
 int pt_num_sms();
+// index of the calling thread's current device, clamped to [0, PT_MAX_DEVICES): per-device caches (function attributes,
+// SM counts, occupancy) are keyed by it, so one process may drive several GPUs
+constexpr int PT_MAX_DEVICES = 64;
+int pt_device_slot();
 
 #define PT_CHECK_ARG(cond, msg)                                   \
   do {                                                            \

@@ -520,15 +520,16 @@ static int gn_red_bytes(int C) {
 static int gn_ctas_per_sm(int C) {
   const int threads = gn_block_threads(C);
   const int smem = gn_red_bytes(C);
-  static int cached_threads = 0, cached_smem = 0, cached_blocks = 0;
-  if (cached_threads != threads || cached_smem != smem) {
+  static int cached_threads[PT_MAX_DEVICES] = {0}, cached_smem[PT_MAX_DEVICES] = {0}, cached_blocks[PT_MAX_DEVICES] = {0};
+  const int d = pt_device_slot();
+  if (cached_threads[d] != threads || cached_smem[d] != smem) {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_fused_kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
-    cached_threads = threads;
-    cached_smem = smem;
-    cached_blocks = nb;
+    cached_threads[d] = threads;
+    cached_smem[d] = smem;
+    cached_blocks[d] = nb;
   }
-  return cached_blocks < 4 ? cached_blocks : 4;
+  return cached_blocks[d] < 4 ? cached_blocks[d] : 4;
 }
 
 constexpr int kGnSmemPerSm = 216 * 1024;  // of 228 KB: 1 KB per CTA is reserved by the system, static smem, margin
@@ -608,11 +609,12 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   p.res_slots = a->mode == 0 ? gn_res_slots(C, gn_ctas_per_sm(C), rows_per_split) : 0;
   p.res_off = gn_red_bytes(C);
   const size_t smem_bytes = (size_t)p.res_off + (size_t)p.res_slots * threads * 16;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[PT_MAX_DEVICES] = {false};  // cudaFuncSetAttribute is per device
+  const int dev_slot = pt_device_slot();
+  if (!attr_set[dev_slot]) {
     cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemPerSm);
     if (e != cudaSuccess) return pt_fail(e, "pt_groupnorm: cudaFuncSetAttribute");
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   pt_launch(gn_fused_kernel, dim3(a->num_stat * splits), dim3(threads), smem_bytes, (void*)stream, 1, p);
   return pt_launched("pt_groupnorm");

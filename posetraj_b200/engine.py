@@ -156,7 +156,11 @@ class NetPlan:
         self.step_ops: List = []    # every denoise step
         self.embed_ops: List = []   # when encoder_hidden_states / added_time_ids change
         self.cond_ops: List = []    # when controlnet_cond / camera_cond change (ControlNet only)
-        self.scale_ops: List = []   # zero-conv GEMMs whose acc_scale is `conditioning_scale`
+        self.scale_ops: List = []   # zero-conv GEMMs scaled by `conditioning_scale`
+        # conditioning_scale as a DEVICE scalar: the zero-conv GEMMs read it when they run, so a captured CUDA graph
+        # of the step follows the value of the current call (controlnet_sdv.py:641-643)
+        self.cond_scale = torch.ones(1, device=device, dtype=F32)
+        self._cond_scale_host = 1.0
         ch = cfg.block_out_channels
         if height % (2 ** (len(ch) - 1)) or width % (2 ** (len(ch) - 1)):
             raise ValueError("latent height/width must be divisible by 8 (three stride-2 levels)")
@@ -512,7 +516,8 @@ class NetPlan:
 
             def done(self_, i, t):
                 key = f"controlnet_down_blocks.{i}"
-                g = ops.Gemm(t, w.linear(key + ".weight"), plan.res[i], bias=w.f32(key + ".bias"), acc_scale=1.0, name=key)
+                g = ops.Gemm(t, w.linear(key + ".weight"), plan.res[i], bias=w.f32(key + ".bias"), acc_scale=1.0,
+                             acc_scale_dev=plan.cond_scale, name=key)
                 plan.step_ops.append(g)
                 plan.scale_ops.append(g)
 
@@ -524,7 +529,7 @@ class NetPlan:
         mid = self.resblock("mid_block.resnets.1.", z, None, ch[-1], hw, 1e-5)
         self.pool.put(z)
         g = ops.Gemm(mid, w.linear("controlnet_mid_block.weight"), self.res[-1], bias=w.f32("controlnet_mid_block.bias"),
-                     acc_scale=1.0, name="controlnet_mid_block")
+                     acc_scale=1.0, acc_scale_dev=self.cond_scale, name="controlnet_mid_block")
         self.step_ops.append(g)
         self.scale_ops.append(g)
         self.pool.put(mid)
@@ -668,8 +673,10 @@ class NetPlan:
     # execution
     # ================================================================================================
     def set_conditioning_scale(self, scale: float) -> None:
-        for g in self.scale_ops:
-            g.args.acc_scale = float(scale)
+        """Stream-ordered write of the device scalar every zero-conv GEMM multiplies its accumulator by."""
+        if float(scale) != self._cond_scale_host:
+            self.cond_scale.fill_(float(scale))
+            self._cond_scale_host = float(scale)
 
     @staticmethod
     def run(op_list, stream_ptr: Optional[int] = None) -> None:

@@ -457,7 +457,6 @@ class FrameShardedEngine:
             plan.ehs.copy_(image_embeddings[:, 0, :])
             plan.time_ids.copy_(added_time_ids.reshape(-1))
             NetPlan.run(plan.embed_ops, sp)
-        self.cplan._cond_key = None
         cond = controlnet_condition[:, f0:f0 + nf].contiguous()
         cam = None if camera_cond is None else camera_cond[:, f0:f0 + nf].contiguous()
         self.controlnet.stage_condition(self.cplan, cond, cam, None, sp)

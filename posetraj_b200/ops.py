@@ -121,7 +121,8 @@ class Gemm:
                  out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_scale: float = 0.0,
                  halo: Optional[tuple] = None, ostride: int = 1, out_halo: bool = False,
                  act_silu=False, name: str = "gemm", alg_k: Optional[int] = None,
-                 cta_pair: Optional[bool] = None, scatter: Optional[dict] = None):
+                 cta_pair: Optional[bool] = None, scatter: Optional[dict] = None,
+                 acc_scale_dev: Optional[torch.Tensor] = None):
         assert a0.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
         assert a0.dim() == 2 and w.dim() == 2 and a0.stride(1) == 1 and w.stride(1) == 1
         self.name = name
@@ -185,6 +186,10 @@ class Gemm:
             if len(rv) == 5:
                 a.rv_mod, a.rv_off = rv[3], rv[4]
         a.acc_scale = acc_scale
+        if acc_scale_dev is not None:
+            # device scalar multiplied into acc_scale at run time (conditioning_scale: survives CUDA-graph replay)
+            assert acc_scale_dev.dtype == torch.float32 and acc_scale_dev.numel() == 1 and not geglu
+            a.acc_scale_ptr = acc_scale_dev.data_ptr()
         out_rows = out.shape[0]
         if scatter is not None:
             # fused all-to-all: `out` is this rank's destination buffer in the OTHER sharding; the rows this GEMM
@@ -245,7 +250,7 @@ class Gemm:
         self.alg_flops = 2.0 * valid_rows * n_out * (2 if geglu else 1) * (alg_k if alg_k is not None else ntaps * (k0 + k1))
         self.alg_bytes = 0.0
         self.args = a
-        self._keep = (a0, a1, w, out, bias, rowvec, res1, res2, out2, aux)
+        self._keep = (a0, a1, w, out, bias, rowvec, res1, res2, out2, aux, acc_scale_dev)
         self._argp = C.addressof(a)
 
     def launch(self, stream_ptr: int) -> None:

@@ -174,9 +174,7 @@ class DenoiseEngine:
             plan.ehs.copy_(image_embeddings[:, 0, :])            # every shard keeps ALL rows' embeddings (fact 11)
             plan.time_ids.copy_(added_time_ids[rb:rb + rc].reshape(-1))
             NetPlan.run(plan.embed_ops, sp)
-        # once per video: always re-run the conditioning embedding (a pointer/version cache key could alias a new
-        # tensor that the caching allocator placed at the same address)
-        self.cplan._cond_key = None
+        # once per video: the conditioning embedding is always re-run
         self.controlnet.stage_condition(self.cplan, controlnet_condition[rb:rb + rc],
                                         None if camera_cond is None else camera_cond[rb:rb + rc], None, sp)
         self.cplan.set_conditioning_scale(cond_scale)
@@ -415,6 +413,12 @@ class StableVideoDiffusionPipelineControlNet:
                 new = out.pop("latents", cb_latents) if isinstance(out, dict) else cb_latents
                 if new.data_ptr() != eng.latents.data_ptr():
                     eng.latents.copy_(new.reshape(eng.latents.shape))
+                # the fused update kernel has already written the NEXT step's model input from the pre-callback
+                # latents; the reference re-derives latent_model_input from `latents` every step (:532-537), so rebuild
+                # it (mode 1: scale by sigma[step_index], which StepAdvance has already moved on) whether the callback
+                # returned a new tensor or edited the view in place
+                if i + 1 < len(timesteps):
+                    eng.prepare_op.launch(torch.cuda.current_stream().cuda_stream)
         if self._frame_shard is not None:
             latents = eng.gather_latents().view(1, num_frames, -1, h, w)
         else:

@@ -51,3 +51,10 @@ def make_small_inputs(cfg, h=16, w=24, seed=1234):
     inp["controlnet_condition"] = torch.cat([cond[None]] * 2)
     inp["camera_cond"] = torch.cat([torch.randn(1, cfg.num_frames, 12, generator=g) * 0.1] * 2)
     return inp
+
+
+def make_small_bbox_maps(cfg, inp, seed=4321):
+    """Sparse +-1 maps for the bbox tower (controlnet_sdv_bbox.py:109-138), same for both rows of the CFG pair."""
+    g = torch.Generator().manual_seed(seed)
+    hw = inp["controlnet_condition"].shape[-2:]
+    return torch.cat([(torch.rand(1, cfg.num_frames, 3, *hw, generator=g) > 0.97).float() * 2 - 1] * 2)

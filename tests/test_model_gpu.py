@@ -138,6 +138,93 @@ def test_pipeline_three_steps(small_setup, cuda_dev):
     assert rel_l2(got2, got) < 1e-6
 
 
+def test_step_end_callback_edits_reach_the_next_model_input(small_setup, cuda_dev):
+    """latents changed by `callback_on_step_end` (returned as a new tensor, or edited in place) must feed the
+    NEXT step's ControlNet / UNet input, as in the reference loop which re-derives latent_model_input from `latents`
+    every iteration (pipeline...controlnet.py:532-537, callback :574-580)."""
+    from oracle.pipeline import denoise_step
+    from oracle.scheduler import EulerKarrasOracle
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    cfg, o_unet, o_cnet, unet, cnet = small_setup
+    inp = make_small_inputs(cfg, seed=31)
+    steps = 3
+
+    def edit(i, lat):
+        return lat * 0.9 if i == 0 else lat + 0.05 * lat.flip(-1)
+
+    sched = EulerKarrasOracle()
+    sched.set_timesteps(steps)
+    want = inp["latents"]
+    for i, t in enumerate(sched.timesteps):
+        want = denoise_step(o_unet, o_cnet, sched, want, i, t, inp["image_latents"], inp["image_embeddings"],
+                            inp["controlnet_condition"], inp["added_time_ids"], inp["guidance"])
+        if i < 2:
+            want = edit(i, want)
+
+    def cb(pipe, i, t, kw):
+        lat = kw["latents"]
+        if i == 0:
+            lat.mul_(0.9)                     # in place: same storage, nothing returned for it
+            return {}
+        if i == 1:
+            return {"latents": edit(i, lat)}  # a new tensor
+        return kw
+
+    pipe = StableVideoDiffusionPipelineControlNet(unet=unet, controlnet=cnet)
+    h, w = inp["latents"].shape[-2:]
+    init_sigma = (700.0 ** 2 + 1) ** 0.5
+    got = pipe(None, inp["controlnet_condition"][0].to(cuda_dev), height=h * 8, width=w * 8, num_frames=cfg.num_frames,
+               num_inference_steps=steps, latents=(inp["latents"] / init_sigma).to(cuda_dev), output_type="latent",
+               image_embeddings=inp["image_embeddings"].to(cuda_dev), image_latents=inp["image_latents"].to(cuda_dev),
+               callback_on_step_end=cb).frames
+    torch.cuda.synchronize()
+    _record("latents after 3 steps with a latents-editing callback", rel_l2(got, want))
+    assert rel_l2(got, want) < 2 * TOL
+
+
+def test_conditioning_scale_follows_the_call_through_the_captured_graph(small_setup, cuda_dev):
+    """engines (and their CUDA graph) are cached per shape; a later call with another controlnet_cond_scale
+    must use the new scale in EVERY step, not only in the eager first one."""
+    from oracle.pipeline import denoise
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    cfg, o_unet, o_cnet, unet, cnet = small_setup
+    inp = make_small_inputs(cfg, seed=55)
+    pipe = StableVideoDiffusionPipelineControlNet(unet=unet, controlnet=cnet)
+    h, w = inp["latents"].shape[-2:]
+    init_sigma = (700.0 ** 2 + 1) ** 0.5
+    outs = {}
+    for scale in (1.0, 0.3):
+        with torch.no_grad():
+            want = denoise(o_unet, o_cnet, inp["latents"], inp["image_latents"], inp["image_embeddings"],
+                           inp["controlnet_condition"], inp["added_time_ids"], inp["guidance"], num_inference_steps=4,
+                           cond_scale=scale)
+        got = pipe(None, inp["controlnet_condition"][0].to(cuda_dev), height=h * 8, width=w * 8,
+                   num_frames=cfg.num_frames, num_inference_steps=4, latents=(inp["latents"] / init_sigma).to(cuda_dev),
+                   output_type="latent", image_embeddings=inp["image_embeddings"].to(cuda_dev),
+                   image_latents=inp["image_latents"].to(cuda_dev), controlnet_cond_scale=scale).frames
+        torch.cuda.synchronize()
+        outs[scale] = want
+        assert rel_l2(got, want) < 2 * TOL, (scale, rel_l2(got, want))
+    assert rel_l2(outs[0.3], outs[1.0]) > 5 * TOL   # the two scales are far enough apart for the check to mean something
+
+
+def test_forward_restages_conditioning_for_a_new_tensor_at_the_same_address(small_setup, cuda_dev):
+    """`forward()` must not infer "same conditioning" from (data_ptr, _version)."""
+    cfg, o_unet, o_cnet, unet, cnet = small_setup
+    inp = to_dev(make_small_inputs(cfg), cuda_dev)
+    x = model_input(inp, 10.0)
+    cond = inp["controlnet_condition"].clone()
+    a = [r.clone() for r in cnet(x, 0.5, inp["image_embeddings"], inp["added_time_ids"], controlnet_cond=cond,
+                                 return_dict=False)[0]]
+    ptr = cond.data_ptr()
+    del cond
+    cond2 = torch.empty_like(inp["controlnet_condition"])      # the caching allocator hands the same block back
+    cond2.copy_(-inp["controlnet_condition"].flip(-1))
+    b = cnet(x, 0.5, inp["image_embeddings"], inp["added_time_ids"], controlnet_cond=cond2, return_dict=False)[0]
+    torch.cuda.synchronize()
+    assert rel_l2(b[0], a[0]) > 1e-3, "conditioning of the previous call was reused" + (" (same address)" if cond2.data_ptr() == ptr else "")
+
+
 def test_error_is_at_the_level_of_torch_bf16(small_setup, cuda_dev):
     """Context for the 1e-2 tolerance: the SAME wiring run as plain torch bf16 on the GPU (cuDNN / cuBLAS / SDPA — the
     reference's own reduced-precision path) is about as far from the fp32 oracle as our kernels are."""
