@@ -129,8 +129,10 @@ def _cpu_sample_plan(budget_s_per_step: float):
     return 1, 24, 40  # quarter-ish resolution: still every layer of both networks
 
 
-def cpu_oracle_steps_per_sec(steps: int, warmup: int, budget_s: float = 150.0):
-    """Times the oracle (fp32, all host threads) on a bounded sample and extrapolates by algorithmic FLOPs."""
+def cpu_oracle_steps_per_sec(steps: int, warmup: int, budget_s: float = 150.0, full: bool = False):
+    """Times the oracle (fp32, all host threads).  `full`: ONE step of the whole workload (CFG pair x 14 frames x 40x72,
+    ~20 s on 16 cores) after a reduced-size warm-up — no extrapolation.  Otherwise a bounded sample (fewer frames /
+    lower resolution, every layer of both networks), scaled by the algorithmic FLOP count, sized to `budget_s`."""
     import torch
     from oracle.models import build_models
     from oracle.pipeline import denoise_step, make_inputs
@@ -139,30 +141,38 @@ def cpu_oracle_steps_per_sec(steps: int, warmup: int, budget_s: float = 150.0):
     from posetraj_b200.roofline import step_flops
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    f, h, w = _cpu_sample_plan(budget_s / max(1, steps + warmup))
     unet, cnet = build_models(seed=0, randomize_zero_convs=True)
-    inp = make_inputs(num_frames=f, h=h, w=w)
-    cond = torch.full((2, f, 3, h * 8, w * 8), -1.0)
     sched = EulerKarrasOracle()
     sched.set_timesteps(SAMPLING_STEPS)
-    lat = inp["latents"]
+
+    def one(f, h, w, k):
+        inp = make_inputs(num_frames=f, h=h, w=w)
+        cond = torch.full((2, f, 3, h * 8, w * 8), -1.0)
+        sched._step_index = None
+        t0 = time.perf_counter()
+        denoise_step(unet, cnet, sched, inp["latents"], k, sched.timesteps[k], inp["image_latents"], inp["image_embeddings"],
+                     cond, inp["added_time_ids"], inp["guidance"])
+        return time.perf_counter() - t0
+
+    if full:
+        one(2, 16, 24, 0)                                # pages the 8.8 GB of fp32 weights in, warms the thread pool
+        times = [one(FRAMES, LAT_H, LAT_W, k % SAMPLING_STEPS) for k in range(max(1, steps))]
+        t_step = sum(times) / len(times)
+        sample = (f"oracle (torch CPU fp32 restatement of the reference), the FULL step: CFG pair x {FRAMES} frames at latent "
+                  f"{LAT_H}x{LAT_W}, {len(times)} timed step(s) of {t_step:.2f} s after a reduced-size warm-up; not extrapolated")
+        return 1.0 / t_step, t_step, cores, sample
+    f, h, w = _cpu_sample_plan(budget_s / max(1, steps + warmup))
     times = []
     for i in range(warmup + steps):
-        sched._step_index = None
-        k = i % SAMPLING_STEPS
-        t0 = time.perf_counter()
-        lat_new = denoise_step(unet, cnet, sched, lat, k, sched.timesteps[k], inp["image_latents"], inp["image_embeddings"],
-                               cond, inp["added_time_ids"], inp["guidance"])
-        dt = time.perf_counter() - t0
+        dt = one(f, h, w, i % SAMPLING_STEPS)
         if i >= warmup:
             times.append(dt)
-        del lat_new
     t_step = sum(times) / len(times)
-    full, _ = step_flops(SVDConfig(), frames=FRAMES, h=LAT_H, w=LAT_W)
+    full_fl, _ = step_flops(SVDConfig(), frames=FRAMES, h=LAT_H, w=LAT_W)
     part, _ = step_flops(SVDConfig(), frames=f, h=h, w=w)
-    value = (part / full) / t_step
+    value = (part / full_fl) / t_step
     sample = (f"oracle (torch CPU fp32 restatement of the reference) on {f} of {FRAMES} frames at latent {h}x{w}, "
-              f"{steps} timed step(s) of {t_step:.2f} s each, scaled by algorithmic FLOPs {part / 1e12:.2f}/{full / 1e12:.2f} TFLOP")
+              f"{steps} timed step(s) of {t_step:.2f} s each, scaled by algorithmic FLOPs {part / 1e12:.2f}/{full_fl / 1e12:.2f} TFLOP")
     return value, t_step, cores, sample
 
 
@@ -170,7 +180,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, t_step, cores, sample = cpu_oracle_steps_per_sec(args.steps, args.warmup)
+    # the whole step costs ~20 s on 16 cores: run it un-sampled when the requested steps fit in a few minutes
+    full = args.steps <= 6
+    value, t_step, cores, sample = cpu_oracle_steps_per_sec(args.steps, args.warmup, full=full)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
@@ -265,6 +277,216 @@ def full_pipeline_leg(unet, cnet, tracks, dev):
                        "CLIP ViT-H/14 632M + VAE 97.7M random-init, 25 steps, frames [14,320,576,3] returned on the host"}
     except Exception as e:  # the extra must never take the contract line down with it
         return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# extra legs (BASELINE.json configs[2] / configs[4]); `value` stays the video-batch number
+# ---------------------------------------------------------------------------------------------------------------
+def _video_inputs(cfg, frames, h, w, seed, pin=True):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(1, frames, 4, h, w, generator=g)
+    img = torch.randn(1, 4, h, w, generator=g)
+    emb = torch.randn(1, 1, cfg.cross_attention_dim, generator=g)
+    out = dict(latents=lat, image_latents=torch.cat([torch.zeros_like(img), img]),
+               image_embeddings=torch.cat([torch.zeros_like(emb), emb]))
+    return {k: (v.pin_memory() if pin else v) for k, v in out.items()}
+
+
+def _max_over_ranks(x, dev, world):
+    import torch
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _rel_l2(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _time_engine_steps(eng, steps, dev, world, barrier):
+    """Device time of `steps` denoise steps of an already captured engine, max over ranks (ms per step)."""
+    import torch
+    eng.reset()
+    eng.step()
+    eng.reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        if i and i % SAMPLING_STEPS == 0:
+            eng.reset()
+        eng.step()
+    e1.record()
+    barrier()
+    return _max_over_ranks(e0.elapsed_time(e1) / steps, dev, world)
+
+
+def cam_leg(cfg, unet, dev, rank, world, steps, barrier):
+    """BASELINE.json configs[2]: controlnet_sdv_cam (camera_control_module branch: cc_projection on [features | camera_RT],
+    /root/reference/models/controlnet_sdv_cam_infer.py:96-122), one video (CFG pair) per GPU, N videos on N GPUs."""
+    import torch
+    from posetraj_b200.models import ControlNetSDVModel
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    from posetraj_b200.trajectory import rasterize_tracks
+    cnet = ControlNetSDVModel.from_random(cfg, dev, seed=0, cam=True, faithful_zero_init=False)
+    pipe = StableVideoDiffusionPipelineControlNet(unet=unet, controlnet=cnet)
+    H, W = LAT_H * 8, LAT_W * 8
+    inp = _video_inputs(cfg, FRAMES, LAT_H, LAT_W, 4321 + rank)
+    tracks = torch.tensor(_synthetic_tracks(FRAMES), dtype=torch.int32).pin_memory()
+    g = torch.Generator().manual_seed(99 + rank)
+    cam = (torch.randn(FRAMES, 12, generator=g) * 0.1).pin_memory()
+    cam[0] = 0.0   # relative pose of frame 0 is the identity offset (infer/run_inference_vipseg_json_cam_concat_repro.py:485-496)
+
+    def call():
+        cond = rasterize_tracks(tracks, FRAMES, H, W, dev, output="f32")
+        return pipe(None, cond, camera_cond=cam, height=H, width=W, num_frames=FRAMES, num_inference_steps=SAMPLING_STEPS,
+                    latents=inp["latents"], output_type="latent", image_embeddings=inp["image_embeddings"],
+                    image_latents=inp["image_latents"]).frames.to("cpu")
+
+    out = call()
+    eng = pipe.engine_for(FRAMES, LAT_H, LAT_W, (H, W))
+    ms = _time_engine_steps(eng, steps, dev, world, barrier)
+    barrier()
+    t0 = time.perf_counter()
+    call()
+    torch.cuda.synchronize()
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, dev, world)
+    res = {"workload": "configs[2]: controlnet_sdv_cam (camera branch), 14 frames 320x576, one video per GPU",
+           "ms_per_step": ms, "value": world * 1000.0 / ms, "unit": UNIT, "videos_per_min": world * 60000.0 / ms / SAMPLING_STEPS,
+           "e2e_value": world * SAMPLING_STEPS / e2e_s, "finite": bool(torch.isfinite(out).all())}
+    del pipe, cnet, eng
+    torch.cuda.empty_cache()
+    return res
+
+
+def cfg_split_leg(cfg, unet, cnet, dev, rank, world, steps, barrier, ms_replica, lat_single_rank0):
+    """SURVEY.md 8e "CFG branch": one video on 2 GPUs, rank r of a pair runs row r of the CFG pair through both networks,
+    the two 161 KB predictions are all-gathered over NCCL each step, both ranks redo the CFG + Euler update."""
+    import torch
+    import torch.distributed as dist
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    from posetraj_b200.sharding import cfg_split_ranks
+    from posetraj_b200.trajectory import rasterize_tracks
+    pairs = cfg_split_ranks(world)
+    groups = [dist.new_group(ranks=list(p)) for p in pairs]   # every rank creates every group (collective)
+    pair, row = rank // 2, rank % 2
+    pipe = StableVideoDiffusionPipelineControlNet(unet=unet, controlnet=cnet)
+    pipe.enable_cfg_split(row, group=groups[pair])
+    H, W = LAT_H * 8, LAT_W * 8
+    inp = _video_inputs(cfg, FRAMES, LAT_H, LAT_W, 1234 + 2 * pair)   # pair 0 = the video rank 0 ran alone
+    tracks = torch.tensor(_synthetic_tracks(FRAMES), dtype=torch.int32).pin_memory()
+
+    def call():
+        cond = rasterize_tracks(tracks, FRAMES, H, W, dev, output="f32")
+        return pipe(None, cond, height=H, width=W, num_frames=FRAMES, num_inference_steps=SAMPLING_STEPS,
+                    latents=inp["latents"], output_type="latent", image_embeddings=inp["image_embeddings"],
+                    image_latents=inp["image_latents"]).frames.to("cpu")
+
+    out = call()
+    eng = pipe.engine_for(FRAMES, LAT_H, LAT_W, (H, W))
+    ms = _time_engine_steps(eng, steps, dev, world, barrier)
+    barrier()
+    t0 = time.perf_counter()
+    call()
+    torch.cuda.synchronize()
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, dev, world)
+    res = {"workload": "configs[1], one video per PAIR of GPUs (rank = row of the CFG pair), NCCL all-gather of 2 x 161 KB per step",
+           "pairs": len(pairs), "ms_per_step": ms, "value": len(pairs) * 1000.0 / ms, "unit": UNIT,
+           "latency_speedup_vs_1gpu": ms_replica / ms, "e2e_value": len(pairs) * SAMPLING_STEPS / e2e_s,
+           "backend": dist.get_backend(groups[pair]), "launches_per_step": eng.launches_per_step}
+    if rank == 0 and lat_single_rank0 is not None:
+        res["rel_l2_latents_25_steps_vs_1gpu"] = _rel_l2(out, lat_single_rank0)
+    del pipe, eng
+    torch.cuda.empty_cache()
+    return res
+
+
+def frame_sharded_leg(cfg, unet, cnet, dev, rank, world, steps, barrier):
+    """BASELINE.json configs[4] / SURVEY.md 8e "Frames": ONE 25-frame 576x1024 video (latent 72x128) over all N GPUs —
+    frame-sharded spatial layers, pixel-sharded temporal layers, the exchange fused into the producing GEMM's epilogue
+    over NVLink peer memory (PtGemmArgs.scatter_mode), one device barrier per exchange, no NCCL inside the step."""
+    import torch
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    from posetraj_b200.roofline import step_flops
+    from posetraj_b200.trajectory import rasterize_tracks
+    F, h, w = 25, 72, 128
+    inp = _video_inputs(cfg, F, h, w, 777, pin=False)   # the same video on every rank
+    tracks = [[[20 + 9 * k, 30 + 5 * k] for k in range(F)]]
+    n_par = 3
+
+    def run(pipe, n_steps):
+        cond = rasterize_tracks(tracks, F, h * 8, w * 8, dev)
+        return pipe(None, cond, height=h * 8, width=w * 8, num_frames=F, num_inference_steps=n_steps, output_type="latent",
+                    latents=inp["latents"], image_embeddings=inp["image_embeddings"], image_latents=inp["image_latents"]).frames
+
+    pipe = StableVideoDiffusionPipelineControlNet(unet=unet, controlnet=cnet)
+    pipe.enable_frame_sharding(rank, world)
+    got = run(pipe, n_par).float().cpu()
+    eng = pipe.engine_for(F, h, w, (h * 8, w * 8))
+    ms = _time_engine_steps(eng, steps, dev, world, barrier)
+    fl, _ = step_flops(cfg, frames=F, h=h, w=w, essential=True)
+    res = {"workload": "configs[4]: 25 frames x 576x1024 (latent 72x128), ONE video frame-sharded over all GPUs",
+           "ms_per_step": ms, "value": 1000.0 / ms, "unit": UNIT, "aggregate_tflops": fl / ms / 1e9,
+           "exchange": "p2p scatter epilogue" if getattr(eng.cplan, "p2p", False) else "nccl all-to-all",
+           "graph": eng.graph is not None, "launches_per_step": eng.launches_per_step,
+           "barriers_or_collectives_per_step": eng.collectives_per_step,
+           "peak_mem_gib_per_rank": torch.cuda.max_memory_allocated() / 2 ** 30}
+    eng.graph = None
+    del pipe, eng
+    torch.cuda.empty_cache()
+    barrier()
+    # rank 0 alone: the unsharded plan on the same inputs — parity of the sharded latents and the in-run 1-GPU time
+    if rank == 0:
+        pipe1 = StableVideoDiffusionPipelineControlNet(unet=unet, controlnet=cnet)
+        want = run(pipe1, n_par).float().cpu()
+        eng1 = pipe1.engine_for(F, h, w, (h * 8, w * 8))
+        ms1 = _time_engine_steps(eng1, 3, dev, 1, torch.cuda.synchronize)
+        res["rel_l2_latents_3_steps_vs_1gpu"] = _rel_l2(got, want)
+        res["ms_per_step_1gpu_same_run"] = ms1
+        res["speedup_vs_1gpu"] = ms1 / ms
+        res["ideal_ms_per_step"] = ms1 / world
+        del pipe1, eng1
+        torch.cuda.empty_cache()
+    barrier()
+    return res
+
+
+def library_baseline_leg(dev, steps=3):
+    """The "library bar": the oracle's wiring as plain torch eager bf16 on this GPU (cuDNN / cuBLAS / SDPA, no fusion) —
+    what the reference would run here, since it ships no Blackwell kernel.  Comparator only (imports oracle/)."""
+    import torch
+    from oracle.models import build_models
+    from oracle.pipeline import denoise_step, make_inputs
+    from oracle.scheduler import EulerKarrasOracle
+    torch.manual_seed(0)
+    with torch.device(dev):
+        unet, cnet = build_models(seed=0, randomize_zero_convs=False)
+    unet, cnet = unet.to(torch.bfloat16), cnet.to(torch.bfloat16)
+    inp = {k: (v.to(dev, torch.bfloat16) if torch.is_tensor(v) else v) for k, v in make_inputs().items()}
+    cond = torch.full((2, FRAMES, 3, LAT_H * 8, LAT_W * 8), -1.0, device=dev, dtype=torch.bfloat16)
+    sched = EulerKarrasOracle()
+    sched.set_timesteps(SAMPLING_STEPS, device=dev)
+    times = []
+    for i in range(steps + 2):
+        sched._step_index = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        denoise_step(unet, cnet, sched, inp["latents"], 0, sched.timesteps[0], inp["image_latents"], inp["image_embeddings"],
+                     cond, inp["added_time_ids"], inp["guidance"])
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    del unet, cnet
+    torch.cuda.empty_cache()
+    return {"what": "torch 2.11 eager bf16 of the same wiring (cuDNN / cuBLAS / SDPA), same GPU, same shapes",
+            "ms_per_step": ms, "value": 1000.0 / ms, "unit": UNIT}
 
 
 def run_own(args):
@@ -417,8 +639,29 @@ def run_own(args):
         }
         if world == 1:
             line["full_pipeline"] = full_pipeline_leg(unet, cnet, tracks, dev)
+    # ---- extra legs: every rank takes part (collectives); rank 0 reports ------------------------------------------
+    extras = {}
+    if not args.no_legs:
+        leg_steps = max(5, min(args.steps, 20))
+
+        def leg(name, fn, *a):
+            try:
+                extras[name] = fn(*a)
+            except Exception as e:  # noqa: BLE001 - an extra must not take the contract line down
+                extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+        leg("configs2_cam", cam_leg, cfg, unet, dev, rank, world, leg_steps, barrier)
+        if world >= 2 and world % 2 == 0:
+            leg("cfg_split", cfg_split_leg, cfg, unet, cnet, dev, rank, world, leg_steps, barrier, ms_per_step,
+                lat_final if rank == 0 else None)
+        if world >= 2:
+            leg("frame_sharded", frame_sharded_leg, cfg, unet, cnet, dev, rank, world, leg_steps, barrier)
+        if world == 1:
+            leg("library_baseline", library_baseline_leg, dev)
+    if rank == 0:
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
-            v, t_step, cores, sample = cpu_oracle_steps_per_sec(1, 1, budget_s=40.0)
+            v, t_step, cores, sample = cpu_oracle_steps_per_sec(1, 0, full=True)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -434,6 +677,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the extra legs (cam, CFG split, frame sharding, library baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
