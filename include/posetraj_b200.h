@@ -163,6 +163,32 @@ typedef struct PtGemmArgs {
 int pt_gemm(const PtGemmArgs* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Fused GEGLU feed-forward (diffusers FeedForward = GEGLU proj + Linear; BasicTransformerBlock.ff,           */
+/* TemporalBasicTransformerBlock.ff_in / .ff as run by models/modified_svd.py:70-74,100-107):                */
+/*   out = acc_scale * (GEGLU(x W1^T + b1) W2^T + b2) + res1_scale * res1 + res2_scale * res2                 */
+/* in ONE kernel: the [rows, 4C] hidden activations stay in TMEM / shared memory (CTA pairs, 256-row tiles,   */
+/* hidden dimension walked in chunks of 64).  For C <= 320 (the output accumulator must fit TMEM next to the */
+/* hidden one): level 0 of the SVD UNet.                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct PtMlpArgs {
+  const PtTensorMap* tmap_x;   /* x  bf16 [rows, C]:  rank-2 {C, rows},        box {64, 128} */
+  const PtTensorMap* tmap_w1;  /* W1 bf16 [2*hidden, C] (value rows, then gate rows): rank-2 {C, 2*hidden}, box {64, 64} */
+  const PtTensorMap* tmap_w2;  /* W2 bf16 [C, hidden]: rank-2 {hidden, C},     box {64, C/4} */
+  int32_t rows, C, hidden;     /* hidden == 4*C; C a multiple of 64, <= 320 */
+  const float* bias1;          /* [2*hidden] */
+  const float* bias2;          /* [C] */
+  float acc_scale;
+  const void* res1;            /* bf16 [rows, res_ld] or NULL */
+  const void* res2;
+  float res1_scale, res2_scale;
+  int32_t res_ld;
+  void* out;                   /* bf16 [rows, out_ld] */
+  int32_t out_ld;
+  void* trace;                 /* debug only: int64[2*8*64] clock stamps of CTA 0, or NULL */
+} PtMlpArgs;
+int pt_mlp_geglu(const PtMlpArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* GroupNorm(32) (+SiLU): diffusers ResnetBlock2D.norm1/2, TemporalResnetBlock.norm1/2 (5-D    */
 /* statistics), TransformerSpatioTemporalModel.norm, conv_norm_out                             */
 /* (models/unet_spatio_temporal_condition_controlnet.py:237-238,494-495)    */

@@ -87,6 +87,11 @@ def _st(name, fields):
 
 i32, f32, vp = C.c_int32, C.c_float, C.c_void_p
 
+PtMlpArgs = _st("PtMlpArgs", [
+    ("tmap_x", vp), ("tmap_w1", vp), ("tmap_w2", vp), ("rows", i32), ("C", i32), ("hidden", i32),
+    ("bias1", vp), ("bias2", vp), ("acc_scale", f32), ("res1", vp), ("res2", vp),
+    ("res1_scale", f32), ("res2_scale", f32), ("res_ld", i32), ("out", vp), ("out_ld", i32), ("trace", vp)])
+
 PtGroupNormArgs = _st("PtGroupNormArgs", [
     ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32),
     ("rows_per_stat", i32), ("num_stat", i32), ("stats", vp), ("gamma", vp), ("beta", vp),
@@ -168,6 +173,7 @@ _SIGNATURES = {
     "pt_cfg_euler_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_gemm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_mlp_geglu": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_groupnorm_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "pt_layernorm": (C.c_int, [C.c_void_p, C.c_void_p]),

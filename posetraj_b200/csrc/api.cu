@@ -118,6 +118,7 @@ extern "C" int pt_sizeof(const char* name) {
   if (!strcmp(name, "PtTensorMap")) return (int)sizeof(PtTensorMap);
   if (!strcmp(name, "PtCfgEulerArgs")) return (int)sizeof(PtCfgEulerArgs);
   if (!strcmp(name, "PtGemmArgs")) return (int)sizeof(PtGemmArgs);
+  if (!strcmp(name, "PtMlpArgs")) return (int)sizeof(PtMlpArgs);
   if (!strcmp(name, "PtGroupNormArgs")) return (int)sizeof(PtGroupNormArgs);
   if (!strcmp(name, "PtLayerNormArgs")) return (int)sizeof(PtLayerNormArgs);
   if (!strcmp(name, "PtAttnSpatialArgs")) return (int)sizeof(PtAttnSpatialArgs);

@@ -89,18 +89,26 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
   griddep_launch();
   griddep_wait();
 
+  // Producer and MMA-issue warps run with all 32 lanes; one elected lane issues the asynchronous instruction, whose
+  // operands then live in uniform registers (no per-instruction R2UR waterfall: see elect_one in common.cuh).
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, NQ * kTileBytes);
-      for (int g = 0; g < NQ; ++g) tma_load_3d(sQ + g * kTileBytes, &tmap_qkv, q_full, head * kHd, q0 + g * kQTile, img);
+    {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, NQ * kTileBytes);
+        for (int g = 0; g < NQ; ++g) tma_load_3d(sQ + g * kTileBytes, &tmap_qkv, q_full, head * kHd, q0 + g * kQTile, img);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1u);
         uint8_t* sK = sKV + (size_t)stage * 2 * kTileBytes;
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * kTileBytes);
-        tma_load_3d(sK, &tmap_qkv, &kv_full[stage], p.C + head * kHd, j * kKTile, img);
-        tma_load_3d(sK + kTileBytes, &tmap_qkv, &kv_full[stage], 2 * p.C + head * kHd, j * kKTile, img);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&kv_full[stage], 2 * kTileBytes);
+          tma_load_3d(sK, &tmap_qkv, &kv_full[stage], p.C + head * kHd, j * kKTile, img);
+          tma_load_3d(sK + kTileBytes, &tmap_qkv, &kv_full[stage], 2 * p.C + head * kHd, j * kKTile, img);
+        }
+        __syncwarp();
         if (++stage == kKvStages) {
           stage = 0;
           phase ^= 1u;
@@ -108,17 +116,21 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t tmem_u = uniform_u32(tmem_base);
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major: hd contiguous)
       auto issue_s = [&](int g, int stage) {
         const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ + g * kTileBytes));
         const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sKV + (size_t)stage * 2 * kTileBytes));
-        const uint32_t d = tmem_base + (uint32_t)g * 128u;
+        const uint32_t d = tmem_u + (uint32_t)g * 128u;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kHd / 16; ++k)
-          tc_mma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
-        tc_commit(&s_full[g]);
+          for (int k = 0; k < kHd / 16; ++k)
+            tc_mma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+          tc_commit(&s_full[g]);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
@@ -147,29 +159,34 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
           bool progressed = false;
 #pragma unroll
           for (int g = 0; g < NQ; ++g) {
-            if (((pend_s >> g) & 1u) && mbar_try_wait(&s_read[g], par)) {
+            // (the polls are made warp-uniform: every lane must take the same branch around elect_one)
+            if (((pend_s >> g) & 1u) && __all_sync(0xffffffffu, mbar_try_wait(&s_read[g], par))) {
               tc_fence_after();
               issue_s(g, stage_n);
               pend_s &= ~(1u << g);
               progressed = true;
             }
-            if (((pend_pv >> g) & 1u) && mbar_try_wait(&p_full[g], par)) {  // P_g(j) in smem, O_g rescaled
+            if (((pend_pv >> g) & 1u) && __all_sync(0xffffffffu, mbar_try_wait(&p_full[g], par))) {  // P_g(j) in smem, O_g rescaled
               tc_fence_after();
               const uint32_t sPg = smem_u32(sP + (size_t)g * 2 * kTileBytes);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kKTile / 16; ++k) {
-                const uint64_t pdesc = make_desc_kmajor_sw128(sPg + (uint32_t)(k >> 2) * kTileBytes) + (uint64_t)(2 * (k & 3));
-                tc_mma_bf16(tmem_base + 256u + (uint32_t)g * 64u, pdesc, vdesc + (uint64_t)(k * 128), idesc_o,
-                            (j | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < kKTile / 16; ++k) {
+                  const uint64_t pdesc = make_desc_kmajor_sw128(sPg + (uint32_t)(k >> 2) * kTileBytes) + (uint64_t)(2 * (k & 3));
+                  tc_mma_bf16(tmem_u + 256u + (uint32_t)g * 64u, pdesc, vdesc + (uint64_t)(k * 128), idesc_o,
+                              (j | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(&o_done[g]);
               }
-              tc_commit(&o_done[g]);
+              __syncwarp();
               pend_pv &= ~(1u << g);
               progressed = true;
             }
           }
           if (!progressed && ++spins > (1u << 26)) asm volatile("trap;");
         }
-        tc_commit(&kv_empty[stage]);
+        if (elect_one()) tc_commit(&kv_empty[stage]);
+        __syncwarp();
         stage = stage_n;
         if (++stage_n == kKvStages) {
           stage_n = 0;

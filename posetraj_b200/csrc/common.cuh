@@ -41,6 +41,27 @@ PT_DEVICE uint32_t lane_id() {
   return l;
 }
 
+// One lane of a CONVERGED warp (deterministic: the same lane for the same mask).  The producer / MMA-issue warps run
+// their loops with all 32 lanes and branch on this only around the asynchronous instruction itself: every operand of
+// the TMA / tcgen05 instruction is then computed in warp-uniform control flow and lives in uniform registers.  Inside
+// an `if (lane == 0)` region the same operands sit in vector registers and ptxas wraps EVERY UTMALDG / UTCHMMA in a
+// "waterfall" (ELECT + 5-7 R2UR.BROADCAST + loop branch), ~120 cycles per instruction — more than a 128 x 128 x 16
+// MMA takes to execute (profiles/r2b_mlp.md).
+PT_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// a value every lane holds identically, made provably warp-uniform for the compiler (uniform-register allocation)
+PT_DEVICE uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 PT_DEVICE float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -56,6 +77,21 @@ PT_DEVICE float rcp_approx(float x) {
 // x * sigmoid(x) with MUFU ex2 / rcp (relative error ~2e-7): the IEEE division of x / (1 + exp(-x)) costs ~10
 // instructions and the GroupNorm+SiLU pass is issue-bound with it (profiles/r1g_groupnorm.md)
 PT_DEVICE float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+
+// GEGLU gate  value * gelu_erf(g)  = value * g * Phi(g)  for the tensor-core epilogues (gemm.cu, mlp.cu), where it is
+// evaluated 128 x 64 times per hidden chunk and bounds the kernel (profiles/r1b, r2).  Phi(g) is evaluated as
+//     sigmoid(2 g (c0 + c1 s + c2 s^2)),  s = min(g^2, 81)
+// — the tanh-form with a quintic argument re-fitted to the EXACT erf GELU (tests/test_gate_approx_cpu.py: max
+// |g Phi~(g) - g Phi(g)| = 2.6e-5 over all g, 150x below the bf16 rounding of the result; the textbook tanh constants
+// give 4.7e-4).  8 FP32 + 2 MUFU per gate instead of 26 + 2 for the Abramowitz-Stegun 7.1.26 evaluation used before.
+// The constants carry the factor -2 log2(e) of the exponential.
+PT_DEVICE float geglu_gate_fast(float value, float g) {
+  const float s = fminf(g * g, 81.0f);
+  float poly = fmaf(-3.53110710e-04f * -2.885390081777927f, s, 3.70155061e-02f * -2.885390081777927f);
+  poly = fmaf(poly, s, 7.97496957e-01f * -2.885390081777927f);
+  const float e = ex2_approx(poly * g);          // exp(-2u)
+  return value * g * rcp_approx(1.0f + e);       // g * sigmoid(2u); e = +inf for very negative g gives exactly 0
+}
 
 // exact (erf) GELU, as diffusers' GEGLU uses F.gelu(gate) with approximate="none"
 PT_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -192,6 +228,24 @@ PT_DEVICE uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
 
 PT_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// Remote arrive WITHOUT the cluster-scope release: `mbarrier.arrive.release.cluster` above makes ptxas emit
+// MEMBAR.ALL.GPU + ERRBAR in front of the arrive (12 % of all stall samples of the fused feed-forward, whose gate warps
+// signal the leader CTA twice per hidden chunk: profiles/r2b_mlp.md).  What those signals order is either a finished
+// tcgen05.ld (tcgen05.fence::before_thread_sync) or shared-memory writes of the signalling CTA that its own tensor core
+// will read (fence.proxy.async.shared::cta), so the default CTA-scope release is enough — the form CUTLASS uses for
+// the accumulator-empty barriers of its 2-SM kernels.
+PT_DEVICE void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// Remote arrive with RELAXED semantics: for signals that order nothing but finished tcgen05.ld reads (already ordered
+// by tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  A releasing arrive has to wait for every earlier load of
+// the thread, and ptxas therefore sinks it below the code that consumes those loads — in the fused feed-forward that
+// delayed "accumulator drained" by the whole gate evaluation of the chunk (profiles/r2b_mlp.md).
+PT_DEVICE void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // TMA loads of a CTA pair: data lands in THIS CTA's smem, the transaction bytes are credited to an mbarrier that

@@ -103,21 +103,8 @@ PT_DEVICE uint4 pack8(const float* v) {
   return u;
 }
 
-// GEGLU gate: value * gelu(g) with the exact-erf GELU written as g * Phi(g), Phi from Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, far below bf16 output rounding): Phi(g) = h for g < 0 and 1 - h for g >= 0 with
-// h = 0.5 * t * P(t) * exp(-g^2 / 2), t = 1 / (1 + p |g| / sqrt 2).  2 MUFU + 12 FP32 ops per gate: the GEGLU epilogue
-// evaluates 128 x block_n/2 of these per tile and is issue-bound at K = 320 (profiles/r1b).
-PT_DEVICE float geglu_gate(float value, float g) {
-  const float t = rcp_approx(fmaf(fabsf(g), 0.3275911f * 0.70710678118654752440f, 1.0f));
-  const float e = ex2_approx(g * g * (-0.5f * 1.4426950408889634f));
-  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-  poly = fmaf(poly, t, 0.5f * 1.421413741f);
-  poly = fmaf(poly, t, 0.5f * -0.284496736f);
-  poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  const float h = poly * t * e;
-  const float phi = g >= 0.f ? 1.0f - h : h;
-  return value * g * phi;
-}
+// GEGLU gate: see geglu_gate_fast in common.cuh (value * g * Phi(g), Phi re-fitted to the exact erf GELU, 2.6e-5 abs).
+PT_DEVICE float geglu_gate(float value, float g) { return geglu_gate_fast(value, g); }
 
 // activation codes of PtGemmArgs.act_silu: 1 SiLU, 2 GELU (exact erf), 3 quick-GELU x*sigmoid(1.702 x)
 PT_DEVICE float apply_act(int act, float v) {
@@ -377,8 +364,8 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
   griddep_wait();
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (whole warp, one elected lane issues) ------------------------------
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = tile_first; t < num_tiles; t += tile_step) {
@@ -399,19 +386,24 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             if constexpr (kPair) {
               // both CTAs credit the LEADER's full barrier; the leader expects the bytes of the whole pair
               const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0u);
-              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * ((uint32_t)kABytes + b_half_bytes));
-              tma_load_3d_pair(sA, ta, bar, ak, arow, batch);
               // B rows of this CTA: the second half of the tile's N range for rank 1 (GEGLU: rank 0 = value rows,
               // rank 1 = gate rows, which is exactly the accumulator column order [value | gate])
               const int brow = kGeglu ? (cta_rank == 0 ? n0 : p.gate_row_offset + n0) : n0 + (int)cta_rank * half;
-              tma_load_2d_pair(sB, &tmap_b, bar, kcol, brow);
+              if (elect_one()) {
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * ((uint32_t)kABytes + b_half_bytes));
+                tma_load_3d_pair(sA, ta, bar, ak, arow, batch);
+                tma_load_2d_pair(sB, &tmap_b, bar, kcol, brow);
+              }
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kABytes + 2u * b_half_bytes);
-              tma_load_3d(sA, ta, &full_bar[stage], ak, arow, batch);
-              tma_load_2d(sB, &tmap_b, &full_bar[stage], kcol, n0);
-              tma_load_2d(sB + b_half_bytes, &tmap_b, &full_bar[stage], kcol,
-                          kGeglu ? p.gate_row_offset + n0 : n0 + half);
+              const int brow1 = kGeglu ? p.gate_row_offset + n0 : n0 + half;
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kABytes + 2u * b_half_bytes);
+                tma_load_3d(sA, ta, &full_bar[stage], ak, arow, batch);
+                tma_load_2d(sB, &tmap_b, &full_bar[stage], kcol, n0);
+                tma_load_2d(sB + b_half_bytes, &tmap_b, &full_bar[stage], kcol, brow1);
+              }
             }
+            __syncwarp();
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -421,8 +413,9 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------ MMA issuer (whole warp of the leader CTA, one elected lane issues) ----------
+    if (cta_rank == 0) {
+      const uint32_t tmem_u = uniform_u32(tmem_base);
       const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)p.block_n, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -432,32 +425,38 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t d_tmem = tmem_u + (uint32_t)acc * 256u;
         for (int ki = 0; ki < k_iters; ++ki) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sA = smem_u32(tiles + (size_t)stage * p.stage_bytes);
           const uint64_t adesc = make_desc_kmajor_sw128(sA);
           const uint64_t bdesc = make_desc_kmajor_sw128(sA + kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-            if constexpr (kPair)
-              tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
-            else
-              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+              if constexpr (kPair)
+                tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
+              else
+                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if constexpr (kPair) tc_commit_pair(&empty_bar[stage], 3);
+            else tc_commit(&empty_bar[stage]);
           }
-          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if constexpr (kPair) tc_commit_pair(&empty_bar[stage], 3);
-          else tc_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if constexpr (kPair) tc_commit_pair(&tfull_bar[acc], 3);
-        else tc_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if constexpr (kPair) tc_commit_pair(&tfull_bar[acc], 3);
+          else tc_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -43,23 +43,32 @@ struct MlpParams {
   int res_ld;
   bf16* out;
   int out_ld;
+  long long* trace;  // debug: clock64 stamps of CTA 0 (tools/mlp_trace.py); nullptr in production
 };
 
 struct alignas(64) MlpTmap {
   uint64_t opaque[16];
 };
 
-// value * gelu_erf(gate): the same Abramowitz-Stegun 7.1.26 evaluation as the GEGLU epilogue of gemm.cu
-PT_DEVICE float mlp_gate(float value, float g) {
-  const float t = rcp_approx(fmaf(fabsf(g), 0.3275911f * 0.70710678118654752440f, 1.0f));
-  const float e = ex2_approx(g * g * (-0.5f * 1.4426950408889634f));
-  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-  poly = fmaf(poly, t, 0.5f * 1.421413741f);
-  poly = fmaf(poly, t, 0.5f * -0.284496736f);
-  poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  const float h = poly * t * e;
-  const float phi = g >= 0.f ? 1.0f - h : h;
-  return value * g * phi;
+PT_DEVICE float mlp_gate(float value, float g) { return geglu_gate_fast(value, g); }
+
+// debug trace: slot = event id, up to 64 chunks per role
+PT_DEVICE void mlp_stamp(long long* trace, int role, int ev, uint32_t chunk) {
+  if (trace != nullptr && blockIdx.x == 0 && chunk < 64u && (threadIdx.x & 31) == 0) trace[(role * 8 + ev) * 64 + chunk] = clock64();
+}
+
+PT_DEVICE void unpack8(uint4 u, float* f) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+PT_DEVICE uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  return u;
 }
 
 __global__ void __launch_bounds__(kMlpThreads, 1)
@@ -83,6 +92,7 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
   uint64_t* acc2_full = p_empty + 2;                     // both: last GEMM2 of the tile retired
   uint64_t* acc2_empty = acc2_full + 1;                  // leader: 16 warps finished reading acc2
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+  volatile uint32_t* zero_word = reinterpret_cast<volatile uint32_t*>(smem + 512);  // always 0 (see the gate warps)
   uint8_t* sX = smem + kMlpCtl;
   uint8_t* sP = sX + (size_t)p.k_chunks * kMlpXChunkBytes;
   uint8_t* sW1 = sP + 2 * kMlpPBytes;
@@ -118,6 +128,7 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
     }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 16);
+    *zero_word = 0u;
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_ptr, kMlpTmemCols);
@@ -130,8 +141,8 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
   griddep_wait();
 
   if (warp == 0) {
-    // ------------------------------ TMA: X tile + W1 ring ------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA: X tile + W1 ring (whole warp, one elected lane issues) -----------------
+    {
       int slot = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -139,17 +150,23 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
         const int r0 = t * 256 + (int)cta_rank * 128;
         mbar_wait(x_empty, ((uint32_t)it & 1u) ^ 1u);
         const uint32_t xbar = map_to_cta(smem_u32(x_full), 0u);
-        if (cta_rank == 0) mbar_arrive_expect_tx(x_full, 2u * (uint32_t)p.k_chunks * kMlpXChunkBytes);
-        for (int kc = 0; kc < p.k_chunks; ++kc)
-          tma_load_2d_pair(sX + (size_t)kc * kMlpXChunkBytes, &tmap_x, xbar, kc * 64, r0);
+        if (elect_one()) {
+          if (cta_rank == 0) mbar_arrive_expect_tx(x_full, 2u * (uint32_t)p.k_chunks * kMlpXChunkBytes);
+          for (int kc = 0; kc < p.k_chunks; ++kc)
+            tma_load_2d_pair(sX + (size_t)kc * kMlpXChunkBytes, &tmap_x, xbar, kc * 64, r0);
+        }
+        __syncwarp();
         for (int j = 0; j < p.n_chunks; ++j) {
           // accumulator columns [value 64 | gate 64]: rank 0 stages the value rows, rank 1 the gate rows
           const int wrow = (cta_rank == 0 ? 0 : p.hidden) + j * 64;
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(&w1_empty[slot], phase ^ 1u);
             const uint32_t bar = map_to_cta(smem_u32(&w1_full[slot]), 0u);
-            if (cta_rank == 0) mbar_arrive_expect_tx(&w1_full[slot], 2u * kMlpW1SlotBytes);
-            tma_load_2d_pair(sW1 + (size_t)slot * kMlpW1SlotBytes, &tmap_w1, bar, kc * 64, wrow);
+            if (elect_one()) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&w1_full[slot], 2u * kMlpW1SlotBytes);
+              tma_load_2d_pair(sW1 + (size_t)slot * kMlpW1SlotBytes, &tmap_w1, bar, kc * 64, wrow);
+            }
+            __syncwarp();
             if (++slot == kMlpW1Slots) {
               slot = 0;
               phase ^= 1u;
@@ -159,19 +176,22 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
       }
     }
   } else if (warp == 2) {
-    // ------------------------------ TMA: W2 ring ---------------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA: W2 ring (whole warp, one elected lane issues) --------------------------
+    {
       int slot = 0;
       uint32_t phase = 0;
       for (int t = pair_first; t < p.num_tiles; t += pair_step) {
         for (int j = 0; j < p.n_chunks; ++j) {
           mbar_wait(&w2_empty[slot], phase ^ 1u);
           const uint32_t bar = map_to_cta(smem_u32(&w2_full[slot]), 0u);
-          if (cta_rank == 0) mbar_arrive_expect_tx(&w2_full[slot], 4u * w2_half_bytes);
           uint8_t* dst = sW2 + (size_t)slot * p.w2_slot_bytes;
-          // MMA a covers output columns [0, C/2): rank r supplies W2 rows [r*C/4, +C/4); MMA b the upper half
-          tma_load_2d_pair(dst, &tmap_w2, bar, j * 64, (int)cta_rank * quarter_rows);
-          tma_load_2d_pair(dst + w2_half_bytes, &tmap_w2, bar, j * 64, (p.C >> 1) + (int)cta_rank * quarter_rows);
+          if (elect_one()) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&w2_full[slot], 4u * w2_half_bytes);
+            // MMA a covers output columns [0, C/2): rank r supplies W2 rows [r*C/4, +C/4); MMA b the upper half
+            tma_load_2d_pair(dst, &tmap_w2, bar, j * 64, (int)cta_rank * quarter_rows);
+            tma_load_2d_pair(dst + w2_half_bytes, &tmap_w2, bar, j * 64, (p.C >> 1) + (int)cta_rank * quarter_rows);
+          }
+          __syncwarp();
           if (++slot == p.w2_slots) {
             slot = 0;
             phase ^= 1u;
@@ -180,12 +200,12 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (leader CTA) ------------------------------
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------ MMA issuer (whole warp of the leader CTA, one elected lane issues) ----------
+    if (cta_rank == 0) {
       const uint32_t idesc1 = make_idesc_bf16(256, 128, 0, 0);
       const uint32_t idesc2 = make_idesc_bf16(256, (uint32_t)(p.C >> 1), 0, 0);
-      const uint32_t acc1 = tmem_base;
-      const uint32_t acc2a = tmem_base + kAcc2Col;
+      const uint32_t acc1 = uniform_u32(tmem_base);
+      const uint32_t acc2a = acc1 + kAcc2Col;
       const uint32_t acc2b = acc2a + (uint32_t)(p.C >> 1);
       int s1 = 0, s2 = 0;
       uint32_t ph1 = 0, ph2 = 0;
@@ -194,8 +214,11 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
       int it = 0;
       auto issue_gemm2 = [&](int jj) {
         const uint32_t b = g2 & 1u;
+        mlp_stamp(p.trace, 0, 3, g2);
         mbar_wait(&p_full[b], (g2 >> 1) & 1u);
+        mlp_stamp(p.trace, 0, 4, g2);
         mbar_wait(&w2_full[s2], ph2);
+        mlp_stamp(p.trace, 0, 5, g2);
         if (jj == 0) mbar_wait(acc2_empty, ((uint32_t)it & 1u) ^ 1u);   // the previous tile's output has been read
         tc_fence_after();
         const uint32_t sPb = smem_u32(sP + (size_t)b * kMlpPBytes);
@@ -203,14 +226,18 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
         const uint64_t pdesc = make_desc_kmajor_sw128(sPb);
         const uint64_t wa = make_desc_kmajor_sw128(sW);
         const uint64_t wb = make_desc_kmajor_sw128(sW + w2_half_bytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t accum = (jj | k) != 0 ? 1u : 0u;
-          tc_mma_bf16_pair(acc2a, pdesc + (uint64_t)(2 * k), wa + (uint64_t)(2 * k), idesc2, accum);
-          tc_mma_bf16_pair(acc2b, pdesc + (uint64_t)(2 * k), wb + (uint64_t)(2 * k), idesc2, accum);
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accum = (jj | k) != 0 ? 1u : 0u;
+            tc_mma_bf16_pair(acc2a, pdesc + (uint64_t)(2 * k), wa + (uint64_t)(2 * k), idesc2, accum);
+            tc_mma_bf16_pair(acc2b, pdesc + (uint64_t)(2 * k), wb + (uint64_t)(2 * k), idesc2, accum);
+          }
+          tc_commit_pair(&w2_empty[s2], 3);
+          tc_commit_pair(&p_empty[b], 3);
         }
-        tc_commit_pair(&w2_empty[s2], 3);
-        tc_commit_pair(&p_empty[b], 3);
+        __syncwarp();
+        mlp_stamp(p.trace, 0, 6, g2);
         if (++s2 == p.w2_slots) {
           s2 = 0;
           ph2 ^= 1u;
@@ -220,29 +247,39 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
       for (int t = pair_first; t < p.num_tiles; t += pair_step, ++it) {
         mbar_wait(x_full, (uint32_t)it & 1u);
         for (int j = 0; j < p.n_chunks; ++j) {
+          mlp_stamp(p.trace, 0, 0, g1);
           mbar_wait(acc1_empty, (g1 & 1u) ^ 1u);   // the gate warps hold acc1 of the previous chunk in registers
           tc_fence_after();
+          mlp_stamp(p.trace, 0, 1, g1);
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(&w1_full[s1], ph1);
             tc_fence_after();
             const uint64_t adesc = make_desc_kmajor_sw128(smem_u32(sX + (size_t)kc * kMlpXChunkBytes));
             const uint64_t bdesc = make_desc_kmajor_sw128(smem_u32(sW1 + (size_t)s1 * kMlpW1SlotBytes));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_bf16_pair(acc1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kc | k) != 0 ? 1u : 0u);
-            tc_commit_pair(&w1_empty[s1], 3);
+              for (int k = 0; k < 4; ++k)
+                tc_mma_bf16_pair(acc1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kc | k) != 0 ? 1u : 0u);
+              tc_commit_pair(&w1_empty[s1], 3);
+            }
+            __syncwarp();
             if (++s1 == kMlpW1Slots) {
               s1 = 0;
               ph1 ^= 1u;
             }
           }
-          tc_commit_pair(acc1_full, 3);
+          if (elect_one()) {
+            tc_commit_pair(acc1_full, 3);
+            if (j == p.n_chunks - 1) tc_commit_pair(x_empty, 3);   // X may be overwritten once these retire
+          }
+          __syncwarp();
+          mlp_stamp(p.trace, 0, 2, g1);
           ++g1;
-          if (j == p.n_chunks - 1) tc_commit_pair(x_empty, 3);   // X may be overwritten once these retire
           if (j > 0) issue_gemm2(j - 1);
         }
         issue_gemm2(p.n_chunks - 1);
-        tc_commit_pair(acc2_full, 3);
+        if (elect_one()) tc_commit_pair(acc2_full, 3);
+        __syncwarp();
       }
     }
   } else {
@@ -258,15 +295,27 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
     int it = 0;
     for (int t = pair_first; t < p.num_tiles; t += pair_step, ++it) {
       for (int j = 0; j < p.n_chunks; ++j, ++g) {
+        if (warp == 3 && lane == 0) mlp_stamp(p.trace, 1, 0, g);
         mbar_wait(acc1_full, g & 1u);
         tc_fence_after();
+        if (warp == 3 && lane == 0) mlp_stamp(p.trace, 1, 1, g);
         uint32_t v[32], gt[32];
         tmem_ld_32x32(t_lane + (uint32_t)(hsel * 32), v);
         tmem_ld_32x32(t_lane + 64u + (uint32_t)(hsel * 32), gt);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc1_empty_l);
+        if (lane == 0) mbar_arrive_remote_relaxed(acc1_empty_l);
+        if (warp == 3 && lane == 0) mlp_stamp(p.trace, 1, 2, g);
+        // The arrive has no result, so the instruction scheduler would sink it below the whole gate evaluation
+        // (measured: "accumulator drained" was signalled ~1.5k cycles late and GEMM1 of the next chunk waited for
+        // it).  A volatile shared-memory load issued after it in program order cannot pass it; folding the (always
+        // zero) word into a few gate inputs puts the load — and with it the arrive — on the critical path.
+        {
+          const uint32_t z = *zero_word;
+          v[0] ^= z; v[8] ^= z; v[16] ^= z; v[24] ^= z;
+          gt[0] ^= z; gt[8] ^= z; gt[16] ^= z; gt[24] ^= z;
+        }
         const int hcol = j * 64 + hsel * 32;
         const float4* bv = reinterpret_cast<const float4*>(p.bias1 + hcol);
         const float4* bg = reinterpret_cast<const float4*>(p.bias1 + p.hidden + hcol);
@@ -280,7 +329,9 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
                                          mlp_gate(__uint_as_float(v[i + 3]) + x.w, __uint_as_float(gt[i + 3]) + y.w));
         }
         const uint32_t b = g & 1u;
+        if (warp == 3 && lane == 0) mlp_stamp(p.trace, 1, 3, g);
         mbar_wait(&p_empty[b], ((g >> 1) & 1u) ^ 1u);   // the GEMM2 that read this P buffer two chunks ago retired
+        if (warp == 3 && lane == 0) mlp_stamp(p.trace, 1, 4, g);
         uint8_t* prow = sP + (size_t)b * kMlpPBytes + (size_t)row * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -290,58 +341,75 @@ mlp_geglu_kernel(const __grid_constant__ MlpTmap tmap_x, const __grid_constant__
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(p_full_l + b * 8u);
+        if (lane == 0) mbar_arrive_remote(p_full_l + b * 8u);
+        if (warp == 3 && lane == 0) mlp_stamp(p.trace, 1, 5, g);
       }
-      // ---- output of the tile: acc2 -> bias, scale, residuals -> bf16 -> global (one row per thread) ----
+      // ---- output of the tile: acc2 -> bias, scale, residuals -> bf16 -> global.  tcgen05.ld hands every thread one
+      // ROW; each warp transposes its 32 x 32 chunk through an XOR-swizzled fp32 tile (the two P buffers are idle now:
+      // 8 warps x 4 KB) so that a lane owns 8 consecutive columns of 4 rows and 4 neighbouring lanes cover 64
+      // contiguous bytes of a row: residual loads and output stores are coalesced row segments (as in gemm.cu) ----
       mbar_wait(acc2_full, (uint32_t)it & 1u);
       tc_fence_after();
-      const int grow = t * 256 + (int)cta_rank * 128 + row;
-      const bool valid = grow < p.rows;
+      const int sub_row = lane >> 2;
+      const int seg = lane & 3;
+      const uint32_t stage_u32 = smem_u32(sP + (size_t)(warp - 3) * 4096);
+      const int row0 = t * 256 + (int)cta_rank * 128 + q * 32;
       const int half_cols = p.C >> 1;
       const int nch = half_cols >> 5;
       for (int c = 0; c < nch; ++c) {
-        const int col = hsel * half_cols + c * 32;
+        const int col = hsel * half_cols + c * 32 + seg * 8;
         uint32_t a[32];
-        tmem_ld_32x32(t_lane + kAcc2Col + (uint32_t)col, a);
+        tmem_ld_32x32(t_lane + kAcc2Col + (uint32_t)(hsel * half_cols + c * 32), a);
         uint4 r1[4], r2[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          r1[s] = (valid && p.res1 != nullptr) ? ldg_nc_u4(p.res1 + (size_t)grow * p.res_ld + col + s * 8) : make_uint4(0, 0, 0, 0);
-          r2[s] = (valid && p.res2 != nullptr) ? ldg_nc_u4(p.res2 + (size_t)grow * p.res_ld + col + s * 8) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 4; ++i) {
+          const int gr = row0 + i * 8 + sub_row;
+          const bool ok = gr < p.rows;
+          r1[i] = (ok && p.res1 != nullptr) ? ldg_nc_u4(p.res1 + (size_t)gr * p.res_ld + col) : make_uint4(0, 0, 0, 0);
+          r2[i] = (ok && p.res2 != nullptr) ? ldg_nc_u4(p.res2 + (size_t)gr * p.res_ld + col) : make_uint4(0, 0, 0, 0);
         }
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + col) + 1);
         tmem_wait_ld();
         if (c == nch - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(acc2_empty_l);
+          if (lane == 0) mbar_arrive_remote_relaxed(acc2_empty_l);
         }
-        if (valid) {
+        __syncwarp();  // the previous chunk's transposed reads are done
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + col + s * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + col + s * 8) + 1);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            const float2 ra = unpack_bf16x2(r1[s].x), rb = unpack_bf16x2(r1[s].y), rc = unpack_bf16x2(r1[s].z), rd = unpack_bf16x2(r1[s].w);
-            const float2 sa = unpack_bf16x2(r2[s].x), sb = unpack_bf16x2(r2[s].y), sc = unpack_bf16x2(r2[s].z), sd = unpack_bf16x2(r2[s].w);
-            const float rr[8] = {ra.x, ra.y, rb.x, rb.y, rc.x, rc.y, rd.x, rd.y};
-            const float ss[8] = {sa.x, sa.y, sb.x, sb.y, sc.x, sc.y, sd.x, sd.y};
-            float f[8];
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint32_t addr = stage_u32 + (uint32_t)lane * 128u + (uint32_t)((jj ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a[4 * jj]), "r"(a[4 * jj + 1]),
+                       "r"(a[4 * jj + 2]), "r"(a[4 * jj + 3]) : "memory");
+        }
+        __syncwarp();
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float val = (__uint_as_float(a[s * 8 + e]) + bb[e]) * p.acc_scale;
-              val = fmaf(p.res1_scale, rr[e], val);
-              val = fmaf(p.res2_scale, ss[e], val);
-              f[e] = val;
-            }
-            uint4 u;
-            u.x = pack_bf16x2(f[0], f[1]);
-            u.y = pack_bf16x2(f[2], f[3]);
-            u.z = pack_bf16x2(f[4], f[5]);
-            u.w = pack_bf16x2(f[6], f[7]);
-            stg_u4(p.out + (size_t)grow * p.out_ld + col + s * 8, u);
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + sub_row;
+          const uint32_t a0 = stage_u32 + (uint32_t)rr * 128u + (uint32_t)(((2 * seg) ^ (rr & 7)) << 4);
+          const uint32_t a1 = stage_u32 + (uint32_t)rr * 128u + (uint32_t)(((2 * seg + 1) ^ (rr & 7)) << 4);
+          float f[8];
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a0));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(a1));
+          const int gr = row0 + rr;
+          if (gr >= p.rows) continue;
+          float x1[8], x2[8];
+          unpack8(r1[i], x1);
+          unpack8(r2[i], x2);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float val = (f[e] + bb[e]) * p.acc_scale;
+            val = fmaf(p.res1_scale, x1[e], val);
+            f[e] = fmaf(p.res2_scale, x2[e], val);
           }
+          stg_u4(p.out + (size_t)gr * p.out_ld + col, pack8(f));
         }
       }
+      // the staging tiles alias the P buffers: no warp may start the next tile's gate (which writes P) before every
+      // warp of this CTA has finished reading its transposed rows
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
 
@@ -388,6 +456,7 @@ extern "C" int pt_mlp_geglu(const PtMlpArgs* a, void* stream) {
   p.res_ld = a->res_ld;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.out_ld = a->out_ld;
+  p.trace = reinterpret_cast<long long*>(a->trace);
   const size_t smem_bytes = (size_t)fixed + (size_t)w2_slots * p.w2_slot_bytes + 1024;
   static bool attr_set[PT_MAX_DEVICES] = {false};
   const int dev_slot = pt_device_slot();

@@ -21,6 +21,7 @@ with these algebraic rewrites, each exact in real arithmetic:
 from __future__ import annotations
 
 import math
+import os
 from collections import defaultdict
 from typing import Dict, List, Optional
 
@@ -31,6 +32,8 @@ from .config import SVDConfig, residual_multipliers, up_block_plan
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+# experiment knob: PT_FUSED_MLP=0 keeps the GEGLU GEMM + output GEMM pair at every width (A/B runs)
+FUSED_MLP = os.environ.get("PT_FUSED_MLP", "1") != "0"
 
 
 def _pad64(c: int) -> int:
@@ -276,6 +279,26 @@ class NetPlan:
         self.step_ops.append(ops.Gemm(a0, wt, out, name=name, **kw))
         return out
 
+    def _ff(self, x, prefix: str, *, res1, res1_scale: float = 1.0, res2=None, res2_scale: float = 1.0,
+            acc_scale: float = 1.0, name: str) -> torch.Tensor:
+        """FeedForward (GEGLU proj -> Linear) + residual terms.  Widths whose output accumulator fits TMEM next to the
+        hidden one (C <= 320: level 0) run as ONE kernel (ops.FusedMlp) and never materialise the [rows, 4C] hidden
+        tensor; wider levels keep the GEGLU GEMM + output GEMM pair."""
+        w = self.w
+        Cc = x.shape[1]
+        w1, b1 = w.linear(prefix + "net.0.proj.weight"), w.f32(prefix + "net.0.proj.bias")
+        w2, b2 = w.linear(prefix + "net.2.weight"), w.f32(prefix + "net.2.bias")
+        if FUSED_MLP and ops.FusedMlp.supported(Cc) and w2.shape == (Cc, 4 * Cc):
+            out = self.pool.get(x.shape[0], Cc)
+            self.step_ops.append(ops.FusedMlp(x, w1, b1, w2, b2, out, acc_scale=acc_scale, res1=res1, res1_scale=res1_scale,
+                                              res2=res2, res2_scale=res2_scale, name=name + ".mlp"))
+            return out
+        f1 = self._gemm(x, w1, 4 * Cc, geglu=True, bias=b1, name=name + ".geglu")
+        out = self._gemm(f1, w2, Cc, bias=b2, acc_scale=acc_scale, res1=res1, res1_scale=res1_scale, res2=res2,
+                         res2_scale=res2_scale, name=name + ".out")
+        self.pool.put(f1)
+        return out
+
     # ================================================================================================
     # blocks
     # ================================================================================================
@@ -385,20 +408,13 @@ class NetPlan:
                         rowvec=xvec_s, rowvec_mode=1, rv=(Fr * HW, 1, 1), name=sb + "attn1.to_out")
         self.pool.put(att, h)
         l3 = self._ln(h2, sb + "norm3")
-        f1 = self._gemm(l3, w.linear(sb + "ff.net.0.proj.weight"), 4 * Cc, geglu=True, bias=w.f32(sb + "ff.net.0.proj.bias"),
-                        name=sb + "ff.geglu")
-        self.pool.put(l3)
-        h3 = self._gemm(f1, w.linear(sb + "ff.net.2.weight"), Cc, bias=w.f32(sb + "ff.net.2.bias"), res1=h2, name=sb + "ff.out")
-        self.pool.put(f1, h2)
+        h3 = self._ff(l3, sb + "ff.", res1=h2, name=sb + "ff")
+        self.pool.put(l3, h2)
         # --- TemporalBasicTransformerBlock on (h3 + frame position embedding)
         ht = self.pool.get(x.shape[0], Cc)
         l_in = self._ln(h3, tb + "norm_in", addvec=pos, hw=HW, frames=Fr, sum_out=ht)
-        fi = self._gemm(l_in, w.linear(tb + "ff_in.net.0.proj.weight"), 4 * Cc, geglu=True,
-                        bias=w.f32(tb + "ff_in.net.0.proj.bias"), name=tb + "ff_in.geglu")
-        self.pool.put(l_in)
-        t1 = self._gemm(fi, w.linear(tb + "ff_in.net.2.weight"), Cc, bias=w.f32(tb + "ff_in.net.2.bias"), res1=ht,
-                        name=tb + "ff_in.out")
-        self.pool.put(fi, ht)
+        t1 = self._ff(l_in, tb + "ff_in.", res1=ht, name=tb + "ff_in")
+        self.pool.put(l_in, ht)
         l1t = self._ln(t1, tb + "norm1")
         qkv_t = self._gemm(l1t, w.qkv(tb + "attn1."), 3 * Cc, name=tb + "attn1.qkv")
         self.pool.put(l1t)
@@ -409,14 +425,11 @@ class NetPlan:
                         rowvec=xvec_t, rowvec_mode=2, rv=rv_t, name=tb + "attn1.to_out")
         self.pool.put(att_t, t1)
         l3t = self._ln(t2, tb + "norm3")
-        f2 = self._gemm(l3t, w.linear(tb + "ff.net.0.proj.weight"), 4 * Cc, geglu=True, bias=w.f32(tb + "ff.net.0.proj.bias"),
-                        name=tb + "ff.geglu")
-        self.pool.put(l3t)
         alpha = w.alpha(prefix + "time_mixer.mix_factor")
         # blend: alpha*h3 + (1-alpha)*(ff(.) + t2)
-        hb = self._gemm(f2, w.linear(tb + "ff.net.2.weight"), Cc, bias=w.f32(tb + "ff.net.2.bias"), acc_scale=1.0 - alpha,
-                        res1=t2, res1_scale=1.0 - alpha, res2=h3, res2_scale=alpha, name=tb + "ff.out+mix")
-        self.pool.put(f2, t2, h3)
+        hb = self._ff(l3t, tb + "ff.", acc_scale=1.0 - alpha, res1=t2, res1_scale=1.0 - alpha, res2=h3, res2_scale=alpha,
+                      name=tb + "ff+mix")
+        self.pool.put(l3t, t2, h3)
         out = self._gemm(hb, w.linear(prefix + "proj_out.weight"), Cc, bias=w.f32(prefix + "proj_out.bias"), res1=x,
                          out2=out2, aux=aux, aux_scale=aux_scale, name=prefix + "proj_out")
         self.pool.put(hb)

@@ -257,6 +257,56 @@ class Gemm:
         _lib.check(_lib.lib().pt_gemm(self._argp, stream_ptr), self.name)
 
 
+class FusedMlp:
+    """out = acc_scale * (GEGLU(x W1^T + b1) W2^T + b2) + res1_scale*res1 + res2_scale*res2 in one kernel (PtMlpArgs)."""
+
+    @staticmethod
+    def supported(C: int) -> bool:
+        return C % 64 == 0 and 64 <= C <= 320
+
+    def __init__(self, x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                 out: torch.Tensor, *, acc_scale: float = 1.0, res1: Optional[torch.Tensor] = None, res1_scale: float = 1.0,
+                 res2: Optional[torch.Tensor] = None, res2_scale: float = 1.0, name: str = "mlp",
+                 trace: Optional[torch.Tensor] = None):
+        rows, Cc = x.shape
+        hidden = w2.shape[1]
+        assert x.dtype == w1.dtype == w2.dtype == out.dtype == torch.bfloat16
+        assert x.stride(1) == 1 and w1.is_contiguous() and w2.is_contiguous() and out.stride(1) == 1
+        assert w1.shape == (2 * hidden, Cc) and w2.shape == (Cc, hidden) and hidden == 4 * Cc and self.supported(Cc)
+        assert b1.dtype == torch.float32 and b1.numel() == 2 * hidden and b2.dtype == torch.float32 and b2.numel() == Cc
+        assert out.shape == (rows, Cc)
+        self.name = name
+        self.tm_x = _lib.encode_tensormap(x.data_ptr(), [Cc, rows], [x.stride(0) * 2], [64, 128])
+        self.tm_w1 = _lib.encode_tensormap(w1.data_ptr(), [Cc, 2 * hidden], [w1.stride(0) * 2], [64, 64])
+        self.tm_w2 = _lib.encode_tensormap(w2.data_ptr(), [hidden, Cc], [w2.stride(0) * 2], [64, Cc // 4])
+        a = _lib.PtMlpArgs()
+        a.tmap_x, a.tmap_w1, a.tmap_w2 = C.addressof(self.tm_x), C.addressof(self.tm_w1), C.addressof(self.tm_w2)
+        a.rows, a.C, a.hidden = rows, Cc, hidden
+        a.bias1, a.bias2 = b1.data_ptr(), b2.data_ptr()
+        a.acc_scale = acc_scale
+        for r in (res1, res2):
+            if r is not None:
+                assert r.dtype == torch.bfloat16 and r.stride(1) == 1 and r.shape == (rows, Cc)
+        if res1 is not None and res2 is not None:
+            assert res1.stride(0) == res2.stride(0)
+        a.res1, a.res2 = _ptr(res1), _ptr(res2)
+        a.res1_scale, a.res2_scale = res1_scale, res2_scale
+        a.res_ld = res1.stride(0) if res1 is not None else (res2.stride(0) if res2 is not None else 0)
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        if trace is not None:
+            assert trace.dtype == torch.int64 and trace.numel() >= 2 * 8 * 64
+            a.trace = trace.data_ptr()
+        self.kind = "gemm"     # a dense contraction: counted with the GEMM class in bench.py's roofline
+        self.alg_flops = 2.0 * rows * Cc * (2 * hidden) + 2.0 * rows * hidden * Cc
+        self.alg_bytes = 0.0
+        self.args = a
+        self._keep = (x, w1, b1, w2, b2, out, res1, res2)
+        self._argp = C.addressof(a)
+
+    def launch(self, stream_ptr: int) -> None:
+        _lib.check(_lib.lib().pt_mlp_geglu(self._argp, stream_ptr), self.name)
+
+
 def conv3x3_taps(w_img: int) -> list[int]:
     """Row shifts of the 9 taps (ky, kx row-major) in the zero-haloed image space of width w_img + 1."""
     return [dy * (w_img + 1) + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)]

@@ -186,3 +186,54 @@ def test_bad_args_raise(cuda_dev):
     out = torch.empty(128, 64, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(ValueError):
         Gemm(a, w, out, block_n=48).launch(sp())
+
+
+@pytest.mark.parametrize("M,C", [(256, 64), (300, 64), (1000, 128), (777, 192), (5000, 256), (2880 * 3 + 17, 320), (80640, 320)])
+@pytest.mark.parametrize("mix", [False, True])
+def test_fused_geglu_mlp(cuda_dev, M, C, mix):
+    """ops.FusedMlp (one kernel, hidden activations stay on the SM) against torch fp32 of diffusers' FeedForward:
+    net.0 = GEGLU(proj), net.2 = Linear, plus the residual / AlphaBlender terms the engine folds into it.  The hidden
+    activations are rounded to bf16 before the second contraction exactly as in the two-kernel path, so the bound is
+    the same 4e-3."""
+    from posetraj_b200.ops import FusedMlp
+    torch.manual_seed(2)
+    H = 4 * C
+    x = rnd(M, C)
+    w1 = rnd(2 * H, C, scale=1 / math.sqrt(C))
+    b1 = torch.randn(2 * H, device="cuda") * 0.1
+    w2 = rnd(C, H, scale=1 / math.sqrt(H))
+    b2 = torch.randn(C, device="cuda") * 0.1
+    res1 = rnd(M, C)
+    res2 = rnd(M, C) if mix else None
+    kw = dict(acc_scale=0.4, res1_scale=0.4, res2_scale=0.6) if mix else {}
+    out = torch.zeros(M, C, device="cuda", dtype=torch.bfloat16)
+    FusedMlp(x, w1, b1, w2, b2, out, res1=res1, res2=res2, name="test.mlp", **kw).launch(sp())
+    torch.cuda.synchronize()
+    h = x.float() @ w1.float().t() + b1
+    hid = (h[:, :H] * F.gelu(h[:, H:])).to(torch.bfloat16).float()
+    ref = hid @ w2.float().t() + b2
+    if mix:
+        ref = 0.4 * ref + 0.4 * res1.float() + 0.6 * res2.float()
+    else:
+        ref = ref + res1.float()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < TOL, rel_l2(out, ref)
+
+
+def test_fused_mlp_matches_the_two_kernel_path(cuda_dev):
+    """Same operands through pt_gemm(geglu) + pt_gemm(out): the two lowerings of one feed-forward agree to bf16 rounding."""
+    from posetraj_b200.ops import FusedMlp, Gemm
+    torch.manual_seed(3)
+    M, C = 2880 * 2, 320
+    H = 4 * C
+    x, w1, w2 = rnd(M, C), rnd(2 * H, C, scale=1 / math.sqrt(C)), rnd(C, H, scale=1 / math.sqrt(H))
+    b1, b2 = torch.randn(2 * H, device="cuda") * 0.1, torch.randn(C, device="cuda") * 0.1
+    res = rnd(M, C)
+    a = torch.zeros(M, C, device="cuda", dtype=torch.bfloat16)
+    FusedMlp(x, w1, b1, w2, b2, a, res1=res).launch(sp())
+    hid = torch.empty(M, H, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(M, C, device="cuda", dtype=torch.bfloat16)
+    Gemm(x, w1, hid, geglu=True, bias=b1).launch(sp())
+    Gemm(hid, w2, b, bias=b2, res1=res).launch(sp())
+    torch.cuda.synchronize()
+    assert rel_l2(a, b) < TOL
