@@ -31,41 +31,44 @@ def _stream_ptr(stream=None) -> int:
 
 # ---------------------------------------------------------------------------------------------------------------
 # Tile configuration: (cta_pair, block_n) per GEMM shape.
-#   1. shapes of the configs[1] denoise step measured on B200 by tools/gemm_sweep.py (gpurun_out/r16_sweep.log);
-#   2. otherwise the argmin of a per-tile cost model fitted to that sweep (8.6 % rms log error, picks within 4 % of
-#      the measured optimum on 24 of 26 shapes): time = max tiles per CTA(-pair) x (k_iters x k-step + epilogue).
+#   1. shapes of the configs[1] denoise step measured on B200 by tools/gemm_sweep.py (round 2, after the warp-uniform
+#      issue loops: gpurun_out/r2f_sweep.log, copied to profiles/r2c_gemm_sweep.txt).  The CTA pair now wins every 3x3
+#      conv and most K >= 640 layers; in round 1 the ~120-cycle issue waterfall per MMA had hidden that.
+#   2. otherwise the argmin of a per-tile cost model fitted to that sweep by tools/fit_cost_model.py (11 % rms log
+#      error; its pick is within 2.1 % of the measured optimum on average, 13 % at worst):
+#      time = launch + max tiles per CTA(-pair) x (k_iters x k-step + epilogue).
 # ---------------------------------------------------------------------------------------------------------------
 TUNED = {
     # (rows, n_out, K per tap, taps, geglu): (cta_pair, block_n)
-    (80640, 320, 320, 1, 0): (False, 128),    # 59.4 us
-    (80640, 960, 320, 1, 0): (False, 160),    # 77.8 us
-    (80640, 1280, 320, 1, 1): (False, 256),   # 168.9 us
-    (80640, 320, 1280, 1, 0): (False, 160),   # 86.0 us
-    (20160, 640, 640, 1, 0): (False, 128),    # 36.9 us
-    (20160, 1920, 640, 1, 0): (False, 192),   # 55.3 us
-    (20160, 2560, 640, 1, 1): (True, 256),    # 118.8 us
-    (20160, 640, 2560, 1, 0): (True, 224),    # 73.7 us
-    (5040, 1280, 1280, 1, 0): (False, 192),   # 28.7 us
-    (5040, 3840, 1280, 1, 0): (False, 224),   # 49.2 us
-    (5040, 5120, 1280, 1, 1): (True, 256),    # 102.4 us
-    (5040, 1280, 5120, 1, 0): (True, 192),    # 69.6 us
-    (1260, 1280, 1280, 1, 0): (False, 128),   # 18.4 us
-    (1260, 5120, 1280, 1, 1): (True, 256),    # 36.9 us
-    (1260, 1280, 5120, 1, 0): (False, 128),   # 36.9 us
-    (83804, 320, 320, 9, 0): (False, 160),    # 147.5 us
-    (21756, 640, 640, 9, 0): (True, 224),     # 132.1 us
-    (5852, 1280, 1280, 9, 0): (True, 256),    # 131.0 us
-    (1680, 1280, 1280, 9, 0): (False, 160),   # 67.7 us
-    (83804, 320, 640, 9, 0): (False, 160),    # 274.4 us
-    (21756, 640, 1280, 9, 0): (True, 224),    # 256.0 us
-    (5852, 1280, 2560, 9, 0): (True, 224),    # 251.9 us
-    (80640, 320, 320, 3, 0): (False, 160),    # 69.7 us
-    (20160, 640, 640, 3, 0): (False, 224),    # 59.4 us
-    (5040, 1280, 1280, 3, 0): (False, 192),   # 55.3 us
-    (1260, 1280, 1280, 3, 0): (False, 96),    # 30.7 us
+    (80640, 320, 320, 1, 0): (False, 160),    # 56.3 us
+    (80640, 960, 320, 1, 0): (False, 192),    # 74.8 us
+    (80640, 1280, 320, 1, 1): (False, 256),   # 146.4 us
+    (80640, 320, 1280, 1, 0): (False, 160),   # 78.8 us
+    (20160, 640, 640, 1, 0): (False, 128),    # 35.8 us
+    (20160, 1920, 640, 1, 0): (True, 224),    # 54.3 us
+    (20160, 2560, 640, 1, 1): (True, 256),    # 97.2 us
+    (20160, 640, 2560, 1, 0): (True, 160),    # 64.5 us
+    (5040, 1280, 1280, 1, 0): (False, 128),   # 27.6 us
+    (5040, 3840, 1280, 1, 0): (True, 224),    # 41.9 us
+    (5040, 5120, 1280, 1, 1): (True, 256),    # 85.0 us
+    (5040, 1280, 5120, 1, 0): (True, 192),    # 58.4 us
+    (1260, 1280, 1280, 1, 0): (False, 96),    # 15.4 us
+    (1260, 5120, 1280, 1, 1): (True, 192),    # 33.8 us
+    (1260, 1280, 5120, 1, 0): (True, 96),     # 27.6 us
+    (83804, 320, 320, 9, 0): (True, 160),     # 101.4 us  (1 466 TFLOP/s)
+    (21756, 640, 640, 9, 0): (True, 160),     # 103.4 us
+    (5852, 1280, 1280, 9, 0): (True, 224),    # 113.7 us
+    (1680, 1280, 1280, 9, 0): (True, 128),    # 46.1 us
+    (83804, 320, 640, 9, 0): (True, 160),     # 193.5 us
+    (21756, 640, 1280, 9, 0): (True, 160),    # 209.5 us
+    (5852, 1280, 2560, 9, 0): (True, 224),    # 222.3 us
+    (80640, 320, 320, 3, 0): (False, 160),    # 68.5 us
+    (20160, 640, 640, 3, 0): (True, 224),     # 54.2 us
+    (5040, 1280, 1280, 3, 0): (True, 192),    # 46.1 us
+    (1260, 1280, 1280, 3, 0): (False, 128),   # 25.6 us
 }
 
-_C_MMA, _C_FLOOR, _C_B, _C_E0, _C_E1, _C_FLOOR_P, _C_B_P = 0.893, 265.8, 0.2507, -315.3, 11.73, 305.1, 0.0097
+_C_MMA, _C_FLOOR, _C_B, _C_E0, _C_E1, _C_FLOOR_P, _C_B_P, _C_LAUNCH = 1.1392, 108.64, 0.785, 199.11, 9.5858, 139.68, 0.352, 12877.0
 
 
 def tile_cost_ns(rows: int, batches: int, n_out: int, k_iters: int, geglu: bool, has_res: bool, pair: bool, bn: int) -> float:
@@ -76,8 +79,8 @@ def tile_cost_ns(rows: int, batches: int, n_out: int, k_iters: int, geglu: bool,
     units = NUM_SMS // 2 if pair else NUM_SMS
     t_max = math.ceil(m_tiles * n_tiles / units)
     kstep = max(bn * _C_MMA, (_C_FLOOR_P + _C_B_P * bn) if pair else (_C_FLOOR + _C_B * bn))
-    epi = _C_E0 + _C_E1 * per * (2.0 if geglu else 1.0) * (1.3 if has_res else 1.0)
-    return t_max * (k_iters * kstep + epi)
+    epi = max(0.0, _C_E0 + _C_E1 * per * (2.0 if geglu else 1.0) * (1.3 if has_res else 1.0))
+    return _C_LAUNCH + t_max * (k_iters * kstep + epi)
 
 
 def pick_config(rows: int, batches: int, n_out: int, k_per_tap: int, taps: int, geglu: bool, has_res: bool,

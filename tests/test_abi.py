@@ -63,7 +63,10 @@ def test_product_package_never_touches_the_oracle():
             offenders.append(str(path.relative_to(ROOT)))
     assert offenders == []
     bench = (ROOT / "bench.py").read_text()
-    # bench.py: the oracle appears only inside the CPU-baseline function
-    head, _, tail = bench.partition("def cpu_oracle_steps_per_sec")
-    body, _, rest = tail.partition("\ndef ")
-    assert "oracle." not in head.replace("the oracle", "") and "from oracle" not in rest
+    # bench.py: the oracle is imported only inside the two BASELINE functions — the CPU baseline (also the --impl
+    # reference arm) and the torch-eager-bf16 "library bar" the round-1 verdict asked for — never on the product path
+    allowed = {"cpu_oracle_steps_per_sec", "library_baseline_leg"}
+    for chunk in re.split(r"\n(?=def )", bench):
+        name = re.match(r"def (\w+)", chunk)
+        if re.search(r"^\s*(from|import)\s+oracle\b", chunk, flags=re.M):
+            assert name is not None and name.group(1) in allowed, chunk[:80]
