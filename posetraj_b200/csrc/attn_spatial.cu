@@ -35,6 +35,11 @@ struct AttnParams {
   int out_ld;
 };
 
+template <bool B>
+struct FullTile {
+  static constexpr bool value = B;
+};
+
 struct alignas(64) AttnTmap {
   uint64_t opaque[16];
 };
@@ -262,35 +267,41 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
           tmem_wait_st();
         }
       }
-      // P = exp2((s - m_ref) * scale) as bf16 into the swizzled smem tile; row sum of what the MMA will multiply
+      // P = exp2((s - m_ref) * scale) as bf16 into the swizzled smem tile; row sum of what the MMA will multiply.
+      // Two instantiations: only the LAST key tile of a sequence can be partial, and the per-element masking
+      // (ISETP + FSEL) was a third of the instructions of this loop when it ran on every tile (profiles/r2d_attn.md).
       const float mb = m_ref * p.scale_log2;
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent row-sum chains
-      const bool full_tile = kvalid == kKTile;
+      auto exp_tile = [&](auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int k0 = c * 32 + i;
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[k0]), p.scale_log2, -mb));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[k0 + 1]), p.scale_log2, -mb));
-          if (!full_tile) {
-            if (k0 >= kvalid) p0 = 0.f;
-            if (k0 + 1 >= kvalid) p1 = 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            const int k0 = c * 32 + i;
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[k0]), p.scale_log2, -mb));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[k0 + 1]), p.scale_log2, -mb));
+            if constexpr (!kFull) {
+              if (k0 >= kvalid) p0 = 0.f;
+              if (k0 + 1 >= kvalid) p1 = 0.f;
+            }
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+            // row sum in fp32 of the un-rounded probabilities (the bf16 rounding of P is unbiased; re-deriving the
+            // rounded values costs 3 extra ALU ops per pair in a loop that is issue-bound)
+            ls4[(i >> 1) & 3] += p0 + p1;
           }
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-          // row sum in fp32 of the un-rounded probabilities (the bf16 rounding of P is unbiased; re-deriving the
-          // rounded values costs 3 extra ALU ops per pair in a loop that is issue-bound)
-          ls4[(i >> 1) & 3] += p0 + p1;
-        }
-        // keys [c*32, c*32+32) -> half (c >> 1), 16-byte chunks (c & 1)*4 .. +3 of this row, XOR-swizzled
-        uint8_t* prow = sPg + (size_t)(c >> 1) * kTileBytes + (size_t)row * 128;
+          // keys [c*32, c*32+32) -> half (c >> 1), 16-byte chunks (c & 1)*4 .. +3 of this row, XOR-swizzled
+          uint8_t* prow = sPg + (size_t)(c >> 1) * kTileBytes + (size_t)row * 128;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = ((c & 1) * 4 + ch) ^ (row & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+          for (int ch = 0; ch < 4; ++ch) {
+            const int chunk = ((c & 1) * 4 + ch) ^ (row & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+          }
         }
-      }
+      };
+      if (kvalid == kKTile) exp_tile(FullTile<true>{});
+      else exp_tile(FullTile<false>{});
       const float lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       l_run += lsum;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
