@@ -161,6 +161,8 @@ typedef struct PtGemmArgs {
   const float* acc_scale_ptr;
 } PtGemmArgs;
 int pt_gemm(const PtGemmArgs* a, void* stream);
+/* debug only: int64[8*64] device buffer receiving clock64 stamps of CTA 0 of later pt_gemm launches (NULL: off) */
+void pt_gemm_set_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Fused GEGLU feed-forward (diffusers FeedForward = GEGLU proj + Linear; BasicTransformerBlock.ff,           */

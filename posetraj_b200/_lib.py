@@ -174,6 +174,7 @@ _SIGNATURES = {
     "pt_step_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_gemm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_mlp_geglu": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_gemm_set_trace": (None, [C.c_void_p]),
     "pt_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_groupnorm_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "pt_layernorm": (C.c_int, [C.c_void_p, C.c_void_p]),

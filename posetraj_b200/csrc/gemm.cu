@@ -73,7 +73,12 @@ struct GemmParams {
   int sc_start[8], sc_count[8];
   bf16* sc_peer[8];
   int epi_depth;  // chunks of operand lookahead in the lean epilogue (1 or 2)
+  long long* trace;  // debug (pt_gemm_set_trace): clock64 stamps of CTA 0's epilogue warp 2 / MMA warp, or nullptr
 };
+
+PT_DEVICE void gemm_stamp(long long* trace, int ev, int it) {
+  if (trace != nullptr && blockIdx.x == 0 && it < 64 && (threadIdx.x & 31) == 0) trace[ev * 64 + it] = clock64();
+}
 
 struct alignas(64) TmapParam {
   uint64_t opaque[16];
@@ -423,8 +428,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
       for (int t = tile_first; t < num_tiles; t += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        gemm_stamp(p.trace, 0, it);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
+        gemm_stamp(p.trace, 1, it);
         const uint32_t d_tmem = tmem_u + (uint32_t)acc * 256u;
         for (int ki = 0; ki < k_iters; ++ki) {
           mbar_wait(&full_bar[stage], phase);
@@ -451,6 +458,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             phase ^= 1u;
           }
         }
+        gemm_stamp(p.trace, 2, it);
         // accumulator complete -> epilogue (of both CTAs)
         if (elect_one()) {
           if constexpr (kPair) tc_commit_pair(&tfull_bar[acc], 3);
@@ -544,8 +552,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
           }
         }
         R.vmask = vmask;
+        if (warp == 2) gemm_stamp(p.trace, 3, it);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
+        if (warp == 2) gemm_stamp(p.trace, 4, it);
         const uint32_t t_acc_f = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
         const int chunks_f = p.block_n >> 5;
         if (hsel >= chunks_f) {
@@ -556,6 +566,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
         constexpr int kBits = (kEpi - kEpiFast) & 7;
         epilogue_fast<(kBits & 1) != 0, (kBits & 2) != 0, (kBits & 4) != 0, kChunkStride>(
             p, R, t_acc_f, stage_u32, n_tile * p.block_n, chunks_f, hsel, lane, acc_scale, [&]() { arrive_tempty(acc); });
+        if (warp == 2) gemm_stamp(p.trace, 5, it);
         continue;
       }
 
@@ -750,6 +761,10 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
 
 using namespace pt;
 
+static long long* g_gemm_trace = nullptr;
+// debug hook (tools/gemm_trace.py): int64[8*64] device buffer receiving clock64 stamps of CTA 0, or NULL to switch off
+extern "C" void pt_gemm_set_trace(void* buf) { g_gemm_trace = reinterpret_cast<long long*>(buf); }
+
 extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
   if (a == nullptr || a->tmap_a0 == nullptr || a->tmap_b == nullptr || a->out == nullptr)
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: null argument");
@@ -874,6 +889,7 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     }
     p.epi_depth = env_depth > 0 ? env_depth : 1;
   }
+  p.trace = g_gemm_trace;
   p.scatter_mode = a->scatter_mode;
   p.sc_world = a->sc_world; p.sc_J = a->sc_J > 0 ? a->sc_J : 1; p.sc_S = a->sc_S > 0 ? a->sc_S : 1;
   p.sc_kept_off = a->sc_kept_off; p.sc_kept_total = a->sc_kept_total;
