@@ -447,6 +447,120 @@ typedef struct PtRasterArgs {
 int pt_rasterize_tracks(const PtRasterArgs* a, void* stream);
 int64_t pt_rasterize_workspace_bytes(int32_t F, int32_t H, int32_t W);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Training step of BASELINE configs[3]: backward / loss / optimizer kernels.             */
+/* Reference: scripts/train_svd_traj_VIPSeg_14_cam_concat.py:1404-1475 (autograd through ControlNet + frozen    */
+/* UNet, EDM-weighted MSE :1423-1436, AdamW :1472).  Formulas: oracle/backward.py (checked against autograd).   */
+/* dgrad of a linear / conv layer is pt_gemm itself with W^T and negated tap shifts.                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct PtEdmLossArgs {
+  const void* pred;          /* bf16 tokens [B*F*HW, pred_ld], C columns: the UNet's noise prediction */
+  int32_t pred_ld;
+  const float* noisy;        /* fp32, element (b, f, c, pix) at b*sample_stride + f*frame_stride + c*HW + pix */
+  const float* target;
+  int64_t sample_stride, frame_stride;
+  const float* sigmas;       /* [B] */
+  int32_t B, F, C, HW;
+  float weight;              /* 1 for the main loss, 0.5 for the spatial pass (:1462) */
+  void* dpred;               /* bf16 tokens [B*F*HW, dpred_ld] = weight * d loss / d pred, or NULL */
+  int32_t dpred_ld;
+  void* workspace;           /* pt_edm_loss_workspace_bytes() */
+  float* loss;               /* [1] */
+  int32_t accumulate;        /* loss += instead of = */
+} PtEdmLossArgs;
+int pt_edm_loss(const PtEdmLossArgs* a, void* stream);
+int64_t pt_edm_loss_workspace_bytes(void);
+
+typedef struct PtGroupNormBwdArgs {
+  const void* x0;            /* forward input, as PtGroupNormArgs */
+  const void* x1;
+  int32_t c0, c1, ld0, ld1;
+  const void* dout;          /* bf16 gradient of the forward output, in the forward output's layout (halo: (H+1)*(W+1) rows/image) */
+  int32_t dout_ld, halo, H, W;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int32_t silu, rows_per_stat, num_stat;
+  void* dx0;                 /* bf16 [rows, dld0] */
+  void* dx1;                 /* bf16 [rows, dld1] or NULL */
+  int32_t dld0, dld1;
+  void* workspace;           /* pt_groupnorm_bwd_workspace_bytes(num_stat, c0 + c1) */
+  float* dgb_out;            /* fp32 [2*(c0+c1)] = dgamma | dbeta, or NULL (frozen layer) */
+  int32_t accumulate_dgb;
+} PtGroupNormBwdArgs;
+int pt_groupnorm_bwd(const PtGroupNormBwdArgs* a, void* stream);
+int64_t pt_groupnorm_bwd_workspace_bytes(int32_t num_stat, int32_t channels);
+
+typedef struct PtLayerNormBwdArgs {
+  const void* x;             /* bf16 [rows, ld]: forward input */
+  int32_t ld;
+  const void* dout;
+  int32_t dout_ld;
+  const float* gamma;
+  float eps;
+  int32_t rows, C;
+  const float* addvec;       /* as PtLayerNormArgs (the forward normalised x + addvec[frame]) or NULL */
+  int32_t hw, F;
+  void* dx;                  /* bf16 [rows, dx_ld] */
+  int32_t dx_ld;
+  int32_t accumulate_dx;
+  float* partials;           /* fp32 [n_blocks][2*C] scratch, or NULL when dgamma / dbeta are not wanted */
+  int32_t n_blocks;          /* grid size (>= 1) */
+  float* dgb_out;            /* fp32 [2*C] = dgamma | dbeta, or NULL */
+  int32_t accumulate_dgb;
+} PtLayerNormBwdArgs;
+int pt_layernorm_bwd(const PtLayerNormBwdArgs* a, void* stream);
+
+/* GEGLU as a separate pass: h bf16 [rows, 2*hidden] (value | gate) -> out bf16 [rows, hidden]; backward -> dh */
+int pt_geglu_fwd(const void* h, int32_t ld, void* out, int32_t out_ld, int64_t rows, int32_t hidden, void* stream);
+int pt_geglu_bwd(const void* h, int32_t ld, const void* dout, int32_t dout_ld, void* dh, int32_t dh_ld, int64_t rows,
+                 int32_t hidden, void* stream);
+
+typedef struct PtColsumArgs {
+  const void* x;             /* bf16 [rows, ld] (halo: zero-haloed image rows, only real pixels are summed) */
+  int32_t ld, halo, H, W;
+  int64_t rows_per_group;    /* logical (un-haloed) rows per group */
+  int32_t groups, C;
+  float scale;
+  float* out;                /* fp32 [groups, C] */
+  int32_t accumulate;
+} PtColsumArgs;
+int pt_colsum(const PtColsumArgs* a, void* stream);
+/* out[i] (+)= scale * sum_b partials[b*n + i], b = 0..nb-1 in order */
+int pt_reduce_partials(const float* partials, int32_t nb, int64_t n, float scale, float* out, int32_t accumulate, void* stream);
+/* out[0] (+)= scale * sum a[r,c]*b[r,c]; workspace: 8 KiB */
+int pt_dot_bf16(const void* a, int32_t lda, const void* b, int32_t ldb, int64_t rows, int32_t cols, float scale, float* out,
+                int32_t accumulate, void* workspace, void* stream);
+/* bf16 [rows, cols] (row stride ld_in) -> [cols, rows] (row stride ld_out) */
+int pt_transpose_bf16(const void* in, int32_t ld_in, void* out, int32_t ld_out, int32_t rows, int32_t cols, void* stream);
+
+typedef struct PtAdamWArgs {
+  float* master;             /* fp32 parameters */
+  const float* grad;         /* fp32 gradients (after the data-parallel all-reduce) */
+  float* m;
+  float* v;
+  void* work;                /* optional bf16 copy the kernels read */
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, grad_scale;
+  int32_t step;              /* 1-based */
+} PtAdamWArgs;
+int pt_adamw(const PtAdamWArgs* a, void* stream);
+
+/* Weight gradient of a linear / implicit-GEMM conv layer (oracle/backward.py conv_rows_wgrad):                  */
+/*   dW[n, t*K + k] = sum_r dD[r, n] * A[r + shift_t, k]                                                         */
+/* tcgen05: A operand = dD^T (K-major over rows, from pt_transpose_bf16), B operand = the layer's input rows as an */
+/* MN-major tile (tap = row shift of the TMA coordinate, out-of-range rows zero-filled like the forward).  Rows are */
+/* split over `splits` CTAs per output tile; fp32 partial tiles are folded in order by pt_reduce_partials.        */
+typedef struct PtWgradArgs {
+  const PtTensorMap* tmap_dt;   /* dD^T bf16 [N, rows]: rank-2 {rows, N}, box {64, 128} */
+  const PtTensorMap* tmap_a;    /* layer input bf16 [rows, K]: rank-2 {K, rows}, box {64, 64} */
+  int32_t rows, N, K, num_taps;
+  int32_t tap_shift[9];
+  int32_t splits;
+  float* partials;              /* fp32 [splits][N][num_taps*K] */
+} PtWgradArgs;
+int pt_wgrad(const PtWgradArgs* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

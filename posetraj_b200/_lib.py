@@ -158,6 +158,36 @@ PtRasterArgs = _st("PtRasterArgs", [
     ("tracks", vp), ("K", i32), ("F", i32), ("H", i32), ("W", i32), ("order", vp), ("out_f32", vp), ("out_u8", vp),
     ("swap_per_track", i32)])
 
+i64, f64 = C.c_int64, C.c_double
+
+PtEdmLossArgs = _st("PtEdmLossArgs", [
+    ("pred", vp), ("pred_ld", i32), ("noisy", vp), ("target", vp), ("sample_stride", i64), ("frame_stride", i64),
+    ("sigmas", vp), ("B", i32), ("F", i32), ("C", i32), ("HW", i32), ("weight", f32), ("dpred", vp), ("dpred_ld", i32),
+    ("workspace", vp), ("loss", vp), ("accumulate", i32)])
+
+PtGroupNormBwdArgs = _st("PtGroupNormBwdArgs", [
+    ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32), ("ld0", i32), ("ld1", i32), ("dout", vp), ("dout_ld", i32),
+    ("halo", i32), ("H", i32), ("W", i32), ("gamma", vp), ("beta", vp), ("eps", f32), ("silu", i32),
+    ("rows_per_stat", i32), ("num_stat", i32), ("dx0", vp), ("dx1", vp), ("dld0", i32), ("dld1", i32),
+    ("workspace", vp), ("dgb_out", vp), ("accumulate_dgb", i32)])
+
+PtLayerNormBwdArgs = _st("PtLayerNormBwdArgs", [
+    ("x", vp), ("ld", i32), ("dout", vp), ("dout_ld", i32), ("gamma", vp), ("eps", f32), ("rows", i32), ("C", i32),
+    ("addvec", vp), ("hw", i32), ("F", i32), ("dx", vp), ("dx_ld", i32), ("accumulate_dx", i32), ("partials", vp),
+    ("n_blocks", i32), ("dgb_out", vp), ("accumulate_dgb", i32)])
+
+PtColsumArgs = _st("PtColsumArgs", [
+    ("x", vp), ("ld", i32), ("halo", i32), ("H", i32), ("W", i32), ("rows_per_group", i64), ("groups", i32), ("C", i32),
+    ("scale", f32), ("out", vp), ("accumulate", i32)])
+
+PtAdamWArgs = _st("PtAdamWArgs", [
+    ("master", vp), ("grad", vp), ("m", vp), ("v", vp), ("work", vp), ("n", i64), ("lr", f32), ("beta1", f32),
+    ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("grad_scale", f32), ("step", i32)])
+
+PtWgradArgs = _st("PtWgradArgs", [
+    ("tmap_dt", vp), ("tmap_a", vp), ("rows", i32), ("N", i32), ("K", i32), ("num_taps", i32), ("tap_shift", i32 * 9),
+    ("splits", i32), ("partials", vp)])
+
 PT_DT_BF16 = 0
 PT_DT_F32 = 1
 
@@ -195,6 +225,22 @@ _SIGNATURES = {
     "pt_bicubic_resize": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_attention_small": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_time_conv3": (C.c_int, [C.c_void_p, C.c_void_p]),
+    # training step
+    "pt_edm_loss": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_edm_loss_workspace_bytes": (C.c_int64, []),
+    "pt_groupnorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_groupnorm_bwd_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "pt_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_geglu_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "pt_geglu_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                               C.c_void_p]),
+    "pt_colsum": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_reduce_partials": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pt_dot_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_int32,
+                              C.c_void_p, C.c_void_p]),
+    "pt_transpose_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "pt_adamw": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_wgrad": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

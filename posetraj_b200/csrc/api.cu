@@ -136,5 +136,11 @@ extern "C" int pt_sizeof(const char* name) {
   if (!strcmp(name, "PtBicubicArgs")) return (int)sizeof(PtBicubicArgs);
   if (!strcmp(name, "PtAttnSmallArgs")) return (int)sizeof(PtAttnSmallArgs);
   if (!strcmp(name, "PtTimeConvArgs")) return (int)sizeof(PtTimeConvArgs);
+  if (!strcmp(name, "PtEdmLossArgs")) return (int)sizeof(PtEdmLossArgs);
+  if (!strcmp(name, "PtGroupNormBwdArgs")) return (int)sizeof(PtGroupNormBwdArgs);
+  if (!strcmp(name, "PtLayerNormBwdArgs")) return (int)sizeof(PtLayerNormBwdArgs);
+  if (!strcmp(name, "PtColsumArgs")) return (int)sizeof(PtColsumArgs);
+  if (!strcmp(name, "PtAdamWArgs")) return (int)sizeof(PtAdamWArgs);
+  if (!strcmp(name, "PtWgradArgs")) return (int)sizeof(PtWgradArgs);
   return -1;
 }
