@@ -456,6 +456,87 @@ def frame_sharded_leg(cfg, unet, cnet, dev, rank, world, steps, barrier):
     return res
 
 
+
+def train_dp_leg(cfg, dev, rank, world, barrier):
+    """BASELINE.json configs[3] (controlnet_sdv_bbox pre-training, data-parallel), the parts that exist as kernels
+    (posetraj_b200/training.py, DESIGN.md "Training"): forward + backward of one level-0 SpatioTemporalResBlock at the
+    per-rank shape (2 videos x 14 frames x 40x72, 320 channels) — 3x3 conv and temporal conv dgrad (pt_gemm) / wgrad
+    (pt_wgrad, tcgen05), 4-D and 5-D GroupNorm+SiLU backward — and the data-parallel tail of a step at FULL size: the
+    683 M ControlNet gradients in 100 MB fp32 buckets, NCCL all-reduce per bucket, fused AdamW.  The whole-network reverse
+    pass (attention backward) is not built: this is not a steps/s number for configs[3]."""
+    import math
+    import torch
+    from posetraj_b200 import training as T
+    from posetraj_b200.config import controlnet_param_shapes
+    B, Fr, H, W, Cc, temb = 2, FRAMES, LAT_H, LAT_W, cfg.block_out_channels[0], cfg.block_out_channels[0] * 4
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    rn = lambda *s, sc=1.0: torch.randn(*s, device=dev, generator=g) * sc
+    params = {}
+    for blk, conv in (("spatial_res_block", (Cc, Cc, 3, 3)), ("temporal_res_block", (Cc, Cc, 3, 1, 1))):
+        for i in (1, 2):
+            params[f"{blk}.norm{i}.weight"], params[f"{blk}.norm{i}.bias"] = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
+            params[f"{blk}.conv{i}.weight"] = rn(*conv, sc=1 / math.sqrt(Cc * 9))
+            params[f"{blk}.conv{i}.bias"] = rn(Cc, sc=0.02)
+    params["time_mixer.mix_factor"] = torch.full((1,), 0.5, device=dev)
+    tr = T.ResBlockTrainer(params, B=B, F=Fr, H=H, W=W, eps=1e-6)
+    rows = B * Fr * H * W
+    x, dout = rn(rows, Cc).to(torch.bfloat16), rn(rows, Cc).to(torch.bfloat16)
+    ts, tt = rn(B, Cc, sc=0.1), rn(B, Cc, sc=0.1)
+
+    def fb():
+        tr.forward(x, ts, tt)
+        return tr.backward(dout)
+
+    fb()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3
+    e0.record()
+    for _ in range(n):
+        fb()
+    e1.record()
+    barrier()
+    ms_block = _max_over_ranks(e0.elapsed_time(e1) / n, dev, world)
+    conv_fl = 2.0 * rows * Cc * Cc * (9 + 9 + 3 + 3)
+    # data-parallel tail at the full ControlNet size
+    sizes = [int(math.prod(sh)) for sh in controlnet_param_shapes(cfg, cam=False, bbox=True).values()]
+    gb = T.GradientBuckets(sizes, dev, bucket_mb=100.0)
+    for f in gb.flat:
+        f.normal_(generator=g)
+    opt = T.AdamW(gb, [torch.zeros(1, device=dev)] * 0, work=[], lr=1e-5)
+
+    def dp_tail():
+        for i in reversed(range(len(sizes))):
+            gb.ready(i)
+        gb.finish()
+
+    dp_tail()
+    barrier()
+    e0.record()
+    dp_tail()
+    e1.record()
+    barrier()
+    ms_ar = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+    opt.step()
+    barrier()
+    e0.record()
+    opt.step()
+    e1.record()
+    barrier()
+    ms_opt = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+    nbytes = 4.0 * sum(sizes)
+    res = {"workload": "configs[3] building blocks: level-0 SpatioTemporalResBlock fwd+bwd (2 videos x 14 frames x 40x72 per rank); "
+                       "all-reduce + AdamW of the full 683 M-parameter ControlNet gradient",
+           "resblock_fwd_bwd_ms": ms_block, "resblock_conv_tflops": 3.0 * conv_fl / ms_block / 1e9,
+           "grad_bytes": nbytes, "buckets": len(gb.buckets), "allreduce_ms": ms_ar if world > 1 else None,
+           "allreduce_busbw_gbs": (2.0 * (world - 1) / world * nbytes / ms_ar / 1e6) if world > 1 else None,
+           "adamw_ms": ms_opt, "adamw_gbs": (nbytes * 7.5) / ms_opt / 1e6,
+           "not_built": "attention backward and the whole-network reverse pass (no configs[3] steps/s yet)"}
+    del gb, opt, tr
+    torch.cuda.empty_cache()
+    return res
+
+
 def library_baseline_leg(dev, steps=3):
     """The "library bar": the oracle's wiring as plain torch eager bf16 on this GPU (cuDNN / cuBLAS / SDPA, no fusion) —
     what the reference would run here, since it ships no Blackwell kernel.  Comparator only (imports oracle/)."""
@@ -651,6 +732,7 @@ def run_own(args):
                 extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
         leg("configs2_cam", cam_leg, cfg, unet, dev, rank, world, leg_steps, barrier)
+        leg("configs3_train_blocks", train_dp_leg, cfg, dev, rank, world, barrier)
         if world >= 2 and world % 2 == 0:
             leg("cfg_split", cfg_split_leg, cfg, unet, cnet, dev, rank, world, leg_steps, barrier, ms_per_step,
                 lat_final if rank == 0 else None)

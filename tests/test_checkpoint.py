@@ -63,3 +63,35 @@ def test_from_pretrained_runs_like_the_oracle(tmp_path, cuda_dev):
     sd.pop("conv_in.weight")
     with pytest.raises(KeyError):
         ControlNetSDVModel(cfg, sd, cuda_dev)
+
+
+@pytest.mark.gpu
+def test_pipeline_from_pretrained_like_the_reference_script(tmp_path, cuda_dev):
+    """scripts/run_inference_vipseg_json_repro.py:335-339, line for line: ControlNet / UNet / pipeline `from_pretrained`,
+    then `enable_model_cpu_offload()` (a no-op here), then one call."""
+    import json
+    from posetraj_b200 import checkpoint
+    from posetraj_b200.models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+    from posetraj_b200.pipeline import StableVideoDiffusionPipelineControlNet
+    cfg = small_cfg()
+    o_unet, o_cnet = oracle_pair(cfg, seed=3)
+    root = tmp_path / "stable-video-diffusion-img2vid"
+    checkpoint.save_pretrained(o_unet.state_dict(), cfg, str(root / "unet"), "UNetSpatioTemporalConditionControlNetModel")
+    checkpoint.save_pretrained(o_cnet.state_dict(), cfg, str(tmp_path / "ckpt" / "controlnet"), "ControlNetSDVModel")
+    (root / "scheduler").mkdir(parents=True)
+    (root / "scheduler" / "scheduler_config.json").write_text(json.dumps(
+        {"_class_name": "EulerDiscreteScheduler", "sigma_min": 0.002, "sigma_max": 700.0, "use_karras_sigmas": True,
+         "prediction_type": "v_prediction", "timestep_type": "continuous", "beta_schedule": "scaled_linear"}))
+    controlnet = ControlNetSDVModel.from_pretrained(str(tmp_path / "ckpt"), subfolder="controlnet", device=cuda_dev)
+    unet = UNetSpatioTemporalConditionControlNetModel.from_pretrained(str(root), subfolder="unet", device=cuda_dev)
+    pipeline = StableVideoDiffusionPipelineControlNet.from_pretrained(str(root), controlnet=controlnet, unet=unet)
+    pipeline.enable_model_cpu_offload()
+    assert pipeline.vae is None and pipeline.image_encoder is None      # not in this directory: passed per call instead
+    inp = make_small_inputs(cfg)
+    h, w = inp["latents"].shape[-2:]
+    out = pipeline(None, inp["controlnet_condition"][0].to(cuda_dev), height=h * 8, width=w * 8, num_frames=cfg.num_frames,
+                   num_inference_steps=2, latents=(inp["latents"] / 700.0).to(cuda_dev), output_type="latent",
+                   image_embeddings=inp["image_embeddings"].to(cuda_dev), image_latents=inp["image_latents"].to(cuda_dev)).frames
+    assert out.shape == (1, cfg.num_frames, 4, h, w) and torch.isfinite(out).all()
+    with pytest.raises(FileNotFoundError):
+        StableVideoDiffusionPipelineControlNet.from_pretrained(str(tmp_path / "nope"), controlnet=controlnet, unet=unet)
