@@ -251,7 +251,12 @@ class Gemm:
         valid_rows = out_rows if not (halo is not None and out_halo) else n_img * a.oH * a.oW
         self.kind = "gemm"
         self.alg_flops = 2.0 * valid_rows * n_out * (2 if geglu else 1) * (alg_k if alg_k is not None else ntaps * (k0 + k1))
-        self.alg_bytes = 0.0
+        # algorithmic bytes (read-once / write-once): the A rows once whatever the tap count, the weights, every epilogue
+        # operand and output
+        esz = out.element_size()
+        self.alg_bytes = float(rows_total * (k0 + k1) * 2 + w.numel() * 2 + valid_rows * n_out * esz
+                               + sum(valid_rows * n_out * 2 for t in (res1, res2, aux) if t is not None)
+                               + (valid_rows * n_out * esz if out2 is not None else 0))
         self.args = a
         self._keep = (a0, a1, w, out, bias, rowvec, res1, res2, out2, aux, acc_scale_dev)
         self._argp = C.addressof(a)
@@ -299,9 +304,9 @@ class FusedMlp:
         if trace is not None:
             assert trace.dtype == torch.int64 and trace.numel() >= 2 * 8 * 64
             a.trace = trace.data_ptr()
-        self.kind = "gemm"     # a dense contraction: counted with the GEMM class in bench.py's roofline
+        self.kind = "mlp_geglu"
         self.alg_flops = 2.0 * rows * Cc * (2 * hidden) + 2.0 * rows * hidden * Cc
-        self.alg_bytes = 0.0
+        self.alg_bytes = float(rows * Cc * 2 * (2 + sum(1 for t in (res1, res2) if t is not None)) + (w1.numel() + w2.numel()) * 2)
         self.args = a
         self._keep = (x, w1, b1, w2, b2, out, res1, res2)
         self._argp = C.addressof(a)
