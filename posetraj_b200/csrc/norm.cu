@@ -70,9 +70,16 @@ PT_DEVICE uint4 lds_u4(uint32_t addr) {
   return u;
 }
 
+// kCluster: the CTAs of one statistics group form ONE thread-block cluster (<= 16 CTAs, every row resident in shared
+// memory): the partial sums are exchanged through distributed shared memory behind the hardware cluster barrier instead of
+// the global-memory rendezvous (atomic counter + polling), whose ~10 us of latency is the floor of the 107 GroupNorm
+// launches on the small tensors of levels 1-3.  Opt-in (PT_GN_CLUSTER=1): measured slower, profiles/r2i_groupnorm_cluster.md.  Co-residency is guaranteed by the cluster
+// launch, so this path makes no assumption about the rest of the GPU being empty.
+template <bool kCluster>
 __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   extern __shared__ __align__(16) float s_red[];  // [rpar][C] sums, [rpar][C] squares, then [C] + [C] per-channel totals; then resident rows
   __shared__ float s_mean[32], s_rstd[32];
+  __shared__ double s_cl[64];  // kCluster: this CTA's per-group {sum, sum of squares}, read by the peers
   const int C = p.c0 + p.c1;
   const int cvec = C >> 3;            // threads along channels (8 channels each)
   const int rpar = blockDim.x / cvec; // row lanes
@@ -187,30 +194,54 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
       a += c_sum[threadIdx.x * cg + i];
       b += c_sq[threadIdx.x * cg + i];
     }
-    double* dst = p.partials + (((size_t)stat * p.splits + split) * 32 + threadIdx.x) * 2;
-    dst[0] = (double)a;
-    dst[1] = (double)b;
-    __threadfence();
+    if constexpr (kCluster) {
+      s_cl[2 * threadIdx.x] = (double)a;
+      s_cl[2 * threadIdx.x + 1] = (double)b;
+    } else {
+      double* dst = p.partials + (((size_t)stat * p.splits + split) * 32 + threadIdx.x) * 2;
+      dst[0] = (double)a;
+      dst[1] = (double)b;
+      __threadfence();
+    }
   }
   __syncthreads();
 
   // ---------------- rendezvous of the CTAs of this statistics group ----------------
-  if (threadIdx.x == 0) {
-    atomicAdd(&p.arrive[stat], 1u);
-    unsigned int spins = 0;
-    while (*reinterpret_cast<volatile unsigned int*>(&p.arrive[stat]) < (unsigned)p.splits) {
-      __nanosleep(20);
-      if (++spins > (1u << 25)) asm volatile("trap;");  // a sizing bug becomes an error, not a hung GPU
+  if constexpr (kCluster) {
+    cluster_sync_all();   // release / acquire at cluster scope: every peer's s_cl is visible
+  } else {
+    if (threadIdx.x == 0) {
+      atomicAdd(&p.arrive[stat], 1u);
+      unsigned int spins = 0;
+      while (*reinterpret_cast<volatile unsigned int*>(&p.arrive[stat]) < (unsigned)p.splits) {
+        __nanosleep(20);
+        if (++spins > (1u << 25)) asm volatile("trap;");  // a sizing bug becomes an error, not a hung GPU
+      }
+      __threadfence();
     }
-    __threadfence();
+    __syncthreads();
   }
-  __syncthreads();
   griddep_launch();
 
   // ---------------- fixed-order fp64 fold of all partials (identical in every CTA of the group) ----------------
   double* s_part = reinterpret_cast<double*>(s_red);  // [nsl][64], reuses the reduction scratch (>= 4 KiB)
   int nsl = blockDim.x >> 6;
   if (nsl > 8) nsl = 8;
+  if constexpr (kCluster) {
+    nsl = 1;
+    if (threadIdx.x < 64) {
+      const uint32_t mine = smem_u32(&s_cl[threadIdx.x]);
+      double acc = 0.0;
+      for (int q = 0; q < p.splits; ++q) {   // rank order: identical bits in every CTA of the cluster
+        double v;
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(map_to_cta(mine, (uint32_t)q)));
+        acc += v;
+      }
+      s_part[threadIdx.x] = acc;
+    }
+    // nobody may leave (or overwrite s_cl in a later launch) while a peer still reads its partials
+    cluster_sync_all();
+  } else {
   if ((int)threadIdx.x < nsl * 64) {
     const int vi = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const double* srcp = p.partials + (size_t)stat * p.splits * 64 + vi;
@@ -223,6 +254,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
     }
     for (; i < p.splits; i += nsl) acc += __ldcg(srcp + (size_t)i * 64);
     s_part[sl * 64 + vi] = acc;
+  }
   }
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -247,10 +279,12 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
   }
   __syncthreads();
   // every CTA has read the partials it needs: the last one to get here re-arms the counters for the next launch
-  if (threadIdx.x == 0) {
-    if (atomicAdd(&p.depart[stat], 1u) == (unsigned)(p.splits - 1)) {
-      p.arrive[stat] = 0u;
-      p.depart[stat] = 0u;
+  if constexpr (!kCluster) {
+    if (threadIdx.x == 0) {
+      if (atomicAdd(&p.depart[stat], 1u) == (unsigned)(p.splits - 1)) {
+        p.arrive[stat] = 0u;
+        p.depart[stat] = 0u;
+      }
     }
   }
 
@@ -524,7 +558,7 @@ static int gn_ctas_per_sm(int C) {
   const int d = pt_device_slot();
   if (cached_threads[d] != threads || cached_smem[d] != smem) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_fused_kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_fused_kernel<false>, threads, smem) != cudaSuccess || nb < 1) nb = 1;
     cached_threads[d] = threads;
     cached_smem[d] = smem;
     cached_blocks[d] = nb;
@@ -605,18 +639,52 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   PT_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "pt_groupnorm: mode must be 0, 1 or 2");
   PT_CHECK_ARG(a->mode == 0 || a->sums != nullptr || (a->mode == 2 && a->n_peers > 0), "pt_groupnorm: modes 1/2 need `sums`");
   PT_CHECK_ARG(a->mode != 2 || a->count > 0, "pt_groupnorm: mode 2 needs `count`");
+  static bool attr_set[PT_MAX_DEVICES] = {false};  // cudaFuncSetAttribute is per device
+  const int dev_slot = pt_device_slot();
+  if (!attr_set[dev_slot]) {
+    cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemPerSm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemPerSm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return pt_fail(e, "pt_groupnorm: cudaFuncSetAttribute");
+    attr_set[dev_slot] = true;
+  }
+  // Cluster path (mode 0): the smallest cluster size in {1, 2, 4, 8, 16} that keeps EVERY row of its CTAs resident in
+  // shared memory, provided the whole grid fits the GPU in one wave (otherwise — the 25-100 MB tensors of level 0 and
+  // the 5-D temporal statistics — the co-resident global rendezvous below is the better schedule).
+  {
+    // Measured on B200 (profiles/r2i_groupnorm_cluster.md): parity green, but the class got SLOWER in the captured step
+    // (4.59 -> 5.11 ms for the 152 launches): cluster scheduling costs more than the polled counter it replaces.
+    // Kept behind PT_GN_CLUSTER=1 as an experiment; the default is the co-resident rendezvous below.
+    static int env_cl = -2;
+    if (env_cl == -2) {
+      const char* e = getenv("PT_GN_CLUSTER");
+      env_cl = e ? atoi(e) : 0;
+    }
+    const int rpar = threads / (C / 8);
+    if (a->mode == 0 && env_cl != 0) {
+      for (int cs = 1; cs <= 16; cs *= 2) {
+        const int rps = (a->rows_per_stat + cs - 1) / cs;
+        const int need = (rps + rpar - 1) / rpar;
+        const size_t smem = (size_t)gn_red_bytes(C) + (size_t)need * threads * 16;
+        if (smem > (size_t)kGnSmemPerSm) continue;
+        const int per_sm = (int)((size_t)kGnSmemPerSm / smem) < 4 ? (int)((size_t)kGnSmemPerSm / smem) : 4;
+        if ((long long)a->num_stat * cs > (long long)pt_num_sms() * per_sm) break;
+        if (cs > 1 && (a->num_stat * cs) % cs != 0) break;
+        GnParams pc = p;
+        pc.splits = cs;
+        pc.res_slots = need;
+        pc.res_off = gn_red_bytes(C);
+        cudaError_t e = pt_launch(gn_fused_kernel<true>, dim3(a->num_stat * cs), dim3(threads), smem, (void*)stream, cs, pc);
+        if (e != cudaSuccess) return pt_fail(e, "pt_groupnorm: cluster launch");
+        return pt_launched("pt_groupnorm");
+      }
+    }
+  }
   const int rows_per_split = (a->rows_per_stat + splits - 1) / splits;
   p.res_slots = a->mode == 0 ? gn_res_slots(C, gn_ctas_per_sm(C), rows_per_split) : 0;
   p.res_off = gn_red_bytes(C);
   const size_t smem_bytes = (size_t)p.res_off + (size_t)p.res_slots * threads * 16;
-  static bool attr_set[PT_MAX_DEVICES] = {false};  // cudaFuncSetAttribute is per device
-  const int dev_slot = pt_device_slot();
-  if (!attr_set[dev_slot]) {
-    cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnSmemPerSm);
-    if (e != cudaSuccess) return pt_fail(e, "pt_groupnorm: cudaFuncSetAttribute");
-    attr_set[dev_slot] = true;
-  }
-  pt_launch(gn_fused_kernel, dim3(a->num_stat * splits), dim3(threads), smem_bytes, (void*)stream, 1, p);
+  pt_launch(gn_fused_kernel<false>, dim3(a->num_stat * splits), dim3(threads), smem_bytes, (void*)stream, 1, p);
   return pt_launched("pt_groupnorm");
 }
 
