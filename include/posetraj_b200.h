@@ -259,6 +259,8 @@ typedef struct PtAttnSpatialArgs {
   void* out;                /* bf16 [n_img*S, out_ld] */
   int32_t out_ld;
   int32_t S, heads, C, n_img;
+  float* lse;               /* optional fp32 [n_img, heads, S]: log2(sum_j exp2(scale*log2e*s_ij)) per query row, kept for
+                             * the training backward (pt_attention_spatial_bwd); NULL at inference */
 } PtAttnSpatialArgs;
 int pt_attention_spatial(const PtAttnSpatialArgs* a, void* stream);
 
@@ -560,6 +562,88 @@ typedef struct PtWgradArgs {
   float* partials;              /* fp32 [splits][N][num_taps*K] */
 } PtWgradArgs;
 int pt_wgrad(const PtWgradArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Whole-network training step: the remaining backward kernels (train_attn.cu, train_misc.cu). */
+/* Reference: autograd through diffusers' Attention / Upsample2D / Downsample2D / TimestepEmbedding and the     */
+/* conditioning embedding (models/controlnet_sdv.py:95-116) inside `accelerator.backward(loss)`,               */
+/* scripts/train_svd_traj_VIPSeg_14_cam_concat.py:1470.                                                        */
+/* ------------------------------------------------------------------------------------------ */
+/* delta[img, head, s] = sum_d dO[row, head*64 + d] * O[row, head*64 + d]  (rows = n_img * S) */
+int pt_attention_delta(const void* out, int32_t out_ld, const void* dout, int32_t dout_ld, float* delta, int64_t rows,
+                       int32_t S, int32_t heads, void* stream);
+
+typedef struct PtAttnSpatialBwdArgs {
+  const void* qkv;          /* bf16 [n_img*S, ld] = (Q | K | V), the forward's input */
+  int32_t ld;
+  const void* dout;         /* bf16 [n_img*S, dout_ld]: gradient of the attention output */
+  int32_t dout_ld;
+  const float* lse;         /* [n_img, heads, S] from pt_attention_spatial (PtAttnSpatialArgs.lse) */
+  const float* delta;       /* [n_img, heads, S] from pt_attention_delta */
+  void* dqkv;               /* bf16 [n_img*S, dld] = (dQ | dK | dV) */
+  int32_t dld;
+  int32_t S, heads, C, n_img;
+} PtAttnSpatialBwdArgs;
+int pt_attention_spatial_bwd(const PtAttnSpatialBwdArgs* a, void* stream);
+
+typedef struct PtAttnTemporalBwdArgs {
+  const void* qkv;          /* bf16 [B*F*HW, ld] = (Q | K | V), rows (b*F + f)*HW + s */
+  int32_t ld;
+  const void* dout;         /* bf16 [B*F*HW, dout_ld] */
+  int32_t dout_ld;
+  void* dqkv;               /* bf16 [B*F*HW, dld] */
+  int32_t dld;
+  int32_t B, F, HW, heads, C;
+} PtAttnTemporalBwdArgs;
+int pt_attention_temporal_bwd(const PtAttnTemporalBwdArgs* a, void* stream);
+
+/* backward of pt_upsample2x (same struct: `x`/`ld` = the compact gradient to WRITE, `out`/`out_ld` = the gradient of the
+ * forward output to READ): sum over the scale x scale children; scale 1 + halo strips the zero halo */
+int pt_upsample2x_bwd(const PtUpsampleArgs* a, void* stream);
+/* gradient of a stride-2 conv output ([n, ceil(H/2), ceil(W/2)] rows, zero-haloed when src_halo) -> zero-haloed
+ * [n, H+1, W+1] rows with the values at the even pixels and zeros elsewhere (every row is written) */
+int pt_dilate2x(const void* src, int32_t src_ld, int32_t src_halo, void* dst, int32_t dst_ld, int32_t n, int32_t H, int32_t W,
+                int32_t C, void* stream);
+/* zero the halo rows (y == H or x == W) of a zero-haloed [n, H+1, W+1] buffer */
+int pt_zero_halo(void* x, int32_t ld, int32_t n, int32_t H, int32_t W, int32_t C, void* stream);
+/* SiLU as a separate pass (bf16 [rows, cols]); backward: dx = dy * silu'(x) */
+int pt_silu_fwd(const void* x, int32_t ld, void* out, int32_t out_ld, int64_t rows, int32_t cols, void* stream);
+int pt_silu_bwd(const void* x, int32_t ld, const void* dy, int32_t dy_ld, void* dx, int32_t dx_ld, int64_t rows, int32_t cols,
+                void* stream);
+
+/* backward of pt_small_linear without output activation: y = W act(x) + b */
+typedef struct PtSmallLinearBwdArgs {
+  const float* x;           /* fp32 [M, x_ld]: the forward input (before act_in) */
+  int32_t x_ld;
+  const void* w;            /* bf16 [N, w_ld] */
+  int32_t w_ld;
+  const float* dy;          /* fp32 [M, dy_ld] */
+  int32_t dy_ld;
+  int32_t M, N, K, act_in_silu;
+  float* dx;                /* fp32 [M, dx_ld] or NULL */
+  int32_t dx_ld, accumulate_dx;
+  float* dw;                /* fp32 [N, K] contiguous or NULL */
+  float* db;                /* fp32 [N] or NULL (written with dw) */
+  int32_t accumulate_w;
+} PtSmallLinearBwdArgs;
+int pt_small_linear_bwd(const PtSmallLinearBwdArgs* a, void* stream);
+
+/* out[g, c] (+)= scale * sum over rows r with group(r) == g of x[r, c]; group(r) =
+ *   mode 1: r / ga            mode 2: ((r / ga) * gb + r % gb) % gc  (PtGemmArgs.rowvec_mode 1 / 2)
+ *   mode 3: (r / ga) % gc     (frame of row (b*F + f)*HW + s with ga = HW, gc = F)
+ * groups <= 40; deterministic (two stages, fixed order) */
+typedef struct PtColsumGroupedArgs {
+  const void* x;            /* bf16 [rows, ld] */
+  int32_t ld;
+  int64_t rows;
+  int32_t C, groups, mode, ga, gb, gc;
+  float scale;
+  float* out;               /* fp32 [groups, out_ld] */
+  int32_t out_ld, accumulate;
+  void* workspace;          /* pt_colsum_grouped_workspace_bytes(rows, groups, C) */
+} PtColsumGroupedArgs;
+int pt_colsum_grouped(const PtColsumGroupedArgs* a, void* stream);
+int64_t pt_colsum_grouped_workspace_bytes(int64_t rows, int32_t groups, int32_t C);
 
 #ifdef __cplusplus
 }

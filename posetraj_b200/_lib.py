@@ -103,7 +103,7 @@ PtLayerNormArgs = _st("PtLayerNormArgs", [
     ("rows", i32), ("C", i32), ("addvec", vp), ("hw", i32), ("F", i32), ("sum_out", vp)])
 
 PtAttnSpatialArgs = _st("PtAttnSpatialArgs", [
-    ("tmap_qkv", vp), ("out", vp), ("out_ld", i32), ("S", i32), ("heads", i32), ("C", i32), ("n_img", i32)])
+    ("tmap_qkv", vp), ("out", vp), ("out_ld", i32), ("S", i32), ("heads", i32), ("C", i32), ("n_img", i32), ("lse", vp)])
 
 PtAttnTemporalArgs = _st("PtAttnTemporalArgs", [
     ("qkv", vp), ("ld", i32), ("out", vp), ("out_ld", i32),
@@ -188,6 +188,22 @@ PtWgradArgs = _st("PtWgradArgs", [
     ("tmap_dt", vp), ("tmap_a", vp), ("rows", i32), ("N", i32), ("K", i32), ("num_taps", i32), ("tap_shift", i32 * 9),
     ("splits", i32), ("partials", vp)])
 
+PtAttnSpatialBwdArgs = _st("PtAttnSpatialBwdArgs", [
+    ("qkv", vp), ("ld", i32), ("dout", vp), ("dout_ld", i32), ("lse", vp), ("delta", vp), ("dqkv", vp), ("dld", i32),
+    ("S", i32), ("heads", i32), ("C", i32), ("n_img", i32)])
+
+PtAttnTemporalBwdArgs = _st("PtAttnTemporalBwdArgs", [
+    ("qkv", vp), ("ld", i32), ("dout", vp), ("dout_ld", i32), ("dqkv", vp), ("dld", i32),
+    ("B", i32), ("F", i32), ("HW", i32), ("heads", i32), ("C", i32)])
+
+PtSmallLinearBwdArgs = _st("PtSmallLinearBwdArgs", [
+    ("x", vp), ("x_ld", i32), ("w", vp), ("w_ld", i32), ("dy", vp), ("dy_ld", i32), ("M", i32), ("N", i32), ("K", i32),
+    ("act_in_silu", i32), ("dx", vp), ("dx_ld", i32), ("accumulate_dx", i32), ("dw", vp), ("db", vp), ("accumulate_w", i32)])
+
+PtColsumGroupedArgs = _st("PtColsumGroupedArgs", [
+    ("x", vp), ("ld", i32), ("rows", i64), ("C", i32), ("groups", i32), ("mode", i32), ("ga", i32), ("gb", i32), ("gc", i32),
+    ("scale", f32), ("out", vp), ("out_ld", i32), ("accumulate", i32), ("workspace", vp)])
+
 PT_DT_BF16 = 0
 PT_DT_F32 = 1
 
@@ -241,6 +257,19 @@ _SIGNATURES = {
     "pt_transpose_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "pt_adamw": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_wgrad": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_attention_delta": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_void_p]),
+    "pt_attention_spatial_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_attention_temporal_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_upsample2x_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_dilate2x": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                              C.c_void_p]),
+    "pt_zero_halo": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "pt_silu_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "pt_silu_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "pt_small_linear_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_colsum_grouped": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_colsum_grouped_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
 }
 
 _lib = None

@@ -142,5 +142,9 @@ extern "C" int pt_sizeof(const char* name) {
   if (!strcmp(name, "PtColsumArgs")) return (int)sizeof(PtColsumArgs);
   if (!strcmp(name, "PtAdamWArgs")) return (int)sizeof(PtAdamWArgs);
   if (!strcmp(name, "PtWgradArgs")) return (int)sizeof(PtWgradArgs);
+  if (!strcmp(name, "PtAttnSpatialBwdArgs")) return (int)sizeof(PtAttnSpatialBwdArgs);
+  if (!strcmp(name, "PtAttnTemporalBwdArgs")) return (int)sizeof(PtAttnTemporalBwdArgs);
+  if (!strcmp(name, "PtSmallLinearBwdArgs")) return (int)sizeof(PtSmallLinearBwdArgs);
+  if (!strcmp(name, "PtColsumGroupedArgs")) return (int)sizeof(PtColsumGroupedArgs);
   return -1;
 }

@@ -33,6 +33,7 @@ struct AttnParams {
   float scale_log2;  // head_dim^-0.5 * log2(e)
   bf16* out;
   int out_ld;
+  float* lse;  // optional [n_img, heads, S]: log2-domain log-sum-exp of the scaled scores (training: pt_attention_spatial_bwd)
 };
 
 template <bool B>
@@ -315,6 +316,8 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
     const int qrow = q0 + g * kQTile + row;
     const float inv = 1.0f / l_run;
     bf16* dst = p.out + ((size_t)img * p.S + qrow) * p.out_ld + head * kHd;
+    if (p.lse != nullptr && qrow < p.S)
+      p.lse[((size_t)img * p.heads + head) * p.S + qrow] = m_ref * p.scale_log2 + log2f(l_run);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
@@ -375,6 +378,7 @@ extern "C" int pt_attention_spatial(const PtAttnSpatialArgs* a, void* stream) {
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.out_ld = a->out_ld;
+  p.lse = a->lse;
   if (a->S <= kQTile) return launch_attn<1>(a, p, (cudaStream_t)stream);
   return launch_attn<2>(a, p, (cudaStream_t)stream);
 }

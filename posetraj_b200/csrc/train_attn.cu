@@ -1,0 +1,509 @@
+// posetraj_b200 — attention backward for the training step of BASELINE configs[3].
+//
+// Reference: autograd through BasicTransformerBlock.attn1 / TemporalBasicTransformerBlock.attn1
+// (F.scaled_dot_product_attention inside diffusers' Attention, run by models/modified_svd.py:64-107) during
+// `accelerator.backward(loss)`, scripts/train_svd_traj_VIPSeg_14_cam_concat.py:1470.  Formulas: oracle/backward.py
+// (attention_backward), the FlashAttention-2 recomputation scheme:
+//     P = exp2(scale*log2e * Q K^T - lse),  D_i = sum_d dO_id O_id,
+//     dV = P^T dO,   dP = dO V^T,   dS = P o (dP - D),   dQ = scale * dS K,   dK = scale * dS^T Q.
+//
+//   pt_attention_delta           D = rowsum(dO o O) per (row, head), fp32
+//   pt_attention_spatial_bwd     two kernels, no atomics (deterministic): dK/dV per 64-key block looping over the query
+//                                blocks, dQ per 64-query block looping over the key blocks; each recomputes S and dP.
+//                                Warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) on cp.async-staged, XOR-swizzled
+//                                64 x 64 shared-memory tiles.  7 matmuls of S^2*64 MACs per (image, head): 2.5x + 1x
+//                                (recomputation) the forward's FLOPs.
+//   pt_attention_temporal_bwd    one warp per (batch, pixel, head): the F x F problem (F <= 32) in fp32 through shared
+//                                memory; HBM-bound (reads qkv + dO, writes dqkv once).
+// These are first, correct versions on the legacy tensor-core path; the forward kernels are tcgen05 (attn_spatial.cu).
+#include "common.cuh"
+#include "launch.h"
+#include "../../include/posetraj_b200.h"
+
+namespace pt {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+PT_DEVICE void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+PT_DEVICE void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+PT_DEVICE void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+PT_DEVICE void cp_async16(uint32_t saddr, const void* g, bool ok) {
+  const int sz = ok ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+PT_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+PT_DEVICE void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// 64 rows x 64 bf16 tile (128 B per row), 16-byte chunks XOR-swizzled by (row & 7): conflict-free ldmatrix.
+constexpr int kBwdTile = 64;
+constexpr int kBwdTileBytes = 64 * 128;
+
+PT_DEVICE uint32_t tile_addr(uint32_t base, int row, int chunk) { return base + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
+
+// rows [row0, row0 + 64) of one (image, head, part) column block -> smem; rows >= S are zero-filled
+PT_DEVICE void load_tile(uint32_t sbase, const bf16* g, int ld, int row0, int S, int tid) {
+  for (int i = tid; i < 512; i += 128) {
+    const int r = i >> 3, ch = i & 7;
+    const bool ok = row0 + r < S;
+    cp_async16(tile_addr(sbase, r, ch), g + (size_t)(ok ? row0 + r : 0) * ld + ch * 8, ok);
+  }
+}
+
+// A fragments (16 rows x 64 k) of rows [r0, r0+16) of a tile: 4 k-steps
+PT_DEVICE void load_a_frags(uint32_t (&a)[4][4], uint32_t sbase, int r0, int lane) {
+  const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm_x4(a[ks], tile_addr(sbase, row, ks * 2 + (lane >> 4)));
+}
+
+// acc[nt] (16 x 8 each, nt over the 64 tile rows) += A(16 x 64) * T^T where the tile T is stored [n rows][k cols]
+PT_DEVICE void mma_a_tileT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t sbase, int lane) {
+  const int mi = lane >> 3;
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {      // pairs of n-tiles
+    const int nrow = np * 16 + (lane & 7) + (mi >> 1) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t b[4];
+      ldsm_x4(b, tile_addr(sbase, nrow, ks * 2 + (mi & 1)));
+      mma_bf16_16816(acc[np * 2], a[ks], b[0], b[1]);
+      mma_bf16_16816(acc[np * 2 + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+
+// acc[nt] (16 x 8 each, nt over the 64 tile COLUMNS) += A(16 x 64) * T where the tile T is stored [k rows][n cols]
+PT_DEVICE void mma_a_tile(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t sbase, int lane) {
+  const int mi = lane >> 3;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int krow = ks * 16 + (lane & 7) + (mi & 1) * 8;
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm_x4_trans(b, tile_addr(sbase, krow, np * 2 + (mi >> 1)));
+      mma_bf16_16816(acc[np * 2], a[ks], b[0], b[1]);
+      mma_bf16_16816(acc[np * 2 + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+
+// C fragments of a 16 x 64 block -> A fragments (bf16) of the same block
+PT_DEVICE void c_to_a(uint32_t (&a)[4][4], const float (&c)[8][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    a[ks][0] = pack_bf16x2(c[2 * ks][0], c[2 * ks][1]);
+    a[ks][1] = pack_bf16x2(c[2 * ks][2], c[2 * ks][3]);
+    a[ks][2] = pack_bf16x2(c[2 * ks + 1][0], c[2 * ks + 1][1]);
+    a[ks][3] = pack_bf16x2(c[2 * ks + 1][2], c[2 * ks + 1][3]);
+  }
+}
+
+struct AttnBwdParams {
+  const bf16* qkv;   // [n_img*S, ld] = Q | K | V
+  int ld;
+  const bf16* dout;  // [n_img*S, dout_ld]
+  int dout_ld;
+  const float* lse;    // [n_img, heads, S] log2 domain
+  const float* delta;  // [n_img, heads, S]
+  bf16* dqkv;          // [n_img*S, dld] = dQ | dK | dV
+  int dld;
+  int S, heads, C;
+  float scale, scale_log2;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// delta = rowsum(dO o O): one warp per (row, head)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* o, int o_ld, const bf16* dout, int d_ld, float* delta, long long rows,
+                                                         int S, int heads) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows * heads) return;
+  const long long row = w / heads;
+  const int head = (int)(w - row * heads);
+  const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + (size_t)row * o_ld + head * 64 + 2 * lane));
+  const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + (size_t)row * d_ld + head * 64 + 2 * lane));
+  const float t = warp_sum(a.x * b.x + a.y * b.y);
+  if (lane == 0) {
+    const long long img = row / S;
+    const int s = (int)(row - img * S);
+    delta[((size_t)img * heads + head) * S + s] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dK, dV of one 64-key block: warp w owns keys [16w, 16w+16); loop over the query blocks
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sK = smem_u32(smem), sV = sK + kBwdTileBytes;
+  const uint32_t sQ0 = sV + kBwdTileBytes;           // 2 stages x (Q, dO)
+  float* s_lse = reinterpret_cast<float*>(smem + 6 * kBwdTileBytes);  // [2][64]
+  float* s_delta = s_lse + 128;                                        // [2][64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int key0 = blockIdx.x * kBwdTile, head = blockIdx.y, img = blockIdx.z;
+  const size_t img_row = (size_t)img * p.S;
+  const bf16* qg = p.qkv + img_row * p.ld + head * 64;
+  const bf16* kg = qg + p.C;
+  const bf16* vg = qg + 2 * p.C;
+  const bf16* dog = p.dout + img_row * p.dout_ld + head * 64;
+  const float* lse_g = p.lse + ((size_t)img * p.heads + head) * p.S;
+  const float* delta_g = p.delta + ((size_t)img * p.heads + head) * p.S;
+  const int n_q = (p.S + kBwdTile - 1) / kBwdTile;
+
+  auto load_q = [&](int st, int it) {
+    const int q0 = it * kBwdTile;
+    load_tile(sQ0 + (uint32_t)st * 2 * kBwdTileBytes, qg, p.ld, q0, p.S, tid);
+    load_tile(sQ0 + (uint32_t)st * 2 * kBwdTileBytes + kBwdTileBytes, dog, p.dout_ld, q0, p.S, tid);
+    if (tid < 64) {
+      const bool ok = q0 + tid < p.S;
+      s_lse[st * 64 + tid] = ok ? lse_g[q0 + tid] : INFINITY;   // exp2(x - inf) = 0: padded queries contribute nothing
+      s_delta[st * 64 + tid] = ok ? delta_g[q0 + tid] : 0.f;
+    }
+  };
+  load_tile(sK, kg, p.ld, key0, p.S, tid);
+  load_tile(sV, vg, p.ld, key0, p.S, tid);
+  load_q(0, 0);
+  cp_async_commit();
+
+  uint32_t ka[4][4], va[4][4];
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dk[i][j] = dv[i][j] = 0.f;
+  const bool key_ok0 = key0 + warp * 16 + g < p.S, key_ok1 = key0 + warp * 16 + g + 8 < p.S;
+
+  for (int it = 0; it < n_q; ++it) {
+    const int st = it & 1;
+    if (it + 1 < n_q) load_q(st ^ 1, it + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (it == 0) {
+      load_a_frags(ka, sK, warp * 16, lane);
+      load_a_frags(va, sV, warp * 16, lane);
+    }
+    const uint32_t sQ = sQ0 + (uint32_t)st * 2 * kBwdTileBytes, sdO = sQ + kBwdTileBytes;
+    float sc[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sc[i][j] = dp[i][j] = 0.f;
+    mma_a_tileT(sc, ka, sQ, lane);    // S^T  = K Q^T   [16 keys x 64 queries]
+    mma_a_tileT(dp, va, sdO, lane);   // dP^T = V dO^T
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int qc = nt * 8 + 2 * t;
+      const float l0 = s_lse[st * 64 + qc], l1 = s_lse[st * 64 + qc + 1];
+      const float d0 = s_delta[st * 64 + qc], d1 = s_delta[st * 64 + qc + 1];
+      float p0 = key_ok0 ? exp2f(sc[nt][0] * p.scale_log2 - l0) : 0.f;
+      float p1 = key_ok0 ? exp2f(sc[nt][1] * p.scale_log2 - l1) : 0.f;
+      float p2 = key_ok1 ? exp2f(sc[nt][2] * p.scale_log2 - l0) : 0.f;
+      float p3 = key_ok1 ? exp2f(sc[nt][3] * p.scale_log2 - l1) : 0.f;
+      sc[nt][0] = p0; sc[nt][1] = p1; sc[nt][2] = p2; sc[nt][3] = p3;
+      dp[nt][0] = p0 * (dp[nt][0] - d0);
+      dp[nt][1] = p1 * (dp[nt][1] - d1);
+      dp[nt][2] = p2 * (dp[nt][2] - d0);
+      dp[nt][3] = p3 * (dp[nt][3] - d1);
+    }
+    uint32_t pa[4][4], dsa[4][4];
+    c_to_a(pa, sc);
+    c_to_a(dsa, dp);
+    mma_a_tile(dv, pa, sdO, lane);    // dV += P^T dO
+    mma_a_tile(dk, dsa, sQ, lane);    // dK += dS^T Q
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  // write dK (x scale) and dV
+  bf16* dkg = p.dqkv + img_row * p.dld + p.C + head * 64;
+  bf16* dvg = p.dqkv + img_row * p.dld + 2 * p.C + head * 64;
+  const int r0 = key0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    if (r0 < p.S) {
+      *reinterpret_cast<uint32_t*>(dkg + (size_t)r0 * p.dld + c) = pack_bf16x2(dk[nt][0] * p.scale, dk[nt][1] * p.scale);
+      *reinterpret_cast<uint32_t*>(dvg + (size_t)r0 * p.dld + c) = pack_bf16x2(dv[nt][0], dv[nt][1]);
+    }
+    if (r1 < p.S) {
+      *reinterpret_cast<uint32_t*>(dkg + (size_t)r1 * p.dld + c) = pack_bf16x2(dk[nt][2] * p.scale, dk[nt][3] * p.scale);
+      *reinterpret_cast<uint32_t*>(dvg + (size_t)r1 * p.dld + c) = pack_bf16x2(dv[nt][2], dv[nt][3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dQ of one 64-query block: warp w owns queries [16w, 16w+16); loop over the key blocks
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem), sdO = sQ + kBwdTileBytes;
+  const uint32_t sK0 = sdO + kBwdTileBytes;          // 2 stages x (K, V)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * kBwdTile, head = blockIdx.y, img = blockIdx.z;
+  const size_t img_row = (size_t)img * p.S;
+  const bf16* qg = p.qkv + img_row * p.ld + head * 64;
+  const bf16* kg = qg + p.C;
+  const bf16* vg = qg + 2 * p.C;
+  const bf16* dog = p.dout + img_row * p.dout_ld + head * 64;
+  const int n_k = (p.S + kBwdTile - 1) / kBwdTile;
+
+  auto load_kv = [&](int st, int it) {
+    load_tile(sK0 + (uint32_t)st * 2 * kBwdTileBytes, kg, p.ld, it * kBwdTile, p.S, tid);
+    load_tile(sK0 + (uint32_t)st * 2 * kBwdTileBytes + kBwdTileBytes, vg, p.ld, it * kBwdTile, p.S, tid);
+  };
+  load_tile(sQ, qg, p.ld, q0, p.S, tid);
+  load_tile(sdO, dog, p.dout_ld, q0, p.S, tid);
+  load_kv(0, 0);
+  cp_async_commit();
+
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  const float* lse_g = p.lse + ((size_t)img * p.heads + head) * p.S;
+  const float* delta_g = p.delta + ((size_t)img * p.heads + head) * p.S;
+  const float l0 = r0 < p.S ? lse_g[r0] : INFINITY, l1 = r1 < p.S ? lse_g[r1] : INFINITY;
+  const float d0 = r0 < p.S ? delta_g[r0] : 0.f, d1 = r1 < p.S ? delta_g[r1] : 0.f;
+
+  uint32_t qa[4][4], doa[4][4];
+  float dq[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+
+  for (int it = 0; it < n_k; ++it) {
+    const int st = it & 1;
+    if (it + 1 < n_k) load_kv(st ^ 1, it + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (it == 0) {
+      load_a_frags(qa, sQ, warp * 16, lane);
+      load_a_frags(doa, sdO, warp * 16, lane);
+    }
+    const uint32_t sK = sK0 + (uint32_t)st * 2 * kBwdTileBytes, sV = sK + kBwdTileBytes;
+    float sc[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sc[i][j] = dp[i][j] = 0.f;
+    mma_a_tileT(sc, qa, sK, lane);    // S  = Q K^T   [16 queries x 64 keys]
+    mma_a_tileT(dp, doa, sV, lane);   // dP = dO V^T
+    const int kbase = it * kBwdTile;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int kc = kbase + nt * 8 + 2 * t;
+      const bool k0ok = kc < p.S, k1ok = kc + 1 < p.S;
+      const float p0 = k0ok ? exp2f(sc[nt][0] * p.scale_log2 - l0) : 0.f;
+      const float p1 = k1ok ? exp2f(sc[nt][1] * p.scale_log2 - l0) : 0.f;
+      const float p2 = k0ok ? exp2f(sc[nt][2] * p.scale_log2 - l1) : 0.f;
+      const float p3 = k1ok ? exp2f(sc[nt][3] * p.scale_log2 - l1) : 0.f;
+      dp[nt][0] = p0 * (dp[nt][0] - d0);
+      dp[nt][1] = p1 * (dp[nt][1] - d0);
+      dp[nt][2] = p2 * (dp[nt][2] - d1);
+      dp[nt][3] = p3 * (dp[nt][3] - d1);
+    }
+    uint32_t dsa[4][4];
+    c_to_a(dsa, dp);
+    mma_a_tile(dq, dsa, sK, lane);    // dQ += dS K
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  bf16* dqg = p.dqkv + img_row * p.dld + head * 64;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    if (r0 < p.S) *reinterpret_cast<uint32_t*>(dqg + (size_t)r0 * p.dld + c) = pack_bf16x2(dq[nt][0] * p.scale, dq[nt][1] * p.scale);
+    if (r1 < p.S) *reinterpret_cast<uint32_t*>(dqg + (size_t)r1 * p.dld + c) = pack_bf16x2(dq[nt][2] * p.scale, dq[nt][3] * p.scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// temporal attention backward: one warp per (batch, pixel, head); rows (b*F + f)*HW + s
+// ------------------------------------------------------------------------------------------------------------
+struct TAttnBwdParams {
+  const bf16* qkv;
+  int ld;
+  const bf16* dout;
+  int dout_ld;
+  bf16* dqkv;
+  int dld;
+  int B, F, HW, heads, C;
+  float scale, scale_log2;
+  int warps_per_cta;
+};
+
+constexpr int kTStride = 65;  // fp32 row stride of the per-warp q/k/v/dO copies: conflict-free column walks
+
+__global__ void attn_temporal_bwd_kernel(const TAttnBwdParams p) {
+  extern __shared__ __align__(16) float tsm[];
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const long long w = (long long)blockIdx.x * p.warps_per_cta + wl;
+  const long long total = (long long)p.B * p.HW * p.heads;
+  if (w >= total) return;   // whole warps only; no block-wide barriers below
+  const int F = p.F;
+  const int head = (int)(w % p.heads);
+  const long long bs = w / p.heads;
+  const int s = (int)(bs % p.HW);
+  const int b = (int)(bs / p.HW);
+  float* base = tsm + (size_t)wl * (4 * F * kTStride + 2 * F * F);
+  float* sq = base;
+  float* sk = sq + F * kTStride;
+  float* sv = sk + F * kTStride;
+  float* sdo = sv + F * kTStride;
+  float* sp = sdo + F * kTStride;   // [F][F] probabilities
+  float* sds = sp + F * F;          // [F][F] dP, then dS
+  const size_t row0 = (size_t)b * F * p.HW + s;
+  for (int f = 0; f < F; ++f) {
+    const size_t row = row0 + (size_t)f * p.HW;
+    const bf16* r = p.qkv + row * p.ld + head * 64 + 2 * lane;
+    const float2 q = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(r));
+    const float2 k = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(r + p.C));
+    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(r + 2 * p.C));
+    const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.dout + row * p.dout_ld + head * 64 + 2 * lane));
+    sq[f * kTStride + 2 * lane] = q.x; sq[f * kTStride + 2 * lane + 1] = q.y;
+    sk[f * kTStride + 2 * lane] = k.x; sk[f * kTStride + 2 * lane + 1] = k.y;
+    sv[f * kTStride + 2 * lane] = v.x; sv[f * kTStride + 2 * lane + 1] = v.y;
+    sdo[f * kTStride + 2 * lane] = d.x; sdo[f * kTStride + 2 * lane + 1] = d.y;
+  }
+  __syncwarp();
+  // S = Q K^T and dP = dO V^T
+  for (int e = lane; e < F * F; e += 32) {
+    const int i = e / F, j = e - i * F;
+    float a = 0.f, c = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 64; ++d) {
+      a = fmaf(sq[i * kTStride + d], sk[j * kTStride + d], a);
+      c = fmaf(sdo[i * kTStride + d], sv[j * kTStride + d], c);
+    }
+    sp[e] = a;
+    sds[e] = c;
+  }
+  __syncwarp();
+  // row softmax, then dS = P o (dP - sum_j P dP) * scale
+  for (int i = 0; i < F; ++i) {
+    const float sv_ = lane < F ? sp[i * F + lane] : -INFINITY;
+    const float m = warp_max(sv_);
+    const float e = lane < F ? exp2f((sv_ - m) * p.scale_log2) : 0.f;
+    const float l = warp_sum(e);
+    const float pr = e / l;
+    const float dpv = lane < F ? sds[i * F + lane] : 0.f;
+    const float dl = warp_sum(pr * dpv);
+    if (lane < F) {
+      sp[i * F + lane] = pr;
+      sds[i * F + lane] = pr * (dpv - dl) * p.scale;
+    }
+  }
+  __syncwarp();
+  // dQ_i = sum_j dS_ij K_j ; dK_j = sum_i dS_ij Q_i ; dV_j = sum_i P_ij dO_i   (lane owns head dims 2*lane, 2*lane+1)
+  const int c0 = 2 * lane;
+  for (int f = 0; f < F; ++f) {
+    float q0 = 0.f, q1 = 0.f, k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int j = 0; j < F; ++j) {
+      const float ds_fj = sds[f * F + j], ds_jf = sds[j * F + f], p_jf = sp[j * F + f];
+      q0 = fmaf(ds_fj, sk[j * kTStride + c0], q0);
+      q1 = fmaf(ds_fj, sk[j * kTStride + c0 + 1], q1);
+      k0 = fmaf(ds_jf, sq[j * kTStride + c0], k0);
+      k1 = fmaf(ds_jf, sq[j * kTStride + c0 + 1], k1);
+      v0 = fmaf(p_jf, sdo[j * kTStride + c0], v0);
+      v1 = fmaf(p_jf, sdo[j * kTStride + c0 + 1], v1);
+    }
+    bf16* o = p.dqkv + (row0 + (size_t)f * p.HW) * p.dld + head * 64 + c0;
+    *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(q0, q1);
+    *reinterpret_cast<uint32_t*>(o + p.C) = pack_bf16x2(k0, k1);
+    *reinterpret_cast<uint32_t*>(o + 2 * p.C) = pack_bf16x2(v0, v1);
+  }
+}
+
+}  // namespace pt
+
+using namespace pt;
+
+extern "C" int pt_attention_delta(const void* out, int32_t out_ld, const void* dout, int32_t dout_ld, float* delta, int64_t rows,
+                                  int32_t S, int32_t heads, void* stream) {
+  PT_CHECK_ARG(out && dout && delta && rows > 0 && S > 0 && heads > 0 && rows % S == 0, "pt_attention_delta: bad argument");
+  PT_CHECK_ARG(out_ld % 2 == 0 && dout_ld % 2 == 0, "pt_attention_delta: row strides must be even");
+  const long long warps = (long long)rows * heads;
+  pt_launch(attn_delta_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, stream, 1, reinterpret_cast<const bf16*>(out), (int)out_ld,
+            reinterpret_cast<const bf16*>(dout), (int)dout_ld, delta, (long long)rows, (int)S, (int)heads);
+  return pt_launched("pt_attention_delta");
+}
+
+extern "C" int pt_attention_spatial_bwd(const PtAttnSpatialBwdArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->qkv && a->dout && a->lse && a->delta && a->dqkv, "pt_attention_spatial_bwd: null argument");
+  PT_CHECK_ARG(a->S > 0 && a->heads > 0 && a->n_img > 0 && a->C == a->heads * 64, "pt_attention_spatial_bwd: need C == heads*64");
+  PT_CHECK_ARG(a->ld % 8 == 0 && a->dout_ld % 8 == 0 && a->dld % 2 == 0, "pt_attention_spatial_bwd: row strides must be multiples of 8");
+  AttnBwdParams p;
+  p.qkv = reinterpret_cast<const bf16*>(a->qkv); p.ld = a->ld;
+  p.dout = reinterpret_cast<const bf16*>(a->dout); p.dout_ld = a->dout_ld;
+  p.lse = a->lse; p.delta = a->delta;
+  p.dqkv = reinterpret_cast<bf16*>(a->dqkv); p.dld = a->dld;
+  p.S = a->S; p.heads = a->heads; p.C = a->C;
+  p.scale = 0.125f; p.scale_log2 = 0.125f * kLog2e;
+  const size_t smem = 6 * kBwdTileBytes + 4 * 64 * sizeof(float);
+  static bool attr_set[PT_MAX_DEVICES] = {false};
+  const int dev_slot = pt_device_slot();
+  if (!attr_set[dev_slot]) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pt_fail(e, "pt_attention_spatial_bwd: cudaFuncSetAttribute");
+    attr_set[dev_slot] = true;
+  }
+  dim3 grid((a->S + kBwdTile - 1) / kBwdTile, a->heads, a->n_img);
+  pt_launch(attn_bwd_dkv_kernel, grid, dim3(128), smem, stream, 1, p);
+  int rc = pt_launched("pt_attention_spatial_bwd (dK, dV)");
+  if (rc != 0) return rc;
+  pt_launch(attn_bwd_dq_kernel, grid, dim3(128), smem, stream, 1, p);
+  return pt_launched("pt_attention_spatial_bwd (dQ)");
+}
+
+extern "C" int pt_attention_temporal_bwd(const PtAttnTemporalBwdArgs* a, void* stream) {
+  PT_CHECK_ARG(a != nullptr && a->qkv && a->dout && a->dqkv, "pt_attention_temporal_bwd: null argument");
+  PT_CHECK_ARG(a->B > 0 && a->F > 0 && a->F <= 32 && a->HW > 0 && a->heads > 0 && a->C == a->heads * 64,
+               "pt_attention_temporal_bwd: need C == heads*64 and 1 <= F <= 32");
+  PT_CHECK_ARG(a->ld % 2 == 0 && a->dout_ld % 2 == 0 && a->dld % 2 == 0, "pt_attention_temporal_bwd: row strides must be even");
+  TAttnBwdParams p;
+  p.qkv = reinterpret_cast<const bf16*>(a->qkv); p.ld = a->ld;
+  p.dout = reinterpret_cast<const bf16*>(a->dout); p.dout_ld = a->dout_ld;
+  p.dqkv = reinterpret_cast<bf16*>(a->dqkv); p.dld = a->dld;
+  p.B = a->B; p.F = a->F; p.HW = a->HW; p.heads = a->heads; p.C = a->C;
+  p.scale = 0.125f; p.scale_log2 = 0.125f * kLog2e;
+  const size_t per_warp = (size_t)(4 * a->F * kTStride + 2 * a->F * a->F) * sizeof(float);
+  int wpc = (int)((size_t)96 * 1024 / per_warp);
+  if (wpc > 8) wpc = 8;
+  if (wpc < 1) wpc = 1;
+  p.warps_per_cta = wpc;
+  const size_t smem = per_warp * wpc;
+  static int attr_smem[PT_MAX_DEVICES] = {0};
+  const int dev_slot = pt_device_slot();
+  if ((int)smem > attr_smem[dev_slot]) {
+    cudaError_t e = cudaFuncSetAttribute(attn_temporal_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pt_fail(e, "pt_attention_temporal_bwd: cudaFuncSetAttribute");
+    attr_smem[dev_slot] = (int)smem;
+  }
+  const long long warps = (long long)a->B * a->HW * a->heads;
+  pt_launch(attn_temporal_bwd_kernel, dim3((unsigned)((warps + wpc - 1) / wpc)), dim3(32 * wpc), smem, stream, 1, p);
+  return pt_launched("pt_attention_temporal_bwd");
+}

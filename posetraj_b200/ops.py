@@ -453,7 +453,7 @@ class LayerNorm(_Op):
 class AttnSpatial(_Op):
     fn_name = "pt_attention_spatial"
 
-    def __init__(self, qkv, out, *, n_img, heads, name=None):
+    def __init__(self, qkv, out, *, n_img, heads, name=None, lse: Optional[torch.Tensor] = None):
         rows, c3 = qkv.shape
         Cc = c3 // 3
         S = rows // n_img
@@ -464,10 +464,13 @@ class AttnSpatial(_Op):
         a.tmap_qkv = C.addressof(self.tm)
         a.out, a.out_ld = out.data_ptr(), out.stride(0)
         a.S, a.heads, a.C, a.n_img = S, heads, Cc, n_img
+        if lse is not None:   # training: keep the per-row log-sum-exp for pt_attention_spatial_bwd
+            assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == n_img * heads * S
+            a.lse = lse.data_ptr()
         self.kind = "attn_spatial"
         self.alg_flops = 4.0 * S * S * 64 * heads * n_img
         self.alg_bytes = 4.0 * rows * Cc * 2
-        self._finish(a, (qkv, out), name)
+        self._finish(a, (qkv, out, lse), name)
 
 
 class AttnTemporal(_Op):

@@ -533,3 +533,118 @@ class AdamW:
             a.grad_scale = 1.0 / self.b.world
             a.step = self.step_count
             _lib.check(_lib.lib().pt_adamw(C.addressof(a), _sp()), "pt_adamw")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole-network backward: the remaining operators (csrc/train_attn.cu, csrc/train_misc.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def attention_spatial_backward(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, *, n_img: int,
+                               heads: int) -> torch.Tensor:
+    """d(Q | K | V) of the per-image self-attention (oracle/backward.py attention_backward); `lse` is what the forward
+    kernel wrote (ops.AttnSpatial(lse=...)), `out` its output."""
+    _check(qkv, BF16), _check(out, BF16), _check(dout, BF16), _check(lse, F32)
+    rows, c3 = qkv.shape
+    Cc, S = c3 // 3, rows // n_img
+    delta = torch.empty(n_img * heads * S, device=qkv.device, dtype=F32)
+    _lib.check(_lib.lib().pt_attention_delta(out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0), delta.data_ptr(), rows, S,
+                                             heads, _sp()), "pt_attention_delta")
+    dqkv = torch.empty(rows, c3, device=qkv.device, dtype=BF16)
+    a = _lib.PtAttnSpatialBwdArgs()
+    a.qkv, a.ld, a.dout, a.dout_ld = qkv.data_ptr(), qkv.stride(0), dout.data_ptr(), dout.stride(0)
+    a.lse, a.delta, a.dqkv, a.dld = lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), dqkv.stride(0)
+    a.S, a.heads, a.C, a.n_img = S, heads, Cc, n_img
+    _lib.check(_lib.lib().pt_attention_spatial_bwd(C.addressof(a), _sp()), "pt_attention_spatial_bwd")
+    return dqkv
+
+
+def attention_temporal_backward(qkv: torch.Tensor, dout: torch.Tensor, *, batch: int, frames: int, hw: int, heads: int) -> torch.Tensor:
+    _check(qkv, BF16), _check(dout, BF16)
+    dqkv = torch.empty_like(qkv)
+    a = _lib.PtAttnTemporalBwdArgs()
+    a.qkv, a.ld, a.dout, a.dout_ld, a.dqkv, a.dld = qkv.data_ptr(), qkv.stride(0), dout.data_ptr(), dout.stride(0), dqkv.data_ptr(), dqkv.stride(0)
+    a.B, a.F, a.HW, a.heads, a.C = batch, frames, hw, heads, qkv.shape[1] // 3
+    _lib.check(_lib.lib().pt_attention_temporal_bwd(C.addressof(a), _sp()), "pt_attention_temporal_bwd")
+    return dqkv
+
+
+def upsample_backward(dout: torch.Tensor, *, n: int, H: int, W: int, halo: bool, scale: int) -> torch.Tensor:
+    """Gradient of ops.Upsample2x: compact [n*H*W, C] from the (haloed) scale x scale output gradient."""
+    _check(dout, BF16)
+    dx = torch.empty(n * H * W, dout.shape[1], device=dout.device, dtype=BF16)
+    a = _lib.PtUpsampleArgs()
+    a.x, a.ld, a.out, a.out_ld = dx.data_ptr(), dx.stride(0), dout.data_ptr(), dout.stride(0)
+    a.n, a.H, a.W, a.C, a.halo, a.scale = n, H, W, dout.shape[1], int(halo), scale
+    _lib.check(_lib.lib().pt_upsample2x_bwd(C.addressof(a), _sp()), "pt_upsample2x_bwd")
+    return dx
+
+
+def dilate2x(src: torch.Tensor, *, n: int, H: int, W: int, src_halo: bool) -> torch.Tensor:
+    """stride-2 conv output gradient -> zero-haloed [n*(H+1)*(W+1), C] rows of the conv's INPUT space."""
+    _check(src, BF16)
+    dst = torch.empty(n * (H + 1) * (W + 1), src.shape[1], device=src.device, dtype=BF16)
+    _lib.check(_lib.lib().pt_dilate2x(src.data_ptr(), src.stride(0), int(src_halo), dst.data_ptr(), dst.stride(0), n, H, W, src.shape[1],
+                                      _sp()), "pt_dilate2x")
+    return dst
+
+
+def zero_halo(x: torch.Tensor, *, n: int, H: int, W: int) -> torch.Tensor:
+    _check(x, BF16)
+    assert x.shape[0] == n * (H + 1) * (W + 1)
+    _lib.check(_lib.lib().pt_zero_halo(x.data_ptr(), x.stride(0), n, H, W, x.shape[1], _sp()), "pt_zero_halo")
+    return x
+
+
+def silu_forward(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _check(x, BF16)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.lib().pt_silu_fwd(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1], _sp()), "pt_silu_fwd")
+    return out
+
+
+def silu_backward(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    _check(x, BF16), _check(dy, BF16)
+    dx = torch.empty_like(x)
+    _lib.check(_lib.lib().pt_silu_bwd(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), dx.data_ptr(), dx.stride(0), x.shape[0],
+                                      x.shape[1], _sp()), "pt_silu_bwd")
+    return dx
+
+
+def small_linear_backward(x: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, *, act_in_silu: bool = False, want_dx: bool = True,
+                          dw: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None, accumulate_w: bool = False,
+                          dx: Optional[torch.Tensor] = None, accumulate_dx: bool = False):
+    """Backward of ops.SmallLinear (no output activation): returns (dx | None, dw, db) in fp32."""
+    _check(x, F32), _check(w, BF16), _check(dy, F32)
+    M, K = x.shape
+    N = w.shape[0]
+    assert dy.shape == (M, N) and w.shape[1] == K
+    if dw is None:
+        dw = torch.empty(N, K, device=x.device, dtype=F32)
+        db = torch.empty(N, device=x.device, dtype=F32)
+        accumulate_w = False
+    if want_dx and dx is None:
+        dx = torch.empty(M, K, device=x.device, dtype=F32)
+        accumulate_dx = False
+    a = _lib.PtSmallLinearBwdArgs()
+    a.x, a.x_ld, a.w, a.w_ld, a.dy, a.dy_ld = x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), dy.data_ptr(), dy.stride(0)
+    a.M, a.N, a.K, a.act_in_silu = M, N, K, int(act_in_silu)
+    if want_dx:
+        a.dx, a.dx_ld, a.accumulate_dx = dx.data_ptr(), dx.stride(0), int(accumulate_dx)
+    a.dw, a.db, a.accumulate_w = dw.data_ptr(), (db.data_ptr() if db is not None else None), int(accumulate_w)
+    _lib.check(_lib.lib().pt_small_linear_bwd(C.addressof(a), _sp()), "pt_small_linear_bwd")
+    return (dx if want_dx else None), dw, db
+
+
+def colsum_grouped(x: torch.Tensor, *, groups: int, mode: int, ga: int, gb: int = 1, gc: int = 1, scale: float = 1.0,
+                   out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """fp32 [groups, C] sums of bf16 rows by group (PtColsumGroupedArgs: mode 1 r/ga, 2 the rowvec_mode-2 map, 3 (r/ga)%gc)."""
+    _check(x, BF16)
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.zeros(groups, Cc, device=x.device, dtype=F32)
+        accumulate = False
+    ws = torch.empty(_lib.lib().pt_colsum_grouped_workspace_bytes(rows, groups, Cc), device=x.device, dtype=torch.uint8)
+    a = _lib.PtColsumGroupedArgs()
+    a.x, a.ld, a.rows, a.C, a.groups, a.mode, a.ga, a.gb, a.gc = x.data_ptr(), x.stride(0), rows, Cc, groups, mode, ga, gb, gc
+    a.scale, a.out, a.out_ld, a.accumulate, a.workspace = scale, out.data_ptr(), out.stride(0), int(accumulate), ws.data_ptr()
+    _lib.check(_lib.lib().pt_colsum_grouped(C.addressof(a), _sp()), "pt_colsum_grouped")
+    return out
