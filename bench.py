@@ -537,6 +537,62 @@ def train_dp_leg(cfg, dev, rank, world, barrier):
     return res
 
 
+def train_step_leg(cfg, unet, dev, rank, world, barrier, steps=3):
+    """BASELINE.json configs[3]: controlnet_sdv_bbox pre-training step, data-parallel, 2 videos per rank (global batch 16 on
+    8 GPUs) x 14 frames x 320x576 — the WHOLE step of scripts/train_svd_traj_VIPSeg_14_cam_concat.py:1404-1475 on the CUDA
+    library (posetraj_b200/train_engine.py): bbox ControlNet forward, frozen UNet forward, EDM loss, the one-frame
+    "spatial" pass, the reverse pass through both networks (tcgen05 dgrad / wgrad, attention backward ...), per-bucket
+    NCCL all-reduce overlapped with the reverse pass, fused AdamW, re-derivation of the bf16 kernel weights."""
+    import torch
+    from posetraj_b200.models import ControlNetSDVModel
+    from posetraj_b200.train_engine import ControlNetTrainer
+    B, Fr, H, W = 2, FRAMES, LAT_H, LAT_W
+    cnet = ControlNetSDVModel.from_random(cfg, dev, seed=5, bbox=True, faithful_zero_init=False)
+    torch.cuda.reset_peak_memory_stats(dev)
+    tr = ControlNetTrainer(unet, cnet, batch=B, frames=Fr, height=H, width=W, lr=1e-5)
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    batch = dict(latents=rn(B, Fr, 4, H, W) * 0.9, noise=rn(B, Fr, 4, H, W), sigmas=torch.tensor([1.3, 0.4], device=dev),
+                 image_embeddings=rn(B, 1, cfg.cross_attention_dim),
+                 trajectories=(torch.rand(B, Fr, 3, 8 * H, 8 * W, device=dev, generator=g) > 0.97).float() * 2 - 1,
+                 motion_values=torch.tensor([127.0, 90.0], device=dev),
+                 controlnet_bbox=(torch.rand(B, Fr, 3, 8 * H, 8 * W, device=dev, generator=g) > 0.98).float() * 2 - 1)
+    losses = [float(tr.step(ran_idx=3, **batch))]           # warm-up (TMA descriptors, attribute caches, NCCL)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * steps + 1)]
+    lc0 = int(_lib_launches())
+    ev[0].record()
+    for i in range(steps):
+        loss = tr.forward_backward(ran_idx=3, **batch)
+        ev[3 * i + 1].record()
+        tr.optimizer_step()
+        ev[3 * i + 2].record()
+        ev[3 * i + 3].record()
+        losses.append(loss.clone())                          # (device copy; read after the timed region)
+    barrier()
+    launches = (int(_lib_launches()) - lc0) / steps
+    ms_step = _max_over_ranks(ev[0].elapsed_time(ev[3 * steps]) / steps, dev, world)
+    ms_fb = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(steps)) / steps
+    ms_tail = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(steps)) / steps
+    losses = [float(x) for x in losses]
+    res = {"workload": "configs[3]: controlnet_sdv_bbox training step (ControlNet + frozen UNet forward, EDM loss + one-frame "
+                       "spatial pass, reverse pass, all-reduce, AdamW), 2 videos x 14 frames x 320x576 per GPU, data-parallel",
+           "ms_per_step": ms_step, "value": 1000.0 * B * world / ms_step, "unit": "videos/s (global batch %d)" % (B * world),
+           "forward_backward_ms": ms_fb, "allreduce_wait_adamw_refresh_ms": ms_tail,
+           "kernel_launches_per_step": launches, "losses": losses[:4],
+           "loss_decreases": bool(losses[-1] < losses[0]),
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+           "params_trained": int(sum(tr.buckets.sizes)), "dtype": "bf16 activations / gradients, fp32 master weights + AdamW"}
+    del tr, cnet
+    torch.cuda.empty_cache()
+    return res
+
+
+def _lib_launches():
+    from posetraj_b200 import _lib
+    return _lib.lib().pt_launch_count()
+
+
 def library_baseline_leg(dev, steps=3):
     """The "library bar": the oracle's wiring as plain torch eager bf16 on this GPU (cuDNN / cuBLAS / SDPA, no fusion) —
     what the reference would run here, since it ships no Blackwell kernel.  Comparator only (imports oracle/)."""
@@ -734,6 +790,7 @@ def run_own(args):
 
         leg("configs2_cam", cam_leg, cfg, unet, dev, rank, world, leg_steps, barrier)
         leg("configs3_train_blocks", train_dp_leg, cfg, dev, rank, world, barrier)
+        leg("configs3_train_step", train_step_leg, cfg, unet, dev, rank, world, barrier)
         if world >= 2 and world % 2 == 0:
             leg("cfg_split", cfg_split_leg, cfg, unet, cnet, dev, rank, world, leg_steps, barrier, ms_per_step,
                 lat_final if rank == 0 else None)

@@ -69,7 +69,7 @@ def add_time_ids(fps, motion_bucket_ids: torch.Tensor, noise_aug_strength, batch
     m = motion_bucket_ids.reshape(-1, 1).to(torch.float32)
     if m.shape[0] != batch_size:
         raise ValueError("The length of motion_bucket_ids must match the batch_size.")
-    base = torch.tensor([fps, noise_aug_strength], dtype=torch.float32).repeat(batch_size, 1)
+    base = torch.tensor([fps, noise_aug_strength], dtype=torch.float32, device=m.device).repeat(batch_size, 1)
     return torch.cat([base, m], dim=1)
 
 
@@ -95,7 +95,7 @@ def training_step(unet, controlnet, *, latents: torch.Tensor, noise: torch.Tenso
     s = sigmas.reshape(b, 1, 1, 1, 1)
     cond = (latents + noise * TRAIN_NOISE_AUG)[:, 0] / scaling_factor
     noisy = latents + noise * s
-    timesteps = torch.tensor([0.25 * float(x.log()) for x in sigmas])
+    timesteps = torch.tensor([0.25 * float(x.log()) for x in sigmas], device=sigmas.device)
     inp = noisy / ((s ** 2 + 1) ** 0.5)
     ehs = image_embeddings
     ids = add_time_ids(6, motion_values, TRAIN_NOISE_AUG, b)

@@ -47,6 +47,8 @@ class WeightStore:
         self.sd = state_dict
         self.device = device
         self._cache: Dict[tuple, torch.Tensor] = {}
+        self._makers: Dict[tuple, object] = {}
+        self._origin: Dict[int, tuple] = {}     # data_ptr of a kernel-ready tensor -> (kind, key)
 
     def has(self, key: str) -> bool:
         return key in self.sd
@@ -63,10 +65,27 @@ class WeightStore:
         k = (kind, key)
         if k not in self._cache:
             self._cache[k] = fn()
+            self._makers[k] = fn
+            self._origin[self._cache[k].data_ptr()] = k
         return self._cache[k]
 
+    def origin(self, t: torch.Tensor) -> tuple:
+        """(kind, key) of a kernel-ready tensor handed out by this store (training: where a weight gradient belongs)."""
+        return self._origin[t.data_ptr()]
+
+    def refresh(self) -> None:
+        """Re-derive every kernel-ready tensor IN PLACE from the (updated) state dict: pointers and TMA descriptors built
+        on them stay valid (training: after each optimizer step)."""
+        for k, fn in self._makers.items():
+            self._cache[k].copy_(fn())
+
     def f32(self, key: str) -> torch.Tensor:
-        return self._memo("f32", key, lambda: self._get(key).to(F32).contiguous())
+        def make():
+            t = self._get(key).to(F32).contiguous()
+            # the kernels read these vectors 16 bytes at a time; a training state dict holds views into the optimizer's
+            # flat master buffers at arbitrary element offsets
+            return t.clone() if t.data_ptr() % 16 else t
+        return self._memo("f32", key, make)
 
     def linear(self, key: str) -> torch.Tensor:
         """[N, K] bf16 — nn.Linear weights are already K-major."""
@@ -115,10 +134,11 @@ class WeightStore:
 class Pool:
     """Reuses activation buffers between ops of one in-order op list."""
 
-    def __init__(self, device):
+    def __init__(self, device, reuse: bool = True):
         self.device = device
         self.free = defaultdict(list)
         self.bytes = 0
+        self.reuse = reuse   # False (training): every activation stays alive for the backward pass
 
     def get(self, rows: int, cols: int, dtype=BF16) -> torch.Tensor:
         key = (rows, cols, dtype)
@@ -129,6 +149,8 @@ class Pool:
         return t
 
     def put(self, *ts) -> None:
+        if not self.reuse:
+            return
         for t in ts:
             if t is not None and not getattr(t, "_pt_no_pool", False):   # peer-mapped exchange buffers are dedicated
                 self.free[(t.shape[0], t.shape[1], t.dtype)].append(t)
@@ -141,9 +163,13 @@ class NetPlan:
                  width: int, device, cam: bool = False, bbox: bool = False, cond_hw: Optional[tuple] = None,
                  sigmas: Optional[torch.Tensor] = None, step_index: Optional[torch.Tensor] = None,
                  x_in: Optional[torch.Tensor] = None, residual_bufs: Optional[List[torch.Tensor]] = None,
-                 ctx_batch: Optional[int] = None, row_offset: int = 0):
+                 ctx_batch: Optional[int] = None, row_offset: int = 0, train: bool = False):
         assert kind in ("unet", "controlnet")
         self.kind, self.cfg, self.w = kind, cfg, weights
+        # train=True (posetraj_b200.train_engine, BASELINE configs[3]): no buffer reuse, pre-activations kept (GEGLU / SiLU as
+        # separate passes, attention log-sum-exp written), parameter-dependent constants re-evaluated every step
+        self.train = train
+        self.alpha_updaters: List = []   # (mix_factor key, fn(alpha)) of every AlphaBlender baked into launch arguments
         self.B, self.F, self.H, self.W = batch, frames, height, width
         self.n = batch * frames
         # CFG-branch sharding: this plan computes rows [row_offset, row_offset + batch) of a call whose
@@ -155,7 +181,7 @@ class NetPlan:
             raise ValueError("row_offset + batch exceeds ctx_batch")
         self.device = device
         self.cam, self.bbox = cam, bbox
-        self.pool = Pool(device)
+        self.pool = Pool(device, reuse=not train)
         self.step_ops: List = []    # every denoise step
         self.embed_ops: List = []   # when encoder_hidden_states / added_time_ids change
         self.cond_ops: List = []    # when controlnet_cond / camera_cond change (ControlNet only)
@@ -234,17 +260,19 @@ class NetPlan:
             self.step_ops.append(ops.SinCos(self.t_sin, sigmas=self.sigmas, step_index=self.step_index, name="time_proj"))
         else:
             self.step_ops.append(ops.SinCos(self.t_sin, t=self.t_buf, name="time_proj"))
+        # training keeps the pre-activation: SiLU moves from the producer's output to the consumer's input (same function)
+        tr = self.train
         self.step_ops.append(ops.SmallLinear(self.t_sin, w.linear("time_embedding.linear_1.weight"), self.t_h,
-                                             w.f32("time_embedding.linear_1.bias"), act_out_silu=True, name="time_embedding.1"))
+                                             w.f32("time_embedding.linear_1.bias"), act_out_silu=not tr, name="time_embedding.1"))
         self.step_ops.append(ops.SmallLinear(self.t_h, w.linear("time_embedding.linear_2.weight"), self.emb,
-                                             w.f32("time_embedding.linear_2.bias"), name="time_embedding.2"))
+                                             w.f32("time_embedding.linear_2.bias"), act_in_silu=tr, name="time_embedding.2"))
         # added_time_ids: Timesteps(256) of the flattened ids -> [B, 768] -> add_embedding (controlnet_sdv.py:577-581)
         self.step_ops.append(ops.SinCos(self.a_sin, t=self.time_ids, name="add_time_proj"))
         a_in = self.a_sin.view(B, 3 * cfg.addition_time_embed_dim)
         self.step_ops.append(ops.SmallLinear(a_in, w.linear("add_embedding.linear_1.weight"), self.a_h,
-                                             w.f32("add_embedding.linear_1.bias"), act_out_silu=True, name="add_embedding.1"))
+                                             w.f32("add_embedding.linear_1.bias"), act_out_silu=not tr, name="add_embedding.1"))
         self.step_ops.append(ops.SmallLinear(self.a_h, w.linear("add_embedding.linear_2.weight"), self.emb,
-                                             w.f32("add_embedding.linear_2.bias"), accumulate=True, name="add_embedding.2"))
+                                             w.f32("add_embedding.linear_2.bias"), act_in_silu=tr, accumulate=True, name="add_embedding.2"))
         # all time_emb_proj(silu(emb)) of the network in one GEMV
         w_all = w.cat_rows(self.temb_keys, "bf16")
         b_all = w.cat_rows([k[: -len("weight")] + "bias" for k in self.temb_keys], "f32")
@@ -288,6 +316,12 @@ class NetPlan:
         Cc = x.shape[1]
         w1, b1 = w.linear(prefix + "net.0.proj.weight"), w.f32(prefix + "net.0.proj.bias")
         w2, b2 = w.linear(prefix + "net.2.weight"), w.f32(prefix + "net.2.bias")
+        if self.train:
+            f0 = self._gemm(x, w1, 8 * Cc, bias=b1, name=name + ".proj")
+            f1 = self.pool.get(x.shape[0], 4 * Cc)
+            self.step_ops.append(ops.GegluFwd(f0, f1, name=name + ".geglu"))
+            return self._gemm(f1, w2, Cc, bias=b2, acc_scale=acc_scale, res1=res1, res1_scale=res1_scale, res2=res2,
+                              res2_scale=res2_scale, name=name + ".out")
         if FUSED_MLP and ops.FusedMlp.supported(Cc) and w2.shape == (Cc, 4 * Cc):
             out = self.pool.get(x.shape[0], Cc)
             self.step_ops.append(ops.FusedMlp(x, w1, b1, w2, b2, out, acc_scale=acc_scale, res1=res1, res1_scale=res1_scale,
@@ -343,6 +377,13 @@ class NetPlan:
         out = self._gemm(t3, w.tconv(t + "conv2.weight"), cout, batches=B, taps=(-HW, 0, HW), bias=w.f32(t + "conv2.bias"),
                          acc_scale=1.0 - alpha, res1=xs, res2=res2, res2_scale=1.0, out2=out2, aux=aux,
                          aux_scale=aux_scale, name=t + "conv2")
+        blend = self.step_ops[-1]
+        blend.io.mix = (prefix + "time_mixer.mix_factor", xs, alpha)   # out = alpha*xs + (1-alpha)*(xs + conv2): see train_engine
+
+        def upd(a, op=blend):
+            op.args.acc_scale = op.io.acc_scale = 1.0 - a
+            op.io.mix = (op.io.mix[0], op.io.mix[1], a)
+        self.alpha_updaters.append((prefix + "time_mixer.mix_factor", upd))
         self.pool.put(t3, xs)
         return out
 
@@ -365,11 +406,16 @@ class NetPlan:
         hid = torch.zeros(Fr, 4 * Cc, device=dev, dtype=F32)
         out = torch.zeros(Fr, Cc, device=dev, dtype=F32)
         frames = torch.arange(Fr, device=dev, dtype=F32)
-        ops.SinCos(sin, t=frames).launch(sp)
-        ops.SmallLinear(sin, w.linear(prefix + "time_pos_embed.linear_1.weight"), hid,
-                        w.f32(prefix + "time_pos_embed.linear_1.bias"), act_out_silu=True).launch(sp)
-        ops.SmallLinear(hid, w.linear(prefix + "time_pos_embed.linear_2.weight"), out,
-                        w.f32(prefix + "time_pos_embed.linear_2.bias")).launch(sp)
+        tr = self.train
+        lst = [ops.SinCos(sin, t=frames, name=prefix + "time_proj"),
+               ops.SmallLinear(sin, w.linear(prefix + "time_pos_embed.linear_1.weight"), hid,
+                               w.f32(prefix + "time_pos_embed.linear_1.bias"), act_out_silu=not tr, name=prefix + "time_pos_embed.1"),
+               ops.SmallLinear(hid, w.linear(prefix + "time_pos_embed.linear_2.weight"), out,
+                               w.f32(prefix + "time_pos_embed.linear_2.bias"), act_in_silu=tr, name=prefix + "time_pos_embed.2")]
+        for op in lst:
+            op.launch(sp)
+        if tr:   # the MLP is trained: re-evaluated with the other parameter-dependent constants every step
+            self.embed_ops += lst
         return out
 
     def transformer(self, prefix: str, x, heads: int, hw: tuple, *, out2=None, aux=None, aux_scale: float = 0.0):
@@ -401,7 +447,8 @@ class NetPlan:
         qkv = self._gemm(l1, w.qkv(sb + "attn1."), 3 * Cc, name=sb + "attn1.qkv")
         self.pool.put(l1)
         att = self.pool.get(x.shape[0], Cc)
-        self.step_ops.append(ops.AttnSpatial(qkv, att, n_img=self.n, heads=heads, name=sb + "attn1"))
+        lse = torch.empty(self.n * heads * HW, device=self.device, dtype=F32) if self.train else None
+        self.step_ops.append(ops.AttnSpatial(qkv, att, n_img=self.n, heads=heads, name=sb + "attn1", lse=lse))
         self.pool.put(qkv)
         # h2 = attn1 + h, then + attn2 (constant per batch row): both in one epilogue
         h2 = self._gemm(att, w.linear(sb + "attn1.to_out.0.weight"), Cc, bias=w.f32(sb + "attn1.to_out.0.bias"), res1=h,
@@ -429,6 +476,16 @@ class NetPlan:
         # blend: alpha*h3 + (1-alpha)*(ff(.) + t2)
         hb = self._ff(l3t, tb + "ff.", acc_scale=1.0 - alpha, res1=t2, res1_scale=1.0 - alpha, res2=h3, res2_scale=alpha,
                       name=tb + "ff+mix")
+        blend = self.step_ops[-1]
+        if hasattr(blend, "io") and hasattr(blend.io, "mix"):   # (the fused-MLP kernel of the inference plans has no record)
+            blend.io.mix = (prefix + "time_mixer.mix_factor", h3, alpha)   # out = alpha*h3 + (1-alpha)*(ff + t2)
+
+        def upd(a, op=blend):
+            op.args.acc_scale, op.args.res1_scale, op.args.res2_scale = 1.0 - a, 1.0 - a, a
+            if hasattr(op, "io") and hasattr(op.io, "mix"):
+                op.io.acc_scale, op.io.res1_scale, op.io.res2_scale = 1.0 - a, 1.0 - a, a
+                op.io.mix = (op.io.mix[0], op.io.mix[1], a)
+        self.alpha_updaters.append((prefix + "time_mixer.mix_factor", upd))
         self.pool.put(l3t, t2, h3)
         out = self._gemm(hb, w.linear(prefix + "proj_out.weight"), Cc, bias=w.f32(prefix + "proj_out.bias"), res1=x,
                          out2=out2, aux=aux, aux_scale=aux_scale, name=prefix + "proj_out")
@@ -555,6 +612,8 @@ class NetPlan:
         Hc, Wc = self.cond_hw
         p = "controlnet_cond_embedding."
         self.cam_rowvec = None
+        if self.train:
+            return self._build_cond_embedding_train()
         towers = [("conv_in", "blocks", self.cond_in)]
         if self.bbox:
             towers.append(("conv_in_2", "blocks_2", self.cond_in2))
@@ -615,6 +674,43 @@ class NetPlan:
                     self.cond_out_cam = ops.Gemm(self.feat_cam, w.conv3(p + "conv_out.weight"), self.cond_emb, **kw)
             else:
                 self.cond_out_bbox = ops.Gemm(feat, w.conv3(p + "conv_out.weight"), self.cond_emb, res1=self.cond_emb, **kw)
+
+    def _build_cond_embedding_train(self):
+        """Training variant of the conditioning embedding: EVERY conv through the implicit-GEMM kernel on the zero-haloed
+        token layout (channels padded to 64), SiLU as its own pass so that the pre-activations exist for the backward."""
+        cfg, w, dev = self.cfg, self.w, self.device
+        if self.cam:
+            raise NotImplementedError("training plan: the camera branch (cc_projection) has no backward yet")
+        ce = cfg.conditioning_embedding_out_channels
+        Hc, Wc = self.cond_hw
+        p = "controlnet_cond_embedding."
+        towers = [("conv_in", "blocks", self.cond_in)]
+        if self.bbox:
+            towers.append(("conv_in_2", "blocks_2", self.cond_in2))
+        feats = []
+        for cin_name, blocks_name, src in towers:
+            layers = [(cin_name, cfg.conditioning_channels, ce[0], 1)]
+            for i in range(len(ce) - 1):
+                layers.append((f"{blocks_name}.{2 * i}", ce[i], ce[i], 1))
+                layers.append((f"{blocks_name}.{2 * i + 1}", ce[i], ce[i + 1], 2))
+            x = torch.zeros(self.n * (Hc + 1) * (Wc + 1), _pad64(cfg.conditioning_channels), device=dev, dtype=BF16)
+            self.cond_ops.append(ops.Layout(src, x, to_tokens=True, halo=True, name=p + cin_name + ".layout"))
+            H, W = Hc, Wc
+            for name, cin, cout, stride in layers:
+                oH, oW = H // stride, W // stride
+                z = torch.zeros(self.n * (oH + 1) * (oW + 1), _pad64(cout), device=dev, dtype=BF16)
+                self.cond_ops.append(ops.Gemm(x, w.conv3(p + name + ".weight", _pad64(cin)), z, taps=ops.conv3x3_taps(W), n_out=cout,
+                                              bias=w.f32(p + name + ".bias"), halo=(H, W), ostride=stride, out_halo=True,
+                                              name=p + name))
+                a = torch.zeros_like(z)
+                self.cond_ops.append(ops.SiluFwd(z, a, name=p + name + ".silu"))
+                x, H, W = a, oH, oW
+            feats.append(x)
+        H, W = self.H, self.W
+        kw = dict(taps=ops.conv3x3_taps(W), bias=w.f32(p + "conv_out.bias"), halo=(H, W), name=p + "conv_out")
+        self.cond_out_plain = ops.Gemm(feats[0], w.conv3(p + "conv_out.weight"), self.cond_emb, **kw)
+        if self.bbox:
+            self.cond_out_bbox = ops.Gemm(feats[1], w.conv3(p + "conv_out.weight"), self.cond_emb, res1=self.cond_emb, **kw)
 
     def cond_op_list(self, use_cam: bool, use_bbox: bool) -> List:
         lst = list(self.cond_ops)

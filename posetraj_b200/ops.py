@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+from types import SimpleNamespace
 from typing import Optional, Sequence
 
 import torch
@@ -260,6 +261,12 @@ class Gemm:
         self.args = a
         self._keep = (a0, a1, w, out, bias, rowvec, res1, res2, out2, aux, acc_scale_dev)
         self._argp = C.addressof(a)
+        # semantic record of the launch (posetraj_b200.train_engine differentiates op lists through it)
+        self.io = SimpleNamespace(a0=a0, a1=a1, w=w, out=out, bias=bias, rowvec=rowvec, rowvec_mode=(rowvec_mode or 1) if rowvec is not None else 0,
+                                  rv=tuple(int(v) for v in rv), acc_scale=acc_scale, acc_scale_dev=acc_scale_dev, res1=res1,
+                                  res1_scale=res1_scale, res2=res2, res2_scale=res2_scale, out2=out2, aux=aux, aux_scale=aux_scale,
+                                  taps=tuple(int(t) for t in taps), batches=batches, halo=halo, ostride=ostride, out_halo=out_halo,
+                                  act=int(act_silu), geglu=bool(geglu), n_out=n_out, scatter=scatter, mix=None)
 
     def launch(self, stream_ptr: int) -> None:
         _lib.check(_lib.lib().pt_gemm(self._argp, stream_ptr), self.name)
@@ -426,6 +433,8 @@ class GroupNorm(_Op):
             assert out.shape[0] == rows
         self.kind = "groupnorm"
         self.alg_bytes = 2.0 * rows * (a.c0 + a.c1) * 2 * (0.5 if mode else 1.0)
+        self.io = SimpleNamespace(x0=x0, x1=x1, out=out, gamma=gamma, beta=beta, rows_per_stat=rows_per_stat, eps=eps, silu=bool(silu),
+                                  halo=halo, mode=mode)
         self._finish(a, (x0, x1, out, gamma, beta, stats, sums), name)
 
 
@@ -447,6 +456,7 @@ class LayerNorm(_Op):
                 a.sum_out = sum_out.data_ptr()
         self.kind = "layernorm"
         self.alg_bytes = (3.0 if sum_out is not None else 2.0) * x.shape[0] * x.shape[1] * 2
+        self.io = SimpleNamespace(x=x, out=out, gamma=gamma, beta=beta, eps=eps, addvec=addvec, hw=hw, frames=frames, sum_out=sum_out)
         self._finish(a, (x, out, gamma, beta, addvec, sum_out), name)
 
 
@@ -470,6 +480,7 @@ class AttnSpatial(_Op):
         self.kind = "attn_spatial"
         self.alg_flops = 4.0 * S * S * 64 * heads * n_img
         self.alg_bytes = 4.0 * rows * Cc * 2
+        self.io = SimpleNamespace(qkv=qkv, out=out, n_img=n_img, heads=heads, lse=lse)
         self._finish(a, (qkv, out, lse), name)
 
 
@@ -486,6 +497,7 @@ class AttnTemporal(_Op):
         self.kind = "attn_temporal"
         self.alg_flops = 4.0 * frames * frames * 64 * heads * batch * hw
         self.alg_bytes = 4.0 * qkv.shape[0] * a.C * 2
+        self.io = SimpleNamespace(qkv=qkv, out=out, batch=batch, frames=frames, hw=hw, heads=heads)
         self._finish(a, (qkv, out), name)
 
 
@@ -504,6 +516,8 @@ class SmallLinear(_Op):
         a.N = w.shape[0]
         assert w.shape[1] == a.K and out.shape == (a.M, a.N)
         a.act_in_silu, a.act_out_silu, a.accumulate = int(act_in_silu), int(act_out_silu), int(accumulate)
+        self.io = SimpleNamespace(x=x, w=w, out=out, bias=bias, act_in_silu=bool(act_in_silu), act_out_silu=bool(act_out_silu),
+                                  accumulate=bool(accumulate))
         self._finish(a, (x, w, out, bias), name)
 
 
@@ -534,6 +548,7 @@ class Upsample2x(_Op):
         assert out.shape[0] == exp_rows
         self.kind = "upsample"
         self.alg_bytes = (x.shape[0] + out.shape[0]) * x.shape[1] * 2.0
+        self.io = SimpleNamespace(x=x, out=out, n=n, H=H, W=W, halo=bool(halo), scale=scale)
         self._finish(a, (x, out), name)
 
 
@@ -608,7 +623,40 @@ class Axpy(_Op):
         a.rows, a.cols = x.shape
         a.scale = float(scale)
         self.alg_bytes = 3.0 * x.numel() * 2
+        self.io = SimpleNamespace(x=x, y=y, out=out, scale=float(scale))
         self._finish(a, (x, y, out), name)
+
+
+class GegluFwd:
+    """out = value * gelu(gate) of h = (value | gate) as its own pass (training keeps the pre-activations)."""
+    kind, alg_flops = "train_misc", 0.0
+
+    def __init__(self, h, out, name="geglu"):
+        assert h.dtype == out.dtype == torch.bfloat16 and h.shape[1] == 2 * out.shape[1] and h.shape[0] == out.shape[0]
+        self.io = SimpleNamespace(h=h, out=out)
+        self.name = name
+        self.alg_bytes = 3.0 * out.numel() * 2
+
+    def launch(self, stream_ptr: int) -> None:
+        h, out = self.io.h, self.io.out
+        _lib.check(_lib.lib().pt_geglu_fwd(h.data_ptr(), h.stride(0), out.data_ptr(), out.stride(0), h.shape[0], out.shape[1], stream_ptr),
+                   self.name)
+
+
+class SiluFwd:
+    """out = silu(x) (bf16 rows) as its own pass (conditioning embedding in training)."""
+    kind, alg_flops = "train_misc", 0.0
+
+    def __init__(self, x, out, name="silu"):
+        assert x.dtype == out.dtype == torch.bfloat16 and x.shape == out.shape
+        self.io = SimpleNamespace(x=x, out=out)
+        self.name = name
+        self.alg_bytes = 2.0 * out.numel() * 2
+
+    def launch(self, stream_ptr: int) -> None:
+        x, out = self.io.x, self.io.out
+        _lib.check(_lib.lib().pt_silu_fwd(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1], stream_ptr),
+                   self.name)
 
 
 class SoftmaxRows(_Op):

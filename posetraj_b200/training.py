@@ -194,7 +194,8 @@ def groupnorm_backward(x0: torch.Tensor, dout: torch.Tensor, gamma: torch.Tensor
 
 
 def layernorm_backward(x: torch.Tensor, dout: torch.Tensor, gamma: torch.Tensor, *, eps: float = 1e-5,
-                       accumulate_into: Optional[torch.Tensor] = None, want_param_grads: bool = True):
+                       accumulate_into: Optional[torch.Tensor] = None, want_param_grads: bool = True,
+                       addvec: Optional[torch.Tensor] = None, hw: int = 1, frames: int = 1):
     """LayerNorm backward (oracle/backward.py layernorm_backward).  Returns (dx, dgb | None); with `accumulate_into` the
     result is added to that tensor in place (the input also feeds a residual branch)."""
     _check(x, BF16), _check(dout, BF16)
@@ -204,6 +205,9 @@ def layernorm_backward(x: torch.Tensor, dout: torch.Tensor, gamma: torch.Tensor,
     a = _lib.PtLayerNormBwdArgs()
     a.x, a.ld, a.dout, a.dout_ld = x.data_ptr(), x.stride(0), dout.data_ptr(), dout.stride(0)
     a.gamma, a.eps, a.rows, a.C = gamma.data_ptr(), eps, rows, Cc
+    if addvec is not None:      # the forward normalised x + addvec[frame of the row]
+        _check(addvec, F32)
+        a.addvec, a.hw, a.F = addvec.data_ptr(), hw, frames
     a.dx, a.dx_ld, a.accumulate_dx = dx.data_ptr(), dx.stride(0), int(accumulate_into is not None)
     a.n_blocks = nb
     dgb = None
@@ -257,6 +261,27 @@ def edm_loss(pred_tokens: torch.Tensor, noisy: torch.Tensor, target: torch.Tenso
     a.workspace, a.loss, a.accumulate = ws.data_ptr(), loss.data_ptr(), int(acc)
     _lib.check(_lib.lib().pt_edm_loss(C.addressof(a), _sp()), "pt_edm_loss")
     return loss, dpred
+
+
+def edm_loss_into(pred_tokens: torch.Tensor, noisy: torch.Tensor, target: torch.Tensor, sigmas: torch.Tensor, *, weight: float,
+                  frame: Optional[int], loss: torch.Tensor, accumulate: bool, dpred: torch.Tensor) -> None:
+    """`edm_loss` writing into caller-owned buffers: `loss` (+)= the weighted loss, `dpred` (a bf16 [rows, C] view, any row
+    stride) = weight * d loss / d pred."""
+    _check(pred_tokens, BF16), _check(noisy, F32), _check(target, F32), _check(sigmas, F32), _check(dpred, BF16)
+    B, Ft, Cc, H, W = noisy.shape
+    Fr = 1 if frame is not None else Ft
+    assert pred_tokens.shape[0] == B * Fr * H * W and noisy.is_contiguous() and target.is_contiguous()
+    assert dpred.shape[0] == pred_tokens.shape[0] and dpred.shape[1] == Cc
+    off = (frame or 0) * Cc * H * W
+    ws = torch.empty(_lib.lib().pt_edm_loss_workspace_bytes(), device=noisy.device, dtype=torch.uint8)
+    a = _lib.PtEdmLossArgs()
+    a.pred, a.pred_ld = pred_tokens.data_ptr(), pred_tokens.stride(0)
+    a.noisy, a.target = noisy.data_ptr() + 4 * off, target.data_ptr() + 4 * off
+    a.sample_stride, a.frame_stride = Ft * Cc * H * W, Cc * H * W
+    a.sigmas, a.B, a.F, a.C, a.HW, a.weight = sigmas.data_ptr(), B, Fr, Cc, H * W, weight
+    a.dpred, a.dpred_ld = dpred.data_ptr(), dpred.stride(0)
+    a.workspace, a.loss, a.accumulate = ws.data_ptr(), loss.data_ptr(), int(accumulate)
+    _lib.check(_lib.lib().pt_edm_loss(C.addressof(a), _sp()), "pt_edm_loss")
 
 
 # ---------------------------------------------------------------------------------------------------------------
