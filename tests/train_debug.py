@@ -1,6 +1,6 @@
 """Per-parameter gradient errors of one training step against the oracle (small config), for debugging on a GPU box."""
 import sys, os, json
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+sys.path.insert(0, os.path.dirname(__file__))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
 from parity_util import oracle_pair, small_cfg
