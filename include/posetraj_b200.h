@@ -631,7 +631,7 @@ int pt_small_linear_bwd(const PtSmallLinearBwdArgs* a, void* stream);
 /* out[g, c] (+)= scale * sum over rows r with group(r) == g of x[r, c]; group(r) =
  *   mode 1: r / ga            mode 2: ((r / ga) * gb + r % gb) % gc  (PtGemmArgs.rowvec_mode 1 / 2)
  *   mode 3: (r / ga) % gc     (frame of row (b*F + f)*HW + s with ga = HW, gc = F)
- * groups <= 40; deterministic (two stages, fixed order) */
+ * deterministic (two stages, fixed order); mode 2 is vectorised for gc <= 4, every other shape has a scalar fallback */
 typedef struct PtColsumGroupedArgs {
   const void* x;            /* bf16 [rows, ld] */
   int32_t ld;

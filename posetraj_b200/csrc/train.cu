@@ -96,241 +96,6 @@ __global__ void edm_loss_final_kernel(const EdmParams p, int nblocks) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GroupNorm(32) (+SiLU) backward
-// ---------------------------------------------------------------------------------------------------------------
-struct GnBwdParams {
-  const bf16* x0;
-  const bf16* x1;
-  int c0, c1, ld0, ld1;
-  const bf16* dout;
-  int dout_ld, halo, H, W;
-  const float* gamma;
-  const float* beta;
-  float eps;
-  int silu, rows_per_stat, num_stat;
-  bf16* dx0;
-  bf16* dx1;
-  int dld0, dld1;
-  float* stats;   // [num_stat*32][4]: mean, rstd, S1/n, S2/n
-  float* dgb;     // [num_stat][2][C] per-statistics-group partials of dgamma / dbeta (nullptr: not wanted)
-};
-
-PT_DEVICE float gn_load_x(const GnBwdParams& p, long long row, int c) {
-  return c < p.c0 ? __bfloat162float(p.x0[(size_t)row * p.ld0 + c]) : __bfloat162float(p.x1[(size_t)row * p.ld1 + (c - p.c0)]);
-}
-
-PT_DEVICE long long gn_dout_row(const GnBwdParams& p, long long row) {
-  if (!p.halo) return row;
-  const int hw = p.H * p.W;
-  const long long img = row / hw;
-  const int rem = (int)(row - img * hw);
-  const int y = rem / p.W, x = rem - y * p.W;
-  return (img * (p.H + 1) + y) * (p.W + 1) + x;
-}
-
-// one block per (statistics group, norm group): phase 0 statistics, phase 1 the two backward sums (+ dgamma/dbeta
-// partials of this statistics group), phase 2 dx
-__global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdParams p, int phase) {
-  __shared__ double red[32];
-  const int C = p.c0 + p.c1;
-  const int cg = C / 32;
-  const int s = blockIdx.x / 32, grp = blockIdx.x % 32;
-  const long long n = (long long)p.rows_per_stat * cg;
-  float* st = p.stats + (size_t)blockIdx.x * 4;
-  if (phase == 0) {
-    double a = 0.0, b = 0.0;
-    for (long long e = threadIdx.x; e < n; e += blockDim.x) {
-      const long long r = e / cg;
-      const int c = grp * cg + (int)(e - r * cg);
-      const double v = gn_load_x(p, (long long)s * p.rows_per_stat + r, c);
-      a += v;
-      b += v * v;
-    }
-    const double sa = block_sum_d(a, red);
-    const double sb = block_sum_d(b, red);
-    if (threadIdx.x == 0) {
-      const double mean = sa / (double)n;
-      double var = sb / (double)n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      st[0] = (float)mean;
-      st[1] = (float)(1.0 / sqrt(var + (double)p.eps));
-    }
-    return;
-  }
-  const float mean = st[0], rstd = st[1];
-  if (phase == 1) {
-    double a = 0.0, b = 0.0;
-    for (long long e = threadIdx.x; e < n; e += blockDim.x) {
-      const long long r = e / cg;
-      const int c = grp * cg + (int)(e - r * cg);
-      const long long row = (long long)s * p.rows_per_stat + r;
-      const float xh = (gn_load_x(p, row, c) - mean) * rstd;
-      float dy = __bfloat162float(p.dout[(size_t)gn_dout_row(p, row) * p.dout_ld + c]);
-      if (p.silu) {
-        const float y = xh * p.gamma[c] + p.beta[c];
-        const float sg = 1.0f / (1.0f + __expf(-y));
-        dy *= sg * (1.0f + y * (1.0f - sg));
-      }
-      const float g = dy * p.gamma[c];
-      a += (double)g;
-      b += (double)g * xh;
-    }
-    const double sa = block_sum_d(a, red);
-    const double sb = block_sum_d(b, red);
-    if (threadIdx.x == 0) {
-      st[2] = (float)(sa / (double)n);
-      st[3] = (float)(sb / (double)n);
-    }
-    if (p.dgb != nullptr) {
-      // per-channel sums over the rows of this statistics group: thread t -> channel (t % cg), row lanes t / cg
-      const int lanes = blockDim.x / cg;
-      if (lanes > 0) {
-        __shared__ float cs[2][256];
-        const int cl = threadIdx.x % cg, rl = threadIdx.x / cg;
-        float ga = 0.f, be = 0.f;
-        if (rl < lanes) {
-          const int c = grp * cg + cl;
-          for (long long r = rl; r < p.rows_per_stat; r += lanes) {
-            const long long row = (long long)s * p.rows_per_stat + r;
-            const float xh = (gn_load_x(p, row, c) - mean) * rstd;
-            float dy = __bfloat162float(p.dout[(size_t)gn_dout_row(p, row) * p.dout_ld + c]);
-            if (p.silu) {
-              const float y = xh * p.gamma[c] + p.beta[c];
-              const float sg = 1.0f / (1.0f + __expf(-y));
-              dy *= sg * (1.0f + y * (1.0f - sg));
-            }
-            ga += dy * xh;
-            be += dy;
-          }
-        }
-        __syncthreads();
-        cs[0][threadIdx.x] = ga;
-        cs[1][threadIdx.x] = be;
-        __syncthreads();
-        if (threadIdx.x < cg) {
-          float sg = 0.f, sb2 = 0.f;
-          for (int l = 0; l < lanes; ++l) {
-            sg += cs[0][l * cg + threadIdx.x];
-            sb2 += cs[1][l * cg + threadIdx.x];
-          }
-          p.dgb[((size_t)s * 2 + 0) * C + grp * cg + threadIdx.x] = sg;
-          p.dgb[((size_t)s * 2 + 1) * C + grp * cg + threadIdx.x] = sb2;
-        }
-      }
-    }
-    return;
-  }
-  // phase 2: dx = rstd (g - mean(g) - xh mean(g xh))
-  const float m1 = st[2], m2 = st[3];
-  for (long long e = threadIdx.x; e < n; e += blockDim.x) {
-    const long long r = e / cg;
-    const int c = grp * cg + (int)(e - r * cg);
-    const long long row = (long long)s * p.rows_per_stat + r;
-    const float xh = (gn_load_x(p, row, c) - mean) * rstd;
-    float dy = __bfloat162float(p.dout[(size_t)gn_dout_row(p, row) * p.dout_ld + c]);
-    if (p.silu) {
-      const float y = xh * p.gamma[c] + p.beta[c];
-      const float sg = 1.0f / (1.0f + __expf(-y));
-      dy *= sg * (1.0f + y * (1.0f - sg));
-    }
-    const float g = dy * p.gamma[c];
-    const float dx = rstd * (g - m1 - xh * m2);
-    if (c < p.c0) p.dx0[(size_t)row * p.dld0 + c] = __float2bfloat16(dx);
-    else p.dx1[(size_t)row * p.dld1 + (c - p.c0)] = __float2bfloat16(dx);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// LayerNorm backward: one warp per row; per-block partial dgamma / dbeta
-// ---------------------------------------------------------------------------------------------------------------
-struct LnBwdParams {
-  const bf16* x;
-  int ld;
-  const bf16* dout;
-  int dout_ld;
-  const float* gamma;
-  float eps;
-  int rows, C;
-  const float* addvec;  // optional: the forward normalised x + addvec[frame] (modified_svd.py:196-197)
-  int hw, F;
-  bf16* dx;
-  int dx_ld;
-  int accumulate_dx;    // dx += (the tensor also feeds a residual branch whose gradient is already there)
-  float* partials;      // [gridDim.x][2][C] or nullptr
-};
-
-constexpr int kLnBwdMaxPerLane = 64;  // C <= 2048
-
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
-  extern __shared__ float ln_sm[];   // [8 warps][2][C]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int per = (p.C + 31) / 32;
-  float dga[kLnBwdMaxPerLane], dbe[kLnBwdMaxPerLane];
-#pragma unroll
-  for (int i = 0; i < kLnBwdMaxPerLane; ++i) { dga[i] = 0.f; dbe[i] = 0.f; }
-  for (int row = blockIdx.x * nw + warp; row < p.rows; row += gridDim.x * nw) {
-    const bf16* xr = p.x + (size_t)row * p.ld;
-    const bf16* dr = p.dout + (size_t)row * p.dout_ld;
-    const float* av = p.addvec != nullptr ? p.addvec + (size_t)((row / p.hw) % p.F) * p.C : nullptr;
-    float sum = 0.f, sq = 0.f;
-    for (int i = 0; i < per; ++i) {
-      const int c = lane + 32 * i;
-      if (c < p.C) {
-        const float v = __bfloat162float(xr[c]) + (av ? av[c] : 0.f);
-        sum += v;
-        sq += v * v;
-      }
-    }
-    sum = warp_sum(sum);
-    sq = warp_sum(sq);
-    const float mean = sum / p.C;
-    const float rstd = rsqrtf(fmaxf(sq / p.C - mean * mean, 0.f) + p.eps);
-    float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < per; ++i) {
-      const int c = lane + 32 * i;
-      if (c < p.C) {
-        const float xh = (__bfloat162float(xr[c]) + (av ? av[c] : 0.f) - mean) * rstd;
-        const float g = __bfloat162float(dr[c]) * p.gamma[c];
-        s1 += g;
-        s2 += g * xh;
-      }
-    }
-    s1 = warp_sum(s1) / p.C;
-    s2 = warp_sum(s2) / p.C;
-#pragma unroll
-    for (int i = 0; i < kLnBwdMaxPerLane; ++i) {
-      const int c = lane + 32 * i;
-      if (i < per && c < p.C) {
-        const float xh = (__bfloat162float(xr[c]) + (av ? av[c] : 0.f) - mean) * rstd;
-        const float d = __bfloat162float(dr[c]);
-        float dx = rstd * (d * p.gamma[c] - s1 - xh * s2);
-        bf16* o = p.dx + (size_t)row * p.dx_ld + c;
-        if (p.accumulate_dx) dx += __bfloat162float(*o);
-        *o = __float2bfloat16(dx);
-        dga[i] += d * xh;
-        dbe[i] += d;
-      }
-    }
-  }
-  if (p.partials == nullptr) return;
-#pragma unroll
-  for (int i = 0; i < kLnBwdMaxPerLane; ++i) {
-    const int c = lane + 32 * i;
-    if (i < per && c < p.C) {
-      ln_sm[(warp * 2 + 0) * p.C + c] = dga[i];
-      ln_sm[(warp * 2 + 1) * p.C + c] = dbe[i];
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < 2 * p.C; c += blockDim.x) {
-    const int which = c / p.C, cc = c - which * p.C;
-    float t = 0.f;
-    for (int w = 0; w < nw; ++w) t += ln_sm[(w * 2 + which) * p.C + cc];
-    p.partials[((size_t)blockIdx.x * 2 + which) * p.C + cc] = t;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // GEGLU as a separate pass (training): out = v * gelu(g); backward with the exact erf derivative
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) geglu_fwd_kernel(const bf16* h, int ld, bf16* out, int out_ld, long long rows, int H) {
@@ -344,19 +109,24 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const bf16* h, int ld, b
   }
 }
 
-__global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* h, int ld, const bf16* dout, int dout_ld, bf16* dh, int dh_ld,
-                                                        long long rows, int H) {
-  const long long total = rows * H;
+// 8 channels (16 bytes) per thread
+__global__ void __launch_bounds__(256) geglu_fwd8_kernel(const bf16* h, int ld, bf16* out, int out_ld, long long rows, int H) {
+  const int hv = H >> 3;
+  const long long total = rows * hv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / H;
-    const int c = (int)(i - r * H);
-    const float v = __bfloat162float(h[(size_t)r * ld + c]);
-    const float g = __bfloat162float(h[(size_t)r * ld + H + c]);
-    const float d = __bfloat162float(dout[(size_t)r * dout_ld + c]);
-    const float Phi = 0.5f * (1.0f + erff(g * 0.70710678118654752440f));
-    const float phi = 0.3989422804014327f * __expf(-0.5f * g * g);
-    dh[(size_t)r * dh_ld + c] = __float2bfloat16(d * g * Phi);
-    dh[(size_t)r * dh_ld + H + c] = __float2bfloat16(d * v * (Phi + g * phi));
+    const long long r = i / hv;
+    const int c = (int)(i - r * hv) * 8;
+    const uint4 uv = ldg_u4(h + (size_t)r * ld + c), ug = ldg_u4(h + (size_t)r * ld + H + c);
+    const uint32_t* pv = reinterpret_cast<const uint32_t*>(&uv);
+    const uint32_t* pg = reinterpret_cast<const uint32_t*>(&ug);
+    uint4 o;
+    uint32_t* po = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 v = unpack_bf16x2(pv[k]), g = unpack_bf16x2(pg[k]);
+      po[k] = pack_bf16x2(geglu_gate_fast(v.x, g.x), geglu_gate_fast(v.y, g.y));
+    }
+    stg_u4(out + (size_t)r * out_ld + c, o);
   }
 }
 
@@ -435,24 +205,6 @@ __global__ void dot_final_kernel(const double* partials, int nb, float scale, fl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// bf16 transpose [rows, cols] -> [cols, rows] (32 x 32 tiles through shared memory)
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) transpose_kernel(const bf16* in, int ld_in, bf16* out, int ld_out, int rows, int cols) {
-  __shared__ bf16 tile[32][34];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : __float2bfloat16(0.f);
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + tx;
-    if (c < cols && r < rows) out[(size_t)c * ld_out + r] = tile[tx][i];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments)
 // ---------------------------------------------------------------------------------------------------------------
 struct AdamParams {
@@ -519,90 +271,15 @@ extern "C" int pt_edm_loss(const PtEdmLossArgs* a, void* stream) {
   return pt_launched("pt_edm_loss(final)");
 }
 
-extern "C" int64_t pt_groupnorm_bwd_workspace_bytes(int32_t num_stat, int32_t channels) {
-  if (num_stat < 1 || channels < 32) return -1;
-  return (int64_t)num_stat * 32 * 4 * 4 + (int64_t)num_stat * 2 * channels * 4;
-}
-
-extern "C" int pt_groupnorm_bwd(const PtGroupNormBwdArgs* a, void* stream) {
-  PT_CHECK_ARG(a != nullptr && a->x0 && a->dout && a->gamma && a->beta && a->dx0 && a->workspace, "pt_groupnorm_bwd: null argument");
-  const int C = a->c0 + a->c1;
-  PT_CHECK_ARG(a->c0 > 0 && C % 32 == 0 && C / 32 <= 256, "pt_groupnorm_bwd: channels must be a multiple of 32 (<= 8192)");
-  PT_CHECK_ARG(a->c1 == 0 || (a->x1 != nullptr && a->dx1 != nullptr), "pt_groupnorm_bwd: c1 > 0 without x1 / dx1");
-  PT_CHECK_ARG(a->rows_per_stat > 0 && a->num_stat > 0, "pt_groupnorm_bwd: empty problem");
-  PT_CHECK_ARG(!a->halo || (a->H > 0 && a->W > 0 && a->rows_per_stat % (a->H * a->W) == 0), "pt_groupnorm_bwd: bad halo geometry");
-  GnBwdParams p;
-  p.x0 = reinterpret_cast<const bf16*>(a->x0);
-  p.x1 = reinterpret_cast<const bf16*>(a->x1);
-  p.c0 = a->c0; p.c1 = a->c1; p.ld0 = a->ld0; p.ld1 = a->ld1;
-  p.dout = reinterpret_cast<const bf16*>(a->dout);
-  p.dout_ld = a->dout_ld; p.halo = a->halo; p.H = a->H > 0 ? a->H : 1; p.W = a->W > 0 ? a->W : 1;
-  p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
-  p.rows_per_stat = a->rows_per_stat; p.num_stat = a->num_stat;
-  p.dx0 = reinterpret_cast<bf16*>(a->dx0);
-  p.dx1 = reinterpret_cast<bf16*>(a->dx1);
-  p.dld0 = a->dld0; p.dld1 = a->dld1;
-  p.stats = reinterpret_cast<float*>(a->workspace);
-  p.dgb = (a->dgb_out != nullptr) ? p.stats + (size_t)a->num_stat * 32 * 4 : nullptr;
-  for (int phase = 0; phase < 3; ++phase) {
-    pt_launch(gn_bwd_kernel, dim3(a->num_stat * 32), dim3(256), 0, stream, 1, p, phase);
-    int rc = pt_launched("pt_groupnorm_bwd");
-    if (rc) return rc;
-  }
-  if (a->dgb_out != nullptr) {
-    // fold the per-statistics-group partials [num_stat][2*C] (dgamma | dbeta) in order
-    pt_launch(reduce_partials_kernel, dim3(grid_for(2LL * C)), dim3(256), 0, stream, 1, (const float*)p.dgb, a->num_stat, (long long)(2 * C),
-              1.0f, a->dgb_out, a->accumulate_dgb);
-    return pt_launched("pt_groupnorm_bwd(dgamma)");
-  }
-  return 0;
-}
-
-extern "C" int pt_layernorm_bwd(const PtLayerNormBwdArgs* a, void* stream) {
-  PT_CHECK_ARG(a != nullptr && a->x && a->dout && a->gamma && a->dx, "pt_layernorm_bwd: null argument");
-  PT_CHECK_ARG(a->C >= 32 && a->C <= 32 * kLnBwdMaxPerLane && a->rows > 0, "pt_layernorm_bwd: C must be in [32, 2048]");
-  LnBwdParams p;
-  p.x = reinterpret_cast<const bf16*>(a->x); p.ld = a->ld;
-  p.dout = reinterpret_cast<const bf16*>(a->dout); p.dout_ld = a->dout_ld;
-  p.gamma = a->gamma; p.eps = a->eps; p.rows = a->rows; p.C = a->C;
-  p.addvec = a->addvec; p.hw = a->hw > 0 ? a->hw : 1; p.F = a->F > 0 ? a->F : 1;
-  p.dx = reinterpret_cast<bf16*>(a->dx); p.dx_ld = a->dx_ld;
-  p.accumulate_dx = a->accumulate_dx;
-  p.partials = a->partials;
-  int blocks = a->n_blocks;
-  PT_CHECK_ARG(blocks >= 1 && blocks <= 4096, "pt_layernorm_bwd: n_blocks out of range");
-  const size_t smem = (size_t)8 * 2 * a->C * sizeof(float);
-  static bool attr_set[PT_MAX_DEVICES] = {false};
-  const int dev_slot = pt_device_slot();
-  if (!attr_set[dev_slot]) {
-    cudaError_t e = cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4);
-    if (e != cudaSuccess) return pt_fail(e, "pt_layernorm_bwd: cudaFuncSetAttribute");
-    attr_set[dev_slot] = true;
-  }
-  pt_launch(ln_bwd_kernel, dim3(blocks), dim3(256), smem, stream, 1, p);
-  int rc = pt_launched("pt_layernorm_bwd");
-  if (rc) return rc;
-  if (a->partials != nullptr && a->dgb_out != nullptr) {
-    pt_launch(reduce_partials_kernel, dim3(grid_for(2LL * a->C)), dim3(256), 0, stream, 1, (const float*)a->partials, blocks,
-              (long long)(2 * a->C), 1.0f, a->dgb_out, a->accumulate_dgb);
-    return pt_launched("pt_layernorm_bwd(dgamma)");
-  }
-  return 0;
-}
-
 extern "C" int pt_geglu_fwd(const void* h, int32_t ld, void* out, int32_t out_ld, int64_t rows, int32_t hidden, void* stream) {
   PT_CHECK_ARG(h && out && rows > 0 && hidden > 0 && hidden % 2 == 0 && ld % 2 == 0 && out_ld % 2 == 0, "pt_geglu_fwd: bad argument");
-  pt_launch(geglu_fwd_kernel, dim3(grid_for(rows * (hidden / 2))), dim3(256), 0, stream, 1, reinterpret_cast<const bf16*>(h), (int)ld,
-            reinterpret_cast<bf16*>(out), (int)out_ld, (long long)rows, (int)hidden);
+  if (hidden % 8 == 0 && ld % 8 == 0 && out_ld % 8 == 0)
+    pt_launch(geglu_fwd8_kernel, dim3(grid_for(rows * (hidden / 8), 256, 148 * 16)), dim3(256), 0, stream, 1, reinterpret_cast<const bf16*>(h),
+              (int)ld, reinterpret_cast<bf16*>(out), (int)out_ld, (long long)rows, (int)hidden);
+  else
+    pt_launch(geglu_fwd_kernel, dim3(grid_for(rows * (hidden / 2))), dim3(256), 0, stream, 1, reinterpret_cast<const bf16*>(h), (int)ld,
+              reinterpret_cast<bf16*>(out), (int)out_ld, (long long)rows, (int)hidden);
   return pt_launched("pt_geglu_fwd");
-}
-
-extern "C" int pt_geglu_bwd(const void* h, int32_t ld, const void* dout, int32_t dout_ld, void* dh, int32_t dh_ld, int64_t rows,
-                            int32_t hidden, void* stream) {
-  PT_CHECK_ARG(h && dout && dh && rows > 0 && hidden > 0, "pt_geglu_bwd: bad argument");
-  pt_launch(geglu_bwd_kernel, dim3(grid_for(rows * hidden)), dim3(256), 0, stream, 1, reinterpret_cast<const bf16*>(h), (int)ld,
-            reinterpret_cast<const bf16*>(dout), (int)dout_ld, reinterpret_cast<bf16*>(dh), (int)dh_ld, (long long)rows, (int)hidden);
-  return pt_launched("pt_geglu_bwd");
 }
 
 extern "C" int pt_colsum(const PtColsumArgs* a, void* stream) {
@@ -631,14 +308,6 @@ extern "C" int pt_dot_bf16(const void* a, int32_t lda, const void* b, int32_t ld
   if (rc) return rc;
   pt_launch(dot_final_kernel, dim3(1), dim3(32), 0, stream, 1, (const double*)workspace, blocks, scale, out, (int)accumulate);
   return pt_launched("pt_dot_bf16(final)");
-}
-
-extern "C" int pt_transpose_bf16(const void* in, int32_t ld_in, void* out, int32_t ld_out, int32_t rows, int32_t cols, void* stream) {
-  PT_CHECK_ARG(in && out && rows > 0 && cols > 0, "pt_transpose_bf16: bad argument");
-  PT_CHECK_ARG((rows + 31) / 32 <= 65535, "pt_transpose_bf16: too many rows for one launch");
-  pt_launch(transpose_kernel, dim3((cols + 31) / 32, (rows + 31) / 32), dim3(256), 0, stream, 1, reinterpret_cast<const bf16*>(in), (int)ld_in,
-            reinterpret_cast<bf16*>(out), (int)ld_out, (int)rows, (int)cols);
-  return pt_launched("pt_transpose_bf16");
 }
 
 extern "C" int pt_adamw(const PtAdamWArgs* a, void* stream) {

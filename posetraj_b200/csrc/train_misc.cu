@@ -218,70 +218,117 @@ __global__ void __launch_bounds__(256) small_linear_dx_kernel(const SlBwdParams 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// grouped column sums, two stages.  group(row):
+// grouped column sums, two stages (per-CTA partials, then a fixed-order fold).  group(row):
 //   mode 1: row / ga                                  (PtGemmArgs.rowvec_mode 1; bias: ga = rows)
-//   mode 2: ((row / ga) * gb + row % gb) % gc         (PtGemmArgs.rowvec_mode 2)
+//   mode 2: ((row / ga) * gb + row % gb) % gc         (PtGemmArgs.rowvec_mode 2; gc <= 4)
 //   mode 3: (row / ga) % gc                           (frame index of row (b*F + f)*HW + s: ga = HW, gc = F)
+// Modes 1 and 3 are RUNS of ga consecutive rows with one group: a CTA sums a slice of one run.  Mode 2 interleaves the
+// groups row by row: a CTA keeps one accumulator set per group.  Threads read whole rows, 8 channels (16 bytes) each.
 // ------------------------------------------------------------------------------------------------------------
 struct ColsumGParams {
   const bf16* x;
   int ld;
   long long rows;
   int C, groups, mode, ga, gb, gc;
+  int sub;            // modes 1 / 3: CTAs per run; mode 2: number of row chunks
   int rows_per_cta;
-  float* partials;   // [chunks][groups][C]
+  int cvec, rpar;
+  float* partials;    // [blocks][C]
 };
 
-constexpr int kCsMaxGroups = 40;
+constexpr int kCsMaxBlocks = 2048;
 
-PT_DEVICE int cs_group(const ColsumGParams& p, long long row) {
-  if (p.mode == 1) return (int)(row / p.ga);
-  if (p.mode == 2) return (int)((((row / p.ga) * p.gb) + (row % p.gb)) % p.gc);
-  return (int)((row / p.ga) % p.gc);
-}
-
-__global__ void __launch_bounds__(256) colsum_grouped_kernel(const ColsumGParams p) {
-  extern __shared__ float cs_acc[];  // [groups][8][32]
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  for (int i = threadIdx.x; i < p.groups * 256; i += 256) cs_acc[i] = 0.f;
-  __syncthreads();
-  const long long r_begin = (long long)blockIdx.y * p.rows_per_cta;
-  long long r_end = r_begin + p.rows_per_cta;
-  if (r_end > p.rows) r_end = p.rows;
-  if (c < p.C) {
-    int cur = -1;
-    float acc = 0.f;
-    for (long long r = r_begin + rl; r < r_end; r += 8) {
-      const int g = cs_group(p, r);
-      if (g != cur) {
-        if (cur >= 0) cs_acc[(cur * 8 + rl) * 32 + cl] += acc;   // (group, rl, cl) belongs to this thread alone
-        cur = g;
-        acc = 0.f;
-      }
-      acc += __bfloat162float(p.x[(size_t)r * p.ld + c]);
-    }
-    if (cur >= 0) cs_acc[(cur * 8 + rl) * 32 + cl] += acc;
+template <int NG>   // accumulator sets per thread: 1 (modes 1 / 3) or gc (mode 2)
+__global__ void __launch_bounds__(512) colsum_grouped_kernel(const ColsumGParams p) {
+  extern __shared__ float cs_sm[];  // [rpar][C]
+  const int cl = threadIdx.x % p.cvec, rl = threadIdx.x / p.cvec;
+  long long r_begin, r_end;
+  if (p.mode == 2) {
+    r_begin = (long long)blockIdx.x * p.rows_per_cta;
+    r_end = r_begin + p.rows_per_cta;
+    if (r_end > p.rows) r_end = p.rows;
+  } else {
+    const long long run = blockIdx.x / p.sub;
+    const int s = blockIdx.x % p.sub;
+    r_begin = run * p.ga + (long long)s * p.rows_per_cta;
+    r_end = r_begin + p.rows_per_cta;
+    if (r_end > (run + 1) * p.ga) r_end = (run + 1) * p.ga;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < p.groups * 32; i += 256) {
-    const int g = i >> 5, cc = i & 31;
-    if (blockIdx.x * 32 + cc < p.C) {
-      float t = 0.f;
+  float acc[NG][8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t += cs_acc[(g * 8 + k) * 32 + cc];
-      p.partials[((size_t)blockIdx.y * p.groups + g) * p.C + blockIdx.x * 32 + cc] = t;
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+  for (long long r = r_begin + rl; r < r_end; r += p.rpar) {
+    const uint4 u = ldg_u4(p.x + (size_t)r * p.ld + cl * 8);
+    const uint32_t* pu = reinterpret_cast<const uint32_t*>(&u);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(pu[k]);
+      v[2 * k] = f.x;
+      v[2 * k + 1] = f.y;
+    }
+    if (NG == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[0][i] += v[i];
+    } else {
+      const int g = (int)((((r / p.ga) * p.gb) + (r % p.gb)) % p.gc);
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg)
+        if (gg == g) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[gg][i] += v[i];
+        }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (g > 0) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs_sm[(size_t)rl * p.C + cl * 8 + i] = acc[g][i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      float t = 0.f;
+      for (int l = 0; l < p.rpar; ++l) t += cs_sm[(size_t)l * p.C + c];
+      p.partials[((size_t)blockIdx.x * NG + g) * p.C + c] = t;
     }
   }
 }
 
-__global__ void __launch_bounds__(256) colsum_fold_kernel(const float* partials, int chunks, long long n, float scale, float* out, int out_ld,
-                                                          int C, int accumulate) {
+__global__ void __launch_bounds__(256) colsum_fold_kernel(const ColsumGParams p, int blocks, float scale, float* out, int out_ld, int accumulate) {
+  const long long n = (long long)p.groups * p.C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i / p.C);
+    const int c = (int)(i - (long long)g * p.C);
     float t = 0.f;
-    for (int b = 0; b < chunks; ++b) t += partials[(size_t)b * n + i];
-    const long long g = i / C;
-    const int c = (int)(i - g * C);
+    if (p.mode == 1) {
+      for (int b = g * p.sub; b < (g + 1) * p.sub; ++b) t += p.partials[(size_t)b * p.C + c];
+    } else if (p.mode == 3) {
+      const int runs = blocks / p.sub;
+      for (int run = g; run < runs; run += p.gc)
+        for (int s = 0; s < p.sub; ++s) t += p.partials[((size_t)run * p.sub + s) * p.C + c];
+    } else {
+      for (int b = 0; b < blocks; ++b) t += p.partials[((size_t)b * p.gc + g) * p.C + c];
+    }
+    float* o = out + (size_t)g * out_ld + c;
+    *o = accumulate ? *o + scale * t : scale * t;
+  }
+}
+
+// scalar fallback for widths that are not multiples of 8 (one thread per column)
+__global__ void __launch_bounds__(256) colsum_scalar_kernel(const ColsumGParams p, float scale, float* out, int out_ld, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  for (int g = 0; g < p.groups; ++g) {
+    float t = 0.f;
+    for (long long r = 0; r < p.rows; ++r) {
+      int gr;
+      if (p.mode == 1) gr = (int)(r / p.ga);
+      else if (p.mode == 2) gr = (int)((((r / p.ga) * p.gb) + (r % p.gb)) % p.gc);
+      else gr = (int)((r / p.ga) % p.gc);
+      if (gr == g) t += __bfloat162float(p.x[(size_t)r * p.ld + c]);
+    }
     float* o = out + (size_t)g * out_ld + c;
     *o = accumulate ? *o + scale * t : scale * t;
   }
@@ -361,28 +408,69 @@ extern "C" int pt_small_linear_bwd(const PtSmallLinearBwdArgs* a, void* stream) 
 
 extern "C" int64_t pt_colsum_grouped_workspace_bytes(int64_t rows, int32_t groups, int32_t C) {
   if (rows <= 0 || groups <= 0 || C <= 0) return -1;
-  long long chunks = (rows + 1023) / 1024;
-  if (chunks > 592) chunks = 592;
-  return (int64_t)chunks * groups * C * (int64_t)sizeof(float);
+  return (int64_t)kCsMaxBlocks * C * (int64_t)sizeof(float);
 }
 
 extern "C" int pt_colsum_grouped(const PtColsumGroupedArgs* a, void* stream) {
   PT_CHECK_ARG(a != nullptr && a->x && a->out && a->workspace && a->rows > 0 && a->C > 0, "pt_colsum_grouped: bad argument");
-  PT_CHECK_ARG(a->groups > 0 && a->groups <= kCsMaxGroups, "pt_colsum_grouped: 1..40 groups");
+  PT_CHECK_ARG(a->groups > 0, "pt_colsum_grouped: groups must be positive");
   PT_CHECK_ARG(a->mode >= 1 && a->mode <= 3 && a->ga > 0 && (a->mode == 1 || a->gc > 0) && (a->mode != 2 || a->gb > 0), "pt_colsum_grouped: bad grouping");
+  if (a->C > 2048 && a->C % 8 == 0) {
+    // wide rows (the GEGLU projections of levels 1-3: 5120 / 10240 columns): column blocks of 2048, one after the other
+    // on the stream (they share the workspace)
+    for (int c0 = 0; c0 < a->C; c0 += 2048) {
+      PtColsumGroupedArgs b = *a;
+      b.x = reinterpret_cast<const bf16*>(a->x) + c0;
+      b.C = a->C - c0 < 2048 ? a->C - c0 : 2048;
+      b.out = a->out + c0;
+      const int rc = pt_colsum_grouped(&b, stream);
+      if (rc != 0) return rc;
+    }
+    return 0;
+  }
   ColsumGParams p;
   p.x = reinterpret_cast<const bf16*>(a->x); p.ld = a->ld; p.rows = a->rows; p.C = a->C; p.groups = a->groups;
-  p.mode = a->mode; p.ga = a->ga; p.gb = a->gb; p.gc = a->gc;
-  long long chunks = (a->rows + 1023) / 1024;
-  if (chunks > 592) chunks = 592;
-  p.rows_per_cta = (int)((a->rows + chunks - 1) / chunks);
+  p.mode = a->mode; p.ga = a->ga; p.gb = a->gb > 0 ? a->gb : 1; p.gc = a->gc > 0 ? a->gc : 1;
   p.partials = reinterpret_cast<float*>(a->workspace);
-  const size_t smem = (size_t)a->groups * 256 * sizeof(float);
-  pt_launch(colsum_grouped_kernel, dim3((a->C + 31) / 32, (unsigned)chunks), dim3(256), smem, stream, 1, p);
+  const bool vec = a->C % 8 == 0 && a->ld % 8 == 0 && ((uintptr_t)a->x % 16 == 0) && a->C <= 4096;
+  const long long runs = (a->rows + a->ga - 1) / a->ga;
+  if (!vec || (a->mode != 2 && (runs > kCsMaxBlocks || a->rows % a->ga != 0)) || (a->mode == 2 && p.gc > 4)) {
+    p.sub = 1; p.rows_per_cta = 0; p.cvec = 0; p.rpar = 0;
+    pt_launch(colsum_scalar_kernel, dim3((a->C + 255) / 256), dim3(256), 0, stream, 1, p, a->scale, a->out, (int)a->out_ld, (int)a->accumulate);
+    return pt_launched("pt_colsum_grouped (scalar)");
+  }
+  p.cvec = a->C / 8;
+  p.rpar = 512 / p.cvec;
+  if (p.rpar < 1) p.rpar = 1;
+  const int threads = p.cvec * p.rpar;
+  const size_t smem = (size_t)p.rpar * a->C * sizeof(float);
+  int blocks;
+  if (a->mode == 2) {
+    long long chunks = (a->rows + 4LL * p.rpar - 1) / (4LL * p.rpar);
+    if (chunks > 512) chunks = 512;
+    if (chunks < 1) chunks = 1;
+    p.sub = (int)chunks;
+    p.rows_per_cta = (int)((a->rows + chunks - 1) / chunks);
+    blocks = (int)chunks;
+    switch (p.gc) {
+      case 1: pt_launch(colsum_grouped_kernel<1>, dim3(blocks), dim3(threads), smem, stream, 1, p); break;
+      case 2: pt_launch(colsum_grouped_kernel<2>, dim3(blocks), dim3(threads), smem, stream, 1, p); break;
+      case 3: pt_launch(colsum_grouped_kernel<3>, dim3(blocks), dim3(threads), smem, stream, 1, p); break;
+      default: pt_launch(colsum_grouped_kernel<4>, dim3(blocks), dim3(threads), smem, stream, 1, p); break;
+    }
+  } else {
+    long long sub = 592 / runs;
+    const long long max_sub = ((long long)a->ga + 4LL * p.rpar - 1) / (4LL * p.rpar);
+    if (sub > max_sub) sub = max_sub;
+    if (sub < 1) sub = 1;
+    p.sub = (int)sub;
+    p.rows_per_cta = (int)(((long long)a->ga + sub - 1) / sub);
+    blocks = (int)(runs * sub);
+    pt_launch(colsum_grouped_kernel<1>, dim3(blocks), dim3(threads), smem, stream, 1, p);
+  }
   int rc = pt_launched("pt_colsum_grouped");
   if (rc != 0) return rc;
   const long long n = (long long)a->groups * a->C;
-  pt_launch(colsum_fold_kernel, dim3(grid_1d(n, 256)), dim3(256), 0, stream, 1, (const float*)p.partials, (int)chunks, n, a->scale, a->out,
-            (int)a->out_ld, (int)a->C, (int)a->accumulate);
+  pt_launch(colsum_fold_kernel, dim3(grid_1d(n, 256)), dim3(256), 0, stream, 1, p, blocks, a->scale, a->out, (int)a->out_ld, (int)a->accumulate);
   return pt_launched("pt_colsum_grouped (fold)");
 }

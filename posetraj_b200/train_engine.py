@@ -81,10 +81,11 @@ class Tape:
         self.gs: Dict[int, torch.Tensor] = {}  # storage ptr of a small fp32 forward buffer -> zero-initialised gradient
         self.wg: Dict[tuple, torch.Tensor] = {}  # (kind, key) of the WeightStore -> fp32 gradient in the KERNEL layout
         self.need: set = set()
-        self._wd: Dict[tuple, torch.Tensor] = {}
         self.on_weight_done = on_weight_done
         self._uses: Dict[tuple, int] = {}
         self.flushed: set = set()
+        # every Tape of a trained plan is a new optimizer step: cached transposed weights are stale
+        self.step_id = plan.__dict__["_tape_steps"] = plan.__dict__.get("_tape_steps", 0) + 1
 
     # ---------------------------------------------------------------------------------------------------------
     # requires-grad sweep
@@ -212,17 +213,21 @@ class Tape:
         self._weight_used(wt)
 
     def dgrad_weight(self, w: torch.Tensor, T: int, n_pad: int) -> torch.Tensor:
-        """[N, T*K] -> [K, T*n_pad] (zero columns for the padded output channels); cached for frozen weights."""
+        """[N, T*K] -> [K, T*n_pad] with Wd[k, t*n_pad + n] = W[n, t*K + k] (zero columns for padded output channels):
+        the B operand of the dgrad GEMM.  Kept on the plan: computed once for frozen weights, re-derived in place (one
+        pt_transpose_bf16 per tap) the first time it is needed in every step for trained ones."""
+        cache = self.plan.__dict__.setdefault("_dgrad_w", {})
         k = (w.data_ptr(), T, n_pad)
-        if not self.trainable and k in self._wd:
-            return self._wd[k]
-        if n_pad != w.shape[0]:
-            wp = torch.zeros(n_pad, w.shape[1], device=w.device, dtype=BF16)
-            wp[: w.shape[0]] = w
-            w = wp
-        wd = training.dgrad_weight(w, T)
-        if not self.trainable:
-            self._wd[k] = wd
+        ent = cache.get(k)
+        if ent is not None and (not self.trainable or ent[1] == self.step_id):
+            return ent[0]
+        N, K = w.shape[0], w.shape[1] // T
+        wd = ent[0] if ent is not None else torch.zeros(K, T * n_pad, device=w.device, dtype=BF16)
+        sp = _sp()
+        for t in range(T):
+            _lib.check(_lib.lib().pt_transpose_bf16(w.data_ptr() + 2 * t * K, w.stride(0), wd.data_ptr() + 2 * t * n_pad, wd.stride(0), N, K, sp),
+                       "pt_transpose_bf16")
+        cache[k] = (wd, self.step_id)
         return wd
 
     # ---------------------------------------------------------------------------------------------------------
