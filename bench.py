@@ -550,6 +550,7 @@ def train_step_leg(cfg, unet, dev, rank, world, barrier, steps=3):
     cnet = ControlNetSDVModel.from_random(cfg, dev, seed=5, bbox=True, faithful_zero_init=False)
     torch.cuda.reset_peak_memory_stats(dev)
     tr = ControlNetTrainer(unet, cnet, batch=B, frames=Fr, height=H, width=W, lr=1e-5)
+    tr.use_cuda_graph = os.environ.get("PT_TRAIN_GRAPH", "1") != "0"
     g = torch.Generator(device=dev).manual_seed(11 + rank)
     rn = lambda *s: torch.randn(*s, device=dev, generator=g)
     batch = dict(latents=rn(B, Fr, 4, H, W) * 0.9, noise=rn(B, Fr, 4, H, W), sigmas=torch.tensor([1.3, 0.4], device=dev),
@@ -558,19 +559,26 @@ def train_step_leg(cfg, unet, dev, rank, world, barrier, steps=3):
                  motion_values=torch.tensor([127.0, 90.0], device=dev),
                  controlnet_bbox=(torch.rand(B, Fr, 3, 8 * H, 8 * W, device=dev, generator=g) > 0.98).float() * 2 - 1)
     losses = [float(tr.step(ran_idx=3, **batch))]           # warm-up (TMA descriptors, attribute caches, NCCL)
+    losses.append(float(tr.step(ran_idx=3, **batch)))       # (graph mode: this call captures and replays once)
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * steps + 1)]
     lc0 = int(_lib_launches())
     ev[0].record()
     for i in range(steps):
-        loss = tr.forward_backward(ran_idx=3, **batch)
+        if tr.use_cuda_graph:
+            for k, v in batch.items():
+                tr._static[k].copy_(v, non_blocking=True)
+            tr._graphs[3].replay()
+            loss = tr.loss
+        else:
+            loss = tr.forward_backward(ran_idx=3, **batch)
         ev[3 * i + 1].record()
         tr.optimizer_step()
         ev[3 * i + 2].record()
         ev[3 * i + 3].record()
         losses.append(loss.clone())                          # (device copy; read after the timed region)
     barrier()
-    launches = (int(_lib_launches()) - lc0) / steps
+    launches = tr.graph_launches if tr.use_cuda_graph else (int(_lib_launches()) - lc0) / steps
     ms_step = _max_over_ranks(ev[0].elapsed_time(ev[3 * steps]) / steps, dev, world)
     ms_fb = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(steps)) / steps
     ms_tail = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(steps)) / steps
@@ -579,7 +587,7 @@ def train_step_leg(cfg, unet, dev, rank, world, barrier, steps=3):
                        "spatial pass, reverse pass, all-reduce, AdamW), 2 videos x 14 frames x 320x576 per GPU, data-parallel",
            "ms_per_step": ms_step, "value": 1000.0 * B * world / ms_step, "unit": "videos/s (global batch %d)" % (B * world),
            "forward_backward_ms": ms_fb, "allreduce_wait_adamw_refresh_ms": ms_tail,
-           "kernel_launches_per_step": launches, "losses": losses[:4],
+           "kernel_launches_per_step": launches, "cuda_graph": bool(tr.use_cuda_graph), "losses": losses[:5],
            "loss_decreases": bool(losses[-1] < losses[0]),
            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
            "params_trained": int(sum(tr.buckets.sizes)), "dtype": "bf16 activations / gradients, fp32 master weights + AdamW"}

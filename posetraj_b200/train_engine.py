@@ -538,9 +538,14 @@ class ControlNetTrainer:
         if use_spatial:
             self.splan = NetPlan("unet", unet.cfg, unet.weights, batch=batch, frames=1, height=height, width=width, device=dev, train=True)
         self.loss = torch.zeros(1, device=dev, dtype=F32)
-        P0 = (height + 1) * (width + 1)
         self._written: set = set()
-        self.last = {}
+        # CUDA-graph replay of forward + backward (one graph per `ran_idx`, sharing one memory pool): the eager step is
+        # ~5 700 launches whose host cost (descriptor objects, ctypes calls, allocator) is as long as the device time
+        self.use_cuda_graph = False
+        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._pool = None
+        self._static: Optional[Dict[str, torch.Tensor]] = None
+        self.graph_launches = 0
 
     # ---------------------------------------------------------------------------------------------------------
     def _stage(self, plan: NetPlan, inp: torch.Tensor, timesteps, ehs, ids) -> None:
@@ -660,7 +665,6 @@ class ControlNetTrainer:
             if i not in self._written:
                 self.buckets.view(i).zero_()
                 self.buckets.ready(i)
-        self.last = dict(unet_tape=tu, cnet_tape=tc)
         return self.loss
 
     def gradients(self) -> Dict[str, torch.Tensor]:
@@ -673,10 +677,38 @@ class ControlNetTrainer:
         self.cw.refresh()
         self._refresh_alphas()
 
-    def step(self, **batch) -> torch.Tensor:
-        loss = self.forward_backward(**batch)
+    def step(self, *, ran_idx: int = 0, **batch) -> torch.Tensor:
+        """One optimizer step.  With `use_cuda_graph` the first call runs eagerly (it fills every cache: kernel attributes,
+        the frozen UNet's transposed weights, NCCL communicators); from the second call on forward + backward (and the
+        bucket all-reduces) replay as one captured graph per `ran_idx`, fed through static input buffers."""
+        if not self.use_cuda_graph:
+            loss = self.forward_backward(ran_idx=ran_idx, **batch)
+            self.optimizer_step()
+            return loss
+        batch = {k: v for k, v in batch.items() if v is not None}
+        if self._static is None:
+            self._static = {k: v.detach().to(self.dev).clone() for k, v in batch.items()}
+            loss = self.forward_backward(ran_idx=ran_idx, **self._static)
+            self.optimizer_step()
+            return loss
+        if set(batch) != set(self._static):
+            raise ValueError("cuda-graph training step: the set of inputs must not change between steps")
+        for k, v in batch.items():
+            self._static[k].copy_(v, non_blocking=True)
+        g = self._graphs.get(ran_idx)
+        if g is None:
+            from . import _lib as _l
+            n0 = _l.lib().pt_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._pool):
+                self.forward_backward(ran_idx=ran_idx, **self._static)
+                self.buckets.finish()           # joins the all-reduce stream back into the capture
+            self.graph_launches = int(_l.lib().pt_launch_count() - n0)
+            self._graphs[ran_idx] = g
+            self._pool = g.pool()
+        g.replay()
         self.optimizer_step()
-        return loss
+        return self.loss
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {k: v.clone() for k, v in self.master.items()}

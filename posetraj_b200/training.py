@@ -89,7 +89,7 @@ def dot(a_: torch.Tensor, b_: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
 
 def to_halo(x: torch.Tensor, n: int, H: int, W: int) -> torch.Tensor:
     """compact [n*H*W, C] -> zero-haloed [n*(H+1)*(W+1), C] (the layout conv inputs / conv output gradients live in)."""
-    out = torch.zeros(n * (H + 1) * (W + 1), x.shape[1], device=x.device, dtype=BF16)
+    out = torch.empty(n * (H + 1) * (W + 1), x.shape[1], device=x.device, dtype=BF16)   # the kernel writes the halo rows (zeros) too
     ops.Upsample2x(x, out, n=n, H=H, W=W, halo=True, scale=1).launch(_sp())
     return out
 

@@ -113,3 +113,96 @@ def test_adamw_step_follows_torch(cuda_dev):
     assert (num / den) ** 0.5 < 2e-3           # first AdamW step = lr * sign(g): only near-zero gradients may differ
     l1 = float(tr.step(ran_idx=0, **batch))
     assert l1 < l0, (l0, l1)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# data-parallel step (SURVEY.md 8e "training DP"): world 2 — NCCL on two GPUs (the step replayed as a CUDA graph with the
+# bucket all-reduces captured in it), gloo with both ranks on cuda:0 on a 1-GPU box (eager)
+# -----------------------------------------------------------------------------------------------------------------
+def _dp_worker(rank, port, q, two_gpus):
+    try:
+        import sys
+        import torch.distributed as dist
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        sys.path.insert(0, os.path.join(root, "tests"))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="2")
+        dev = torch.device("cuda", rank if two_gpus else 0)
+        torch.cuda.set_device(dev)
+        if two_gpus:
+            dist.init_process_group("nccl", rank=rank, world_size=2, device_id=dev)
+        else:
+            dist.init_process_group("gloo", rank=rank, world_size=2)
+        from posetraj_b200.models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+        from posetraj_b200.train_engine import ControlNetTrainer
+        cfg = small_cfg()
+        unet = UNetSpatioTemporalConditionControlNetModel.from_random(cfg, dev, seed=0)
+        cnet = ControlNetSDVModel.from_random(cfg, dev, seed=3, bbox=True, faithful_zero_init=False)
+        batches = []
+        for r in range(2):
+            b, bm = make_batch(cfg, seed=40 + r)
+            b["controlnet_bbox"] = bm
+            batches.append({k: v.to(dev) for k, v in b.items()})
+        out = {}
+        # every rank computes BOTH per-sample-batch gradients alone (no group): the expected average
+        solo = ControlNetTrainer(unet, cnet, batch=2, frames=cfg.num_frames, height=16, width=24, group=dist.new_group([rank]))
+        want = None
+        for r in range(2):
+            solo.forward_backward(ran_idx=1, **batches[r])
+            solo.buckets.finish()
+            g = torch.cat([f.clone() for f in solo.buckets.flat])
+            want = g if want is None else want + g
+        want = want / 2
+        del solo
+        tr = ControlNetTrainer(unet, cnet, batch=2, frames=cfg.num_frames, height=16, width=24, lr=1e-4)
+        tr.use_cuda_graph = two_gpus
+        losses = []
+        # step 1 (always eager): the all-reduced buckets hold the SUM of the two ranks' gradients
+        loss = tr.forward_backward(ran_idx=1, **batches[rank])
+        tr.buckets.finish()
+        got = torch.cat([f.clone() for f in tr.buckets.flat]) / 2
+        out["grad_err"] = float((got - want).norm() / want.norm())
+        losses.append(float(loss))
+        tr.optimizer_step()
+        for it in range(3):          # graph mode: eager (fills the static inputs), capture + replay, replay
+            losses.append(float(tr.step(ran_idx=1, **batches[rank])))
+        params = torch.cat([m.reshape(-1) for m in tr.opt.master])
+        gathered = [torch.empty_like(params) for _ in range(2)]
+        dist.all_gather(gathered, params)
+        out["param_diff"] = float((gathered[0] - gathered[1]).abs().max())
+        out["losses"] = losses
+        q.put((rank, out))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, {"error": traceback.format_exc()}))
+
+
+def test_data_parallel_step_world2():
+    import socket
+    import torch.multiprocessing as mp
+    two_gpus = torch.cuda.device_count() >= 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, port, q, two_gpus)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    try:
+        for _ in range(2):
+            rank, out = q.get(timeout=400)
+            assert "error" not in out, out.get("error")
+            res[rank] = out
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for r in (0, 1):
+        assert res[r]["grad_err"] < 1e-5, res[r]          # all-reduced gradient = mean of the two ranks' gradients
+        assert res[r]["param_diff"] == 0.0, res[r]        # both ranks hold identical parameters after 3 steps
+        assert all(l == l for l in res[r]["losses"])
