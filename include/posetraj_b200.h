@@ -550,11 +550,11 @@ int pt_adamw(const PtAdamWArgs* a, void* stream);
 
 /* Weight gradient of a linear / implicit-GEMM conv layer (oracle/backward.py conv_rows_wgrad):                  */
 /*   dW[n, t*K + k] = sum_r dD[r, n] * A[r + shift_t, k]                                                         */
-/* tcgen05: A operand = dD^T (K-major over rows, from pt_transpose_bf16), B operand = the layer's input rows as an */
-/* MN-major tile (tap = row shift of the TMA coordinate, out-of-range rows zero-filled like the forward).  Rows are */
-/* split over `splits` CTAs per output tile; fp32 partial tiles are folded in order by pt_reduce_partials.        */
+/* tcgen05, both operands MN-major, i.e. read in the layout the tensors already have: tap = row shift of the TMA           */
+/* coordinate of the input (out-of-range rows zero-filled like the forward).  Rows are split over `splits` CTAs per      */
+/* output tile (128 n x up to 256 k); fp32 partial tiles are folded in order by pt_reduce_partials.                       */
 typedef struct PtWgradArgs {
-  const PtTensorMap* tmap_dt;   /* dD^T bf16 [N, rows]: rank-2 {rows, N}, box {64, 128} */
+  const PtTensorMap* tmap_dt;   /* dD bf16 [rows, N] (the gradient itself, no transpose): rank-2 {N, rows}, box {64, 64} */
   const PtTensorMap* tmap_a;    /* layer input bf16 [rows, K]: rank-2 {K, rows}, box {64, 64} */
   int32_t rows, N, K, num_taps;
   int32_t tap_shift[9];

@@ -122,8 +122,8 @@ def linear_dgrad(dout: torch.Tensor, w: torch.Tensor, *, taps: Sequence[int] = (
 
 def wgrad(dout: torch.Tensor, a: torch.Tensor, *, taps: Sequence[int] = (0,), splits: Optional[int] = None,
           scale: float = 1.0, out: Optional[torch.Tensor] = None, accumulate: bool = False, batches: int = 1) -> torch.Tensor:
-    """fp32 dW[n, t*K + k] = scale * sum_r dD[r, n] A[r + s_t, k] (pt_wgrad on tcgen05 + fixed-order fold of the row
-    slices).  `dout` [rows, N] and `a` [rows, K] share one row space (zero-haloed for convs).  `batches` > 1: the taps
+    """fp32 dW[n, t*K + k] = scale * sum_r dD[r, n] A[r + s_t, k] (pt_wgrad on tcgen05, both operands read as they are,
+    + fixed-order fold of the row slices).  `dout` [rows, N] and `a` [rows, K] share one row space (zero-haloed for convs).  `batches` > 1: the taps
     must not reach across batch rows (temporal convs: frame f +- 1 of the SAME video), so each batch is its own launch
     whose out-of-range rows are zero-filled by TMA, exactly like the forward's rank-3 tensor map."""
     _check(dout, BF16), _check(a, BF16)
@@ -137,12 +137,12 @@ def wgrad(dout: torch.Tensor, a: torch.Tensor, *, taps: Sequence[int] = (0,), sp
     K = a.shape[1]
     assert a.shape[0] == rows and K % 64 == 0 and a.stride(1) == 1
     T = len(taps)
-    dt = transpose(dout)                                   # [N, rows] (padded stride)
-    tiles = T * ((N + 127) // 128) * (K // 64)
+    assert dout.stride(1) == 1 and dout.stride(0) % 8 == 0 and N % 8 == 0
+    tiles = T * ((N + 127) // 128) * ((K // 64 + 3) // 4)
     if splits is None:
         splits = max(1, min((rows + 63) // 64, (2 * ops.NUM_SMS + tiles - 1) // tiles))
     partials = torch.empty(splits, N, T * K, device=dout.device, dtype=F32)
-    tm_dt = _lib.encode_tensormap(dt.data_ptr(), [rows, N], [dt.stride(0) * 2], [64, 128])
+    tm_dt = _lib.encode_tensormap(dout.data_ptr(), [N, rows], [dout.stride(0) * 2], [64, 64])
     tm_a = _lib.encode_tensormap(a.data_ptr(), [K, rows], [a.stride(0) * 2], [64, 64])
     args = _lib.PtWgradArgs()
     args.tmap_dt, args.tmap_a = C.addressof(tm_dt), C.addressof(tm_a)
