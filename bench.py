@@ -630,8 +630,48 @@ def library_baseline_leg(dev, steps=3):
     ms = sum(times) / len(times)
     del unet, cnet
     torch.cuda.empty_cache()
-    return {"what": "torch 2.11 eager bf16 of the same wiring (cuDNN / cuBLAS / SDPA), same GPU, same shapes",
-            "ms_per_step": ms, "value": 1000.0 / ms, "unit": UNIT}
+    res = {"what": "torch 2.11 eager bf16 of the same wiring (cuDNN / cuBLAS / SDPA), same GPU, same shapes",
+           "ms_per_step": ms, "value": 1000.0 / ms, "unit": UNIT}
+    # the same bar for the configs[3] training step: torch autograd + torch.optim.AdamW (fused) on the bbox models in bf16
+    try:
+        from oracle.train import training_step
+        torch.manual_seed(0)
+        with torch.device(dev):
+            unet, cnet = build_models(seed=0, bbox=True, randomize_zero_convs=False)   # (zero-convs at zero: same kernels, same time)
+        unet, cnet = unet.to(torch.bfloat16).requires_grad_(False), cnet.to(torch.bfloat16).requires_grad_(True)
+        opt = torch.optim.AdamW(cnet.parameters(), lr=1e-5, fused=True)
+        g = torch.Generator(device=dev).manual_seed(11)
+        B = 2
+        rn = lambda *sh: torch.randn(*sh, device=dev, generator=g).to(torch.bfloat16)
+        batch = dict(latents=rn(B, FRAMES, 4, LAT_H, LAT_W) * 0.9, noise=rn(B, FRAMES, 4, LAT_H, LAT_W),
+                     sigmas=torch.tensor([1.3, 0.4], device=dev), image_embeddings=rn(B, 1, 1024),
+                     trajectories=((torch.rand(B, FRAMES, 3, 8 * LAT_H, 8 * LAT_W, device=dev, generator=g) > 0.97).float() * 2 - 1).to(torch.bfloat16),
+                     motion_values=torch.tensor([127.0, 90.0], device=dev))
+        bbox = ((torch.rand(B, FRAMES, 3, 8 * LAT_H, 8 * LAT_W, device=dev, generator=g) > 0.98).float() * 2 - 1).to(torch.bfloat16)
+
+        def cn(*a, **k):
+            return cnet(*a, controlnet_bbox=bbox, **k)
+
+        times = []
+        for i in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = training_step(unet, cn, ran_idx=3, **batch)
+            out["loss"].backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 1:
+                times.append(e0.elapsed_time(e1))
+        res["train_step"] = {"what": "torch eager bf16 autograd + fused AdamW of the configs[3] step (bbox ControlNet, 2 videos x 14 frames x 320x576)",
+                             "ms_per_step": sum(times) / len(times), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        del unet, cnet, opt, out
+    except Exception as e:  # noqa: BLE001 - a comparator must not take the line down
+        res["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_own(args):

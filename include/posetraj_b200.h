@@ -625,8 +625,10 @@ typedef struct PtSmallLinearBwdArgs {
   float* dw;                /* fp32 [N, K] contiguous or NULL */
   float* db;                /* fp32 [N] or NULL (written with dw) */
   int32_t accumulate_w;
+  void* dx_workspace;       /* pt_small_linear_bwd_workspace_bytes(M, N, K) when dx is wanted */
 } PtSmallLinearBwdArgs;
 int pt_small_linear_bwd(const PtSmallLinearBwdArgs* a, void* stream);
+int64_t pt_small_linear_bwd_workspace_bytes(int32_t M, int32_t N, int32_t K);
 
 /* out[g, c] (+)= scale * sum over rows r with group(r) == g of x[r, c]; group(r) =
  *   mode 1: r / ga            mode 2: ((r / ga) * gb + r % gb) % gc  (PtGemmArgs.rowvec_mode 1 / 2)

@@ -198,7 +198,8 @@ PtAttnTemporalBwdArgs = _st("PtAttnTemporalBwdArgs", [
 
 PtSmallLinearBwdArgs = _st("PtSmallLinearBwdArgs", [
     ("x", vp), ("x_ld", i32), ("w", vp), ("w_ld", i32), ("dy", vp), ("dy_ld", i32), ("M", i32), ("N", i32), ("K", i32),
-    ("act_in_silu", i32), ("dx", vp), ("dx_ld", i32), ("accumulate_dx", i32), ("dw", vp), ("db", vp), ("accumulate_w", i32)])
+    ("act_in_silu", i32), ("dx", vp), ("dx_ld", i32), ("accumulate_dx", i32), ("dw", vp), ("db", vp), ("accumulate_w", i32),
+    ("dx_workspace", vp)])
 
 PtColsumGroupedArgs = _st("PtColsumGroupedArgs", [
     ("x", vp), ("ld", i32), ("rows", i64), ("C", i32), ("groups", i32), ("mode", i32), ("ga", i32), ("gb", i32), ("gc", i32),
@@ -268,6 +269,7 @@ _SIGNATURES = {
     "pt_silu_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "pt_silu_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "pt_small_linear_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pt_small_linear_bwd_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "pt_colsum_grouped": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pt_colsum_grouped_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
 }

@@ -173,12 +173,24 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColsumParams p) {
   }
 }
 
-// out[i] (+)= scale * sum_b partials[b][i], b in order
+// out[i] (+)= scale * sum_b partials[b][i]: 32 elements x 8 slices of b per CTA, slices folded in order (deterministic)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* partials, int nb, long long n, float scale, float* out, int accumulate) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  __shared__ float sm[8][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (long long i0 = (long long)blockIdx.x * 32; i0 < n; i0 += (long long)gridDim.x * 32) {
+    const long long i = i0 + cl;
     float t = 0.f;
-    for (int b = 0; b < nb; ++b) t += partials[(size_t)b * n + i];
-    out[i] = accumulate ? out[i] + scale * t : scale * t;
+    if (i < n)
+      for (int b = sl; b < nb; b += 8) t += partials[(size_t)b * n + i];
+    sm[sl][cl] = t;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+      float tt = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tt += sm[k][cl];
+      out[i] = accumulate ? out[i] + scale * tt : scale * tt;
+    }
+    __syncthreads();
   }
 }
 
@@ -186,22 +198,45 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* parti
 __global__ void __launch_bounds__(256) dot_kernel(const bf16* a, int lda, const bf16* b, int ldb, long long rows, int C, double* partials) {
   __shared__ double red[32];
   double acc = 0.0;
-  const long long total = rows * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / C;
-    const int c = (int)(i - r * C);
-    acc += (double)(__bfloat162float(a[(size_t)r * lda + c]) * __bfloat162float(b[(size_t)r * ldb + c]));
+  if ((C & 7) == 0 && (lda & 7) == 0 && (ldb & 7) == 0) {   // 8 elements (16 bytes) per thread and operand
+    const int cv = C >> 3;
+    const long long total = rows * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / cv;
+      const int c = (int)(i - r * cv) * 8;
+      const uint4 ua = ldg_u4(a + (size_t)r * lda + c), ub = ldg_u4(b + (size_t)r * ldb + c);
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(&ua);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(&ub);
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = unpack_bf16x2(pa[k]), y = unpack_bf16x2(pb[k]);
+        t = fmaf(x.x, y.x, t);
+        t = fmaf(x.y, y.y, t);
+      }
+      acc += (double)t;
+    }
+  } else {
+    const long long total = rows * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / C;
+      const int c = (int)(i - r * C);
+      acc += (double)(__bfloat162float(a[(size_t)r * lda + c]) * __bfloat162float(b[(size_t)r * ldb + c]));
+    }
   }
   const double t = block_sum_d(acc, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
-__global__ void dot_final_kernel(const double* partials, int nb, float scale, float* out, int accumulate) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double t = 0.0;
-  for (int i = 0; i < nb; ++i) t += partials[i];
-  const float v = (float)(t * scale);
-  out[0] = accumulate ? out[0] + v : v;
+__global__ void __launch_bounds__(256) dot_final_kernel(const double* partials, int nb, float scale, float* out, int accumulate) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) acc += partials[i];   // fixed thread -> element map: deterministic
+  const double t = block_sum_d(acc, red);
+  if (threadIdx.x == 0) {
+    const float v = (float)(t * scale);
+    out[0] = accumulate ? out[0] + v : v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -294,7 +329,7 @@ extern "C" int pt_colsum(const PtColsumArgs* a, void* stream) {
 
 extern "C" int pt_reduce_partials(const float* partials, int32_t nb, int64_t n, float scale, float* out, int32_t accumulate, void* stream) {
   PT_CHECK_ARG(partials && out && nb > 0 && n > 0, "pt_reduce_partials: bad argument");
-  pt_launch(reduce_partials_kernel, dim3(grid_for(n)), dim3(256), 0, stream, 1, partials, (int)nb, (long long)n, scale, out, (int)accumulate);
+  pt_launch(reduce_partials_kernel, dim3(grid_for(n, 32, 148 * 8)), dim3(256), 0, stream, 1, partials, (int)nb, (long long)n, scale, out, (int)accumulate);
   return pt_launched("pt_reduce_partials");
 }
 
@@ -306,7 +341,7 @@ extern "C" int pt_dot_bf16(const void* a, int32_t lda, const void* b, int32_t ld
             (int)ldb, (long long)rows, (int)cols, reinterpret_cast<double*>(workspace));
   int rc = pt_launched("pt_dot_bf16");
   if (rc) return rc;
-  pt_launch(dot_final_kernel, dim3(1), dim3(32), 0, stream, 1, (const double*)workspace, blocks, scale, out, (int)accumulate);
+  pt_launch(dot_final_kernel, dim3(1), dim3(256), 0, stream, 1, (const double*)workspace, blocks, scale, out, (int)accumulate);
   return pt_launched("pt_dot_bf16(final)");
 }
 

@@ -195,22 +195,29 @@ __global__ void __launch_bounds__(256) small_linear_dw_kernel(const SlBwdParams 
   }
 }
 
-__global__ void __launch_bounds__(256) small_linear_dx_kernel(const SlBwdParams p) {
-  // one CTA per (m, block of 256 k); the dy row is staged through shared memory in chunks
+// grid (K / 256, M, N slabs of 1024): each CTA sums its slab of n for 256 k; slabs are folded by small_linear_dx_fold_kernel
+__global__ void __launch_bounds__(256) small_linear_dx_kernel(const SlBwdParams p, float* partial) {
   __shared__ float sdy[1024];
   const int m = blockIdx.y;
   const int k = blockIdx.x * 256 + threadIdx.x;
+  const int n0 = blockIdx.z * 1024;
+  const int nn = min(1024, p.N - n0);
+  for (int j = threadIdx.x; j < nn; j += 256) sdy[j] = p.dy[(size_t)m * p.dy_ld + n0 + j];
+  __syncthreads();
+  if (k >= p.K) return;
   float acc = 0.f;
-  for (int n0 = 0; n0 < p.N; n0 += 1024) {
-    const int nn = min(1024, p.N - n0);
-    __syncthreads();
-    for (int j = threadIdx.x; j < nn; j += 256) sdy[j] = p.dy[(size_t)m * p.dy_ld + n0 + j];
-    __syncthreads();
-    if (k < p.K) {
-      for (int j = 0; j < nn; ++j) acc = fmaf(sdy[j], __bfloat162float(p.w[(size_t)(n0 + j) * p.w_ld + k]), acc);
-    }
-  }
-  if (k < p.K) {
+  const bf16* w = p.w + (size_t)n0 * p.w_ld + k;
+#pragma unroll 4
+  for (int j = 0; j < nn; ++j) acc = fmaf(sdy[j], __bfloat162float(w[(size_t)j * p.w_ld]), acc);
+  partial[((size_t)blockIdx.z * p.M + m) * p.K + k] = acc;
+}
+
+__global__ void __launch_bounds__(256) small_linear_dx_fold_kernel(const SlBwdParams p, const float* partial, int slabs) {
+  const long long total = (long long)p.M * p.K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / p.K), k = (int)(i - (long long)m * p.K);
+    float acc = 0.f;
+    for (int s2 = 0; s2 < slabs; ++s2) acc += partial[(size_t)s2 * total + i];
     if (p.act_in_silu) acc *= silu_grad(p.x[(size_t)m * p.x_ld + k]);
     float* o = p.dx + (size_t)m * p.dx_ld + k;
     *o = p.accumulate_dx ? *o + acc : acc;
@@ -296,23 +303,35 @@ __global__ void __launch_bounds__(512) colsum_grouped_kernel(const ColsumGParams
   }
 }
 
+// 32 columns x 8 slices of the partial blocks per CTA; blockIdx.y = group
 __global__ void __launch_bounds__(256) colsum_fold_kernel(const ColsumGParams p, int blocks, float scale, float* out, int out_ld, int accumulate) {
-  const long long n = (long long)p.groups * p.C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i / p.C);
-    const int c = (int)(i - (long long)g * p.C);
-    float t = 0.f;
+  __shared__ float sm[8][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int g = blockIdx.y;
+  const int c = blockIdx.x * 32 + cl;
+  float t = 0.f;
+  if (c < p.C) {
     if (p.mode == 1) {
-      for (int b = g * p.sub; b < (g + 1) * p.sub; ++b) t += p.partials[(size_t)b * p.C + c];
+      for (int b = g * p.sub + sl; b < (g + 1) * p.sub; b += 8) t += p.partials[(size_t)b * p.C + c];
     } else if (p.mode == 3) {
       const int runs = blocks / p.sub;
-      for (int run = g; run < runs; run += p.gc)
-        for (int s = 0; s < p.sub; ++s) t += p.partials[((size_t)run * p.sub + s) * p.C + c];
+      const int per_g = (runs - g + p.gc - 1) / p.gc * p.sub;   // partial blocks of this group: run = g + gc*j, s
+      for (int e = sl; e < per_g; e += 8) {
+        const int run = g + p.gc * (e / p.sub), s2 = e % p.sub;
+        t += p.partials[((size_t)run * p.sub + s2) * p.C + c];
+      }
     } else {
-      for (int b = 0; b < blocks; ++b) t += p.partials[((size_t)b * p.gc + g) * p.C + c];
+      for (int b = sl; b < blocks; b += 8) t += p.partials[((size_t)b * p.gc + g) * p.C + c];
     }
+  }
+  sm[sl][cl] = t;
+  __syncthreads();
+  if (sl == 0 && c < p.C) {
+    float tt = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tt += sm[k][cl];
     float* o = out + (size_t)g * out_ld + c;
-    *o = accumulate ? *o + scale * t : scale * t;
+    *o = accumulate ? *o + scale * tt : scale * tt;
   }
 }
 
@@ -387,6 +406,11 @@ extern "C" int pt_silu_bwd(const void* x, int32_t ld, const void* dy, int32_t dy
   return pt_launched("pt_silu_bwd");
 }
 
+extern "C" int64_t pt_small_linear_bwd_workspace_bytes(int32_t M, int32_t N, int32_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return -1;
+  return (int64_t)((N + 1023) / 1024) * M * K * (int64_t)sizeof(float);
+}
+
 extern "C" int pt_small_linear_bwd(const PtSmallLinearBwdArgs* a, void* stream) {
   PT_CHECK_ARG(a != nullptr && a->x && a->w && a->dy && a->M > 0 && a->N > 0 && a->K > 0, "pt_small_linear_bwd: bad argument");
   SlBwdParams p;
@@ -400,8 +424,14 @@ extern "C" int pt_small_linear_bwd(const PtSmallLinearBwdArgs* a, void* stream) 
     if (rc != 0) return rc;
   }
   if (a->dx != nullptr) {
-    pt_launch(small_linear_dx_kernel, dim3((a->K + 255) / 256, a->M), dim3(256), 0, stream, 1, p);
-    return pt_launched("pt_small_linear_bwd (dx)");
+    PT_CHECK_ARG(a->dx_workspace != nullptr, "pt_small_linear_bwd: dx needs dx_workspace (pt_small_linear_bwd_workspace_bytes)");
+    const int slabs = (a->N + 1023) / 1024;
+    float* partial = reinterpret_cast<float*>(a->dx_workspace);
+    pt_launch(small_linear_dx_kernel, dim3((a->K + 255) / 256, a->M, slabs), dim3(256), 0, stream, 1, p, partial);
+    int rc = pt_launched("pt_small_linear_bwd (dx)");
+    if (rc != 0) return rc;
+    pt_launch(small_linear_dx_fold_kernel, dim3(grid_1d((long long)a->M * a->K, 256)), dim3(256), 0, stream, 1, p, (const float*)partial, slabs);
+    return pt_launched("pt_small_linear_bwd (dx fold)");
   }
   return 0;
 }
@@ -470,7 +500,7 @@ extern "C" int pt_colsum_grouped(const PtColsumGroupedArgs* a, void* stream) {
   }
   int rc = pt_launched("pt_colsum_grouped");
   if (rc != 0) return rc;
-  const long long n = (long long)a->groups * a->C;
-  pt_launch(colsum_fold_kernel, dim3(grid_1d(n, 256)), dim3(256), 0, stream, 1, p, blocks, a->scale, a->out, (int)a->out_ld, (int)a->accumulate);
+  pt_launch(colsum_fold_kernel, dim3((a->C + 31) / 32, a->groups), dim3(256), 0, stream, 1, p, blocks, a->scale, a->out, (int)a->out_ld,
+            (int)a->accumulate);
   return pt_launched("pt_colsum_grouped (fold)");
 }

@@ -37,12 +37,24 @@ static int grid_cap(long long n, int per_block, int max_blocks) {
   return (int)b;
 }
 
-// out[i] (+)= scale * sum_b partials[b*n + i]
+// out[i] (+)= scale * sum_b partials[b*n + i]: 32 elements x 8 slices of b per CTA, slices folded in order (deterministic)
 __global__ void __launch_bounds__(256) fold_partials_kernel(const float* partials, int nb, long long n, float scale, float* out, int accumulate) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  __shared__ float sm[8][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (long long i0 = (long long)blockIdx.x * 32; i0 < n; i0 += (long long)gridDim.x * 32) {
+    const long long i = i0 + cl;
     float t = 0.f;
-    for (int b = 0; b < nb; ++b) t += partials[(size_t)b * n + i];
-    out[i] = accumulate ? out[i] + scale * t : scale * t;
+    if (i < n)
+      for (int b = sl; b < nb; b += 8) t += partials[(size_t)b * n + i];
+    sm[sl][cl] = t;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+      float tt = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tt += sm[k][cl];
+      out[i] = accumulate ? out[i] + scale * tt : scale * tt;
+    }
+    __syncthreads();
   }
 }
 
@@ -504,7 +516,7 @@ extern "C" int pt_groupnorm_bwd(const PtGroupNormBwdArgs* a, void* stream) {
   if ((rc = pt_launched("pt_groupnorm_bwd (P2)")) != 0) return rc;
   if (a->dgb_out != nullptr) {
     // dgamma | dbeta = the per-channel B | A partials summed over every (statistics group, chunk) in order
-    pt_launch(fold_partials_kernel, dim3(grid_cap(2LL * C, 256, 64)), dim3(256), 0, stream, 1, (const float*)p.part1, a->num_stat * chunks,
+    pt_launch(fold_partials_kernel, dim3(grid_cap(2LL * C, 32, 512)), dim3(256), 0, stream, 1, (const float*)p.part1, a->num_stat * chunks,
               (long long)(2 * C), 1.0f, a->dgb_out, (int)a->accumulate_dgb);
     return pt_launched("pt_groupnorm_bwd (dgamma)");
   }
@@ -548,7 +560,7 @@ extern "C" int pt_layernorm_bwd(const PtLayerNormBwdArgs* a, void* stream) {
   else rc = launch_ln_bwd<8>(p, blocks, smem, stream);
   if (rc) return rc;
   if (a->partials != nullptr && a->dgb_out != nullptr) {
-    pt_launch(fold_partials_kernel, dim3(grid_cap(2LL * a->C, 256, 64)), dim3(256), 0, stream, 1, (const float*)a->partials, blocks,
+    pt_launch(fold_partials_kernel, dim3(grid_cap(2LL * a->C, 32, 512)), dim3(256), 0, stream, 1, (const float*)a->partials, blocks,
               (long long)(2 * a->C), 1.0f, a->dgb_out, (int)a->accumulate_dgb);
     return pt_launched("pt_layernorm_bwd (dgamma)");
   }

@@ -444,7 +444,8 @@ def _bw_small_linear(T: Tape, op: ops.SmallLinear) -> None:
     a.N, a.act_in_silu = io.w.shape[0], int(io.act_in_silu)
     if want_dx:
         dx = T.gsmall(io.x)
-        a.dx, a.dx_ld, a.accumulate_dx = dx.data_ptr(), dx.stride(0), 1
+        ws = torch.empty(_lib.lib().pt_small_linear_bwd_workspace_bytes(a.M, a.N, a.K), device=dx.device, dtype=torch.uint8)
+        a.dx, a.dx_ld, a.accumulate_dx, a.dx_workspace = dx.data_ptr(), dx.stride(0), 1, ws.data_ptr()
     if T.trainable:
         a.dw, a.db, a.accumulate_w = dw.data_ptr(), (db.data_ptr() if db is not None else None), 1
     _lib.check(_lib.lib().pt_small_linear_bwd(training.C.addressof(a), _sp()), "pt_small_linear_bwd")

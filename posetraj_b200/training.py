@@ -653,7 +653,8 @@ def small_linear_backward(x: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, *,
     a.x, a.x_ld, a.w, a.w_ld, a.dy, a.dy_ld = x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), dy.data_ptr(), dy.stride(0)
     a.M, a.N, a.K, a.act_in_silu = M, N, K, int(act_in_silu)
     if want_dx:
-        a.dx, a.dx_ld, a.accumulate_dx = dx.data_ptr(), dx.stride(0), int(accumulate_dx)
+        ws = torch.empty(_lib.lib().pt_small_linear_bwd_workspace_bytes(M, N, K), device=x.device, dtype=torch.uint8)
+        a.dx, a.dx_ld, a.accumulate_dx, a.dx_workspace = dx.data_ptr(), dx.stride(0), int(accumulate_dx), ws.data_ptr()
     a.dw, a.db, a.accumulate_w = dw.data_ptr(), (db.data_ptr() if db is not None else None), int(accumulate_w)
     _lib.check(_lib.lib().pt_small_linear_bwd(C.addressof(a), _sp()), "pt_small_linear_bwd")
     return (dx if want_dx else None), dw, db
