@@ -415,6 +415,8 @@ def frame_sharded_leg(cfg, unet, cnet, dev, rank, world, steps, barrier):
     from posetraj_b200.roofline import step_flops
     from posetraj_b200.trajectory import rasterize_tracks
     F, h, w = 25, 72, 128
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
     inp = _video_inputs(cfg, F, h, w, 777, pin=False)   # the same video on every rank
     tracks = [[[20 + 9 * k, 30 + 5 * k] for k in range(F)]]
     n_par = 3
@@ -462,8 +464,8 @@ def train_dp_leg(cfg, dev, rank, world, barrier):
     (posetraj_b200/training.py, DESIGN.md "Training"): forward + backward of one level-0 SpatioTemporalResBlock at the
     per-rank shape (2 videos x 14 frames x 40x72, 320 channels) — 3x3 conv and temporal conv dgrad (pt_gemm) / wgrad
     (pt_wgrad, tcgen05), 4-D and 5-D GroupNorm+SiLU backward — and the data-parallel tail of a step at FULL size: the
-    683 M ControlNet gradients in 100 MB fp32 buckets, NCCL all-reduce per bucket, fused AdamW.  The whole-network reverse
-    pass (attention backward) is not built: this is not a steps/s number for configs[3]."""
+    683 M ControlNet gradients in 100 MB fp32 buckets, NCCL all-reduce per bucket, fused AdamW.  (The whole step is the
+    next leg, `train_step_leg`.)"""
     import math
     import torch
     from posetraj_b200 import training as T
@@ -531,7 +533,7 @@ def train_dp_leg(cfg, dev, rank, world, barrier):
            "grad_bytes": nbytes, "buckets": len(gb.buckets), "allreduce_ms": ms_ar if world > 1 else None,
            "allreduce_busbw_gbs": (2.0 * (world - 1) / world * nbytes / ms_ar / 1e6) if world > 1 else None,
            "adamw_ms": ms_opt, "adamw_gbs": (nbytes * 7.5) / ms_opt / 1e6,
-           "not_built": "attention backward and the whole-network reverse pass (no configs[3] steps/s yet)"}
+           "see": "configs3_train_step for the whole step (this leg keeps the per-block and the collective-only timings)"}
     del gb, opt, tr
     torch.cuda.empty_cache()
     return res
