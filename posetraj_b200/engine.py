@@ -126,6 +126,13 @@ class WeightStore:
                               else self._get(k).to(dt).reshape(-1) for k in keys], 0).contiguous()
         return self._memo(("cat", kind), tuple(keys), make)
 
+    def cc_split(self, key: str, c_feat: int):
+        """cc_projection.weight [C, C + 12] (controlnet_sdv_cam_infer.py:84) as its two column blocks, both bf16: the
+        feature block [C, C] (a GEMM on the conditioning features) and the camera block [C, 12] (a per-frame row vector)."""
+        feat = self._memo(("ccf", c_feat), key, lambda: self._get(key).to(F32)[:, :c_feat].to(BF16).contiguous())
+        cam = self._memo(("ccc", c_feat), key, lambda: self._get(key).to(F32)[:, c_feat:].to(BF16).contiguous())
+        return feat, cam
+
     def alpha(self, key: str) -> float:
         """sigmoid(mix_factor) of an AlphaBlender (image_only_indicator is all zeros on this path)."""
         return float(torch.sigmoid(self._get(key).to(F32).reshape(-1)[0]).item())
@@ -679,8 +686,6 @@ class NetPlan:
         """Training variant of the conditioning embedding: EVERY conv through the implicit-GEMM kernel on the zero-haloed
         token layout (channels padded to 64), SiLU as its own pass so that the pre-activations exist for the backward."""
         cfg, w, dev = self.cfg, self.w, self.device
-        if self.cam:
-            raise NotImplementedError("training plan: the camera branch (cc_projection) has no backward yet")
         ce = cfg.conditioning_embedding_out_channels
         Hc, Wc = self.cond_hw
         p = "controlnet_cond_embedding."
@@ -709,6 +714,18 @@ class NetPlan:
         H, W = self.H, self.W
         kw = dict(taps=ops.conv3x3_taps(W), bias=w.f32(p + "conv_out.bias"), halo=(H, W), name=p + "conv_out")
         self.cond_out_plain = ops.Gemm(feats[0], w.conv3(p + "conv_out.weight"), self.cond_emb, **kw)
+        if self.cam:
+            # cc_projection on [features | camera] (controlnet_sdv_cam_infer.py:109-119): the feature block as a GEMM, the
+            # 12 camera columns as a per-frame row vector added in its epilogue
+            c_last = ce[-1]
+            w_feat, w_cam = w.cc_split(p + "cc_projection.weight", c_last)
+            self.cam_rowvec = torch.zeros(self.n, c_last, device=dev, dtype=F32)
+            self.cam_ops = [ops.SmallLinear(self.cam_in, w_cam, self.cam_rowvec, w.f32(p + "cc_projection.bias"),
+                                            name=p + "cc_projection.cam")]
+            proj = torch.zeros_like(feats[0])
+            self.cam_gemm = ops.Gemm(feats[0], w_feat, proj, taps=(0,), n_out=c_last, rowvec=self.cam_rowvec, rowvec_mode=1,
+                                     rv=((H + 1) * (W + 1), 1, 1), halo=(H, W), out_halo=True, name=p + "cc_projection")
+            self.cond_out_cam = ops.Gemm(proj, w.conv3(p + "conv_out.weight"), self.cond_emb, **kw)
         if self.bbox:
             self.cond_out_bbox = ops.Gemm(feats[1], w.conv3(p + "conv_out.weight"), self.cond_emb, res1=self.cond_emb, **kw)
 

@@ -474,6 +474,12 @@ def to_param_grads(kind_key: tuple, g: Optional[torch.Tensor], shapes: Dict[str,
         return {key: a.reshape(shapes[key])}
     if kind == "f32":
         return {key: g[: math.prod(shapes[key])].reshape(shapes[key])}
+    if isinstance(kind, tuple) and kind[0] in ("ccf", "ccc"):
+        # one column block of cc_projection.weight: (gradient, column slice of the parameter)
+        c_feat = kind[1]
+        co = shapes[key][0]
+        sl = (slice(None), slice(0, c_feat)) if kind[0] == "ccf" else (slice(None), slice(c_feat, shapes[key][1]))
+        return {key: (g[:co, : (c_feat if kind[0] == "ccf" else shapes[key][1] - c_feat)], sl)}
     if kind == "lin":
         shp = shapes[key]
         return {key: g[: shp[0]].reshape(shp)}
@@ -519,9 +525,8 @@ class ControlNetTrainer:
         self.dev, self.B, self.F, self.H, self.W = dev, batch, frames, height, width
         self.cfg: SVDConfig = controlnet.cfg
         self.bbox = bool(controlnet.flags.get("bbox"))
-        if controlnet.flags.get("cam"):
-            raise NotImplementedError("ControlNetTrainer: the camera branch has no backward yet (plain and bbox models only)")
-        self.shapes = controlnet_param_shapes(self.cfg, cam=False, bbox=self.bbox)
+        self.cam = bool(controlnet.flags.get("cam"))
+        self.shapes = controlnet_param_shapes(self.cfg, cam=self.cam, bbox=self.bbox)
         self.names = list(self.shapes.keys())
         self.index = {k: i for i, k in enumerate(self.names)}
         sizes = [int(math.prod(self.shapes[k])) for k in self.names]
@@ -532,7 +537,7 @@ class ControlNetTrainer:
         self.master = {k: self.opt.param(i).view(self.shapes[k]) for i, k in enumerate(self.names)}
         self.cw = WeightStore(self.master, dev)
         self.cplan = NetPlan("controlnet", self.cfg, self.cw, batch=batch, frames=frames, height=height, width=width, device=dev,
-                             bbox=self.bbox, train=True)
+                             bbox=self.bbox, cam=self.cam, train=True)
         self.uplan = NetPlan("unet", unet.cfg, unet.weights, batch=batch, frames=frames, height=height, width=width, device=dev,
                              residual_bufs=self.cplan.res, x_in=self.cplan.x_in, train=True)
         self.use_spatial = use_spatial
@@ -571,16 +576,28 @@ class ControlNetTrainer:
         all-reduce starts as soon as the bucket is complete — overlapped with the rest of the reverse pass)."""
         for name, pg in to_param_grads(kind_key, g, self.shapes).items():
             i = self.index[name]
-            self.buckets.view(i).view(self.shapes[name]).copy_(pg)
+            view = self.buckets.view(i).view(self.shapes[name])
+            if isinstance(pg, tuple):       # a column block of a parameter that two launches share (cc_projection.weight)
+                pg, sl = pg
+                if i not in self._partial:
+                    view.zero_()
+                    self._partial[i] = 0
+                view[sl].copy_(pg)
+                self._partial[i] += 1
+                if self._partial[i] < 2:
+                    continue
+            else:
+                view.copy_(pg)
             self._written.add(i)
             self.buckets.ready(i)
 
     # ---------------------------------------------------------------------------------------------------------
     def forward_backward(self, *, latents, noise, sigmas, image_embeddings, trajectories, motion_values, controlnet_bbox=None,
-                         ran_idx: int = 0, scaling_factor: float = 0.18215, noise_aug: float = 0.02) -> torch.Tensor:
+                         camera_cond=None, ran_idx: int = 0, scaling_factor: float = 0.18215, noise_aug: float = 0.02) -> torch.Tensor:
         """Loss and ControlNet gradients (into the gradient buckets; all-reduces launched).  Inputs as oracle/train.py
         `training_step`: latents [b, F, 4, h, w] (already x scaling_factor), noise like latents, sigmas [b],
-        image_embeddings [b, 1, D], trajectories [b, F, 3, 8h, 8w], motion_values [b]."""
+        image_embeddings [b, 1, D], trajectories [b, F, 3, 8h, 8w], motion_values [b]; `camera_cond` [b, F, 12] for the
+        camera model (scripts/train_svd_traj_VIPSeg_14_cam_concat.py:1404-1412), `controlnet_bbox` like trajectories."""
         sp = _sp()
         b, Fr = latents.shape[:2]
         assert (b, Fr) == (self.B, self.F)
@@ -602,7 +619,12 @@ class ControlNetTrainer:
         use_bbox = self.bbox and controlnet_bbox is not None
         if use_bbox:
             cp.cond_in2.copy_(controlnet_bbox.to(dev, F32).reshape(cp.cond_in2.shape))
-        cond_ops = cp.cond_op_list(False, use_bbox)
+        use_cam = self.cam and camera_cond is not None
+        if camera_cond is not None and not self.cam:
+            raise ValueError("camera_cond given but this ControlNet was built without cc_projection (cam=False)")
+        if use_cam:
+            cp.cam_in.copy_(camera_cond.to(dev, F32).reshape(cp.n, 12))
+        cond_ops = cp.cond_op_list(use_cam, use_bbox)
         NetPlan.run(cond_ops, sp)
         NetPlan.run(cp.step_ops, sp)
         # ---- UNet on the same input (x_in is shared) with the residuals read in place
@@ -630,6 +652,7 @@ class ControlNetTrainer:
                                    dpred=dpred_s[:, : self.cfg.out_channels])
         # ---- reverse pass: UNet(s) from the loss to the residuals, then the ControlNet
         self._written = set()
+        self._partial: Dict[int, int] = {}
         tu = Tape(up, trainable=False)
         tu.mark([up.step_ops], seeds=cp.res)
         tu.seed(up.noise_pred, dpred)
@@ -664,7 +687,8 @@ class ControlNetTrainer:
         # parameters no launch touched (dead cross-attention queries / keys, norm2, conv_out_2 ...): zero gradient
         for i in range(len(self.names)):
             if i not in self._written:
-                self.buckets.view(i).zero_()
+                if i not in self._partial:          # (a half-written split parameter keeps its written block, the rest is zero)
+                    self.buckets.view(i).zero_()
                 self.buckets.ready(i)
         return self.loss
 
