@@ -27,6 +27,13 @@ int pt_device_slot();
 // (profiles/r1h_pdl_gn.md); the device-side waits are no-ops for grids launched without the attribute.
 bool pt_pdl_enabled();
 
+// set for the NEXT pt_launch of the calling thread only: launch cooperatively, i.e. the driver guarantees that every CTA
+// of the grid is co-resident or fails the launch (kernels with an in-kernel grid rendezvous: gn_fused_kernel)
+inline bool& pt_next_launch_cooperative() {
+  static thread_local bool flag = false;
+  return flag;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t pt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, int cluster_x,
                              Args&&... args) {
@@ -35,8 +42,14 @@ inline cudaError_t pt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n = 0;
+  if (pt_next_launch_cooperative()) {
+    pt_next_launch_cooperative() = false;
+    attr[n].id = cudaLaunchAttributeCooperative;
+    attr[n].val.cooperative = 1;
+    ++n;
+  }
   if (cluster_x > 1) {
     attr[n].id = cudaLaunchAttributeClusterDimension;
     attr[n].val.clusterDim.x = (unsigned)cluster_x;

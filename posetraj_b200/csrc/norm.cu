@@ -684,7 +684,17 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   p.res_slots = a->mode == 0 ? gn_res_slots(C, gn_ctas_per_sm(C), rows_per_split) : 0;
   p.res_off = gn_red_bytes(C);
   const size_t smem_bytes = (size_t)p.res_off + (size_t)p.res_slots * threads * 16;
-  pt_launch(gn_fused_kernel<false>, dim3(a->num_stat * splits), dim3(threads), smem_bytes, (void*)stream, 1, p);
+  // The CTAs of a statistics group wait for each other inside the kernel.  Launched COOPERATIVELY the driver either places
+  // the whole grid at once or fails the launch (e.g. a second stream / process holding SMs): a clean error instead of CTAs
+  // spinning on peers that cannot be scheduled.  PT_GN_COOP=0 restores the plain launch (profiles/r2n_gn_cooperative.md).
+  static int env_coop = -2;
+  if (env_coop == -2) {
+    const char* e = getenv("PT_GN_COOP");
+    env_coop = e ? atoi(e) : 1;
+  }
+  if (env_coop != 0 && a->mode != 2 && splits > 1) pt_next_launch_cooperative() = true;
+  cudaError_t le = pt_launch(gn_fused_kernel<false>, dim3(a->num_stat * splits), dim3(threads), smem_bytes, (void*)stream, 1, p);
+  if (le != cudaSuccess) return pt_fail(le, "pt_groupnorm: launch (cooperative: the grid must be co-resident)");
   return pt_launched("pt_groupnorm");
 }
 
