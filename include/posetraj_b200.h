@@ -119,7 +119,7 @@ typedef struct PtGemmArgs {
   int32_t out_ld;
   int32_t out_dtype;          /* PT_DT_BF16 / PT_DT_F32 */
   /* optional second output: out2[m,n] = val + aux_scale * aux[m,n]  (ControlNet residual injected into the
-   * UNet skip tensor, models/unet_spatio_temporal_condition_controlnet.py:451-459) */
+   * UNet skip tensor, models/unet_spatio_temporal_condition_controlnet.py:451-459); aux NULL: out2 = val */
   void* out2;
   const void* aux;
   float aux_scale;

@@ -132,7 +132,7 @@ __device__ __noinline__ void epilogue_tail(const GemmParams& p, const float* acc
     if (p.out_dtype == PT_DT_BF16) reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16(v);
     else reinterpret_cast<float*>(p.out)[off] = v;
     if (p.out2 != nullptr) {
-      v = fmaf(p.aux_scale, __bfloat162float(p.aux[off]), v);
+      if (p.aux != nullptr) v = fmaf(p.aux_scale, __bfloat162float(p.aux[off]), v);
       if (p.out_dtype == PT_DT_BF16) reinterpret_cast<bf16*>(p.out2)[off] = __float2bfloat16(v);
       else reinterpret_cast<float*>(p.out2)[off] = v;
     }
@@ -178,7 +178,7 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if constexpr (kRes) P.r1[i] = has_res1 ? ldg_nc_u4(p.res1 + R.res_off[i] + ncol) : make_uint4(0, 0, 0, 0);
-          if constexpr (kOut2) P.ax[i] = ldg_nc_u4(p.aux + R.out_off[i] + ncol);
+          if constexpr (kOut2) P.ax[i] = p.aux != nullptr ? ldg_nc_u4(p.aux + R.out_off[i] + ncol) : make_uint4(0, 0, 0, 0);
         }
       }
     }
@@ -227,7 +227,7 @@ PT_DEVICE void epilogue_fast(const GemmParams& p, const EpiRows& R, uint32_t t_a
           if (has_res1) r1w = ldg_nc_u4(p.res1 + R.res_off[i] + ncol);
           if (has_res2) r2w = ldg_nc_u4(p.res2 + R.res_off[i] + ncol);
         }
-        if constexpr (kOut2) axw = ldg_nc_u4(p.aux + R.out_off[i] + ncol);
+        if constexpr (kOut2) axw = p.aux != nullptr ? ldg_nc_u4(p.aux + R.out_off[i] + ncol) : make_uint4(0, 0, 0, 0);
       }
       f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
       f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
@@ -657,7 +657,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmapParam tmap_a0, const __grid_cons
             const bool ok = full && ((vmask >> i) & 1u);
             r1[i] = (ok && p.res1 != nullptr) ? ldg_u4(p.res1 + (size_t)orow4[i] * p.res_ld + ncol) : make_uint4(0, 0, 0, 0);
             r2[i] = (ok && p.res2 != nullptr) ? ldg_u4(p.res2 + (size_t)orow4[i] * p.res_ld + ncol) : make_uint4(0, 0, 0, 0);
-            ax[i] = (ok && p.out2 != nullptr) ? ldg_u4(p.aux + (size_t)orow4[i] * p.out_ld + ncol) : make_uint4(0, 0, 0, 0);
+            ax[i] = (ok && p.out2 != nullptr && p.aux != nullptr) ? ldg_u4(p.aux + (size_t)orow4[i] * p.out_ld + ncol) : make_uint4(0, 0, 0, 0);
           }
           tmem_wait_ld();
           if (c + kChunkStride >= chunks) {
@@ -784,8 +784,6 @@ extern "C" int pt_gemm(const PtGemmArgs* a, void* stream) {
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: bad haloed-image mapping");
   if (a->rowvec_mode != 0 && (a->rowvec == nullptr || a->rv_a < 1))
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: rowvec_mode without rowvec");
-  if (a->out2 != nullptr && a->aux == nullptr)
-    return pt_fail(cudaErrorInvalidValue, "pt_gemm: out2 without aux");
   if (a->geglu && (a->rowvec_mode != 0 || a->res1 != nullptr || a->res2 != nullptr || a->out2 != nullptr || a->acc_scale != 1.0f || a->acc_scale_ptr != nullptr))
     return pt_fail(cudaErrorInvalidValue, "pt_gemm: GEGLU tiles support a bias-only epilogue");
   if (a->scatter_mode != 0) {

@@ -170,12 +170,18 @@ class NetPlan:
                  width: int, device, cam: bool = False, bbox: bool = False, cond_hw: Optional[tuple] = None,
                  sigmas: Optional[torch.Tensor] = None, step_index: Optional[torch.Tensor] = None,
                  x_in: Optional[torch.Tensor] = None, residual_bufs: Optional[List[torch.Tensor]] = None,
-                 ctx_batch: Optional[int] = None, row_offset: int = 0, train: bool = False):
+                 ctx_batch: Optional[int] = None, row_offset: int = 0, train: bool = False, defer_injection: bool = False):
         assert kind in ("unet", "controlnet")
         self.kind, self.cfg, self.w = kind, cfg, weights
         # train=True (posetraj_b200.train_engine, BASELINE configs[3]): no buffer reuse, pre-activations kept (GEGLU / SiLU as
         # separate passes, attention log-sum-exp written), parameter-dependent constants re-evaluated every step
         self.train = train
+        # defer_injection (UNet only): the encoder does not read the ControlNet residuals — the skips are written without them
+        # and `inject_ops` adds m_i * r_i afterwards — so that `step_ops[:split_index]` (time embedding, encoder, first half
+        # of the mid block) can run CONCURRENTLY with the ControlNet on a second stream (pipeline.DenoiseEngine)
+        self.defer_injection = defer_injection
+        self.inject_ops: List = []
+        self.split_index = 0
         self.alpha_updaters: List = []   # (mix_factor key, fn(alpha)) of every AlphaBlender baked into launch arguments
         self.B, self.F, self.H, self.W = batch, frames, height, width
         self.n = batch * frames
@@ -754,6 +760,9 @@ class NetPlan:
             def __call__(self_, i):
                 rows, cols = plan.res_shapes[i]
                 skips[i] = torch.empty(rows, cols, device=dev, dtype=BF16)
+                if plan.defer_injection:
+                    plan.inject_ops.append(ops.Axpy(skips[i], plan.res[i], skips[i], float(mult[i]), name=f"inject.{i}"))
+                    return dict(out2=skips[i], aux=None, aux_scale=0.0)
                 return dict(out2=skips[i], aux=plan.res[i], aux_scale=float(mult[i]))
 
             def done(self_, i, t):
@@ -763,6 +772,7 @@ class NetPlan:
                 plan.pool.put(t)
 
         z = self._encoder(Skips())
+        self.split_index = len(self.step_ops)
         hw = self.level_hw[-1]
         # second mid resnet + mid residual (unet...:469) as the second residual operand of its last GEMM
         x = self.resblock("mid_block.resnets.1.", z, None, ch[-1], hw, 1e-5, res2=self.res[-1])

@@ -214,11 +214,12 @@ class Gemm:
         a.out_ld = out.stride(0)
         a.out_dtype = PT_DT_BF16 if out.dtype == torch.bfloat16 else PT_DT_F32
         if out2 is not None:
-            assert aux is not None and out2.dtype == out.dtype and out2.stride(0) == out.stride(0)
-            assert aux.dtype == torch.bfloat16 and aux.stride(0) == out.stride(0)
+            assert out2.dtype == out.dtype and out2.stride(0) == out.stride(0)
             a.out2 = out2.data_ptr()
-            a.aux = aux.data_ptr()
-            a.aux_scale = aux_scale
+            if aux is not None:       # aux None: out2 = val (a second copy of the output that outlives the pooled one)
+                assert aux.dtype == torch.bfloat16 and aux.stride(0) == out.stride(0)
+                a.aux = aux.data_ptr()
+                a.aux_scale = aux_scale
         if halo is not None:
             h, w_ = halo  # unpadded image height/width of the A row space
             a.map_mode = 1

@@ -20,6 +20,8 @@ What runs where
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Union
 
@@ -143,8 +145,14 @@ class DenoiseEngine:
         if self.split:
             kw.update(ctx_batch=2, row_offset=self.row_begin)
         self.cplan: NetPlan = controlnet.plan_for(self.row_count, frames, h, w, cond_hw=cond_hw, **kw)
+        # Two-stream step (PT_TWO_STREAM, default on): the UNet's encoder never reads the ControlNet's residuals before they are
+        # added to its skips, so it runs CONCURRENTLY with the ControlNet on a second stream inside the captured graph (the
+        # kernels of levels 2-3 fill a fraction of the 148 SMs, and every persistent GEMM has a partial last wave); the 13
+        # injections `skip_i += m_i * r_i` follow the join (models/unet_spatio_temporal_condition_controlnet.py:451-469).
+        self.two_stream = os.environ.get("PT_TWO_STREAM", "1") != "0"
+        ukw = dict(kw, defer_injection=True) if self.two_stream else kw
         self.uplan: NetPlan = unet.plan_for(self.row_count, frames, h, w, x_in=self.cplan.x_in,
-                                            residual_bufs=self.cplan.res, **kw)
+                                            residual_bufs=self.cplan.res, **ukw)
         # the prediction of the whole pair: the UNet plan's own buffer, or the all-gather target when sharded
         self.pred_all = self.uplan.noise_pred if not self.split else torch.zeros(
             2 * frames * h * w, cfg.out_channels, device=device, dtype=BF16)
@@ -153,7 +161,13 @@ class DenoiseEngine:
                       row_begin=self.row_begin, row_count=self.row_count)
         self.prepare_op = ops.CfgEuler(noise_pred=None, mode=1, **common)
         self.update_op = ops.CfgEuler(noise_pred=self.pred_all, mode=0, **common)
-        self.net_ops = self.cplan.step_ops + self.uplan.step_ops
+        if self.two_stream:
+            k = self.uplan.split_index
+            self.unet_head, self.unet_rest = self.uplan.step_ops[:k], self.uplan.inject_ops + self.uplan.step_ops[k:]
+            self.net_ops = self.cplan.step_ops + self.unet_head + self.unet_rest
+            self._side = torch.cuda.Stream(device=device)
+        else:
+            self.net_ops = self.cplan.step_ops + self.uplan.step_ops
         self.tail_ops = [self.update_op, ops.StepAdvance(self.step_index)]
         self.step_ops = self.net_ops + self.tail_ops
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -226,7 +240,15 @@ class DenoiseEngine:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             with torch.cuda.graph(g, stream=s):
-                NetPlan.run(self.net_ops if self.split else self.step_ops, torch.cuda.current_stream().cuda_stream)
+                if self.two_stream:
+                    self._side.wait_stream(s)                         # fork
+                    with torch.cuda.stream(self._side):
+                        NetPlan.run(self.unet_head, self._side.cuda_stream)
+                    NetPlan.run(self.cplan.step_ops, s.cuda_stream)
+                    s.wait_stream(self._side)                         # join
+                    NetPlan.run(self.unet_rest + ([] if self.split else self.tail_ops), s.cuda_stream)
+                else:
+                    NetPlan.run(self.net_ops if self.split else self.step_ops, torch.cuda.current_stream().cuda_stream)
         torch.cuda.current_stream().wait_stream(s)
         # capture does not execute, but keep state exactly as before anyway
         self.step_index.copy_(saved[0]); self.latents.copy_(saved[1]); self.cplan.x_in.copy_(saved[2])
