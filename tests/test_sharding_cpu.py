@@ -81,9 +81,9 @@ def test_gloo_world2_collectives():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in range(world))
+    res = sorted(q.get(timeout=400) for _ in range(world))
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
     for rank, ids, t, m0, m1 in res:
         assert ids == [0, 1, 2, 3, 4]
@@ -160,9 +160,9 @@ def test_gloo_world2_ragged_all_to_all_rows():
     procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict((r, (d, s)) for r, d, s in (q.get(timeout=120) for _ in range(2)))
+    res = dict((r, (d, s)) for r, d, s in (q.get(timeout=400) for _ in range(2)))
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
     # rank 0 receives its own first 2 rows and rank 1's first row; rank 1 receives rank 0's last 3 and its own last 4
     assert res[0][0] == [[0.0, 1.0], [2.0, 3.0], [100.0, 101.0]]

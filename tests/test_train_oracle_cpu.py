@@ -152,11 +152,11 @@ def test_data_parallel_gradient_average_world2():
     res = {}
     try:
         for _ in range(2):
-            r, sample, norm = q.get(timeout=240)
+            r, sample, norm = q.get(timeout=400)
             res[r] = (torch.from_numpy(sample), norm)
     finally:
         for p in procs:
-            p.join(timeout=30)
+            p.join(timeout=180)
             if p.is_alive():
                 p.kill()
     grads = []

@@ -66,10 +66,10 @@ def test_gradient_buckets_average_over_two_gloo_ranks():
         p.start()
     got = dict()
     for _ in range(2):
-        rank, avg, local, nb = q.get(timeout=120)
+        rank, avg, local, nb = q.get(timeout=400)
         got[rank] = (avg, local, nb)
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
     assert got[0][2] == got[1][2] >= 3
     for i in range(4):
