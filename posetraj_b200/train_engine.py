@@ -593,11 +593,14 @@ class ControlNetTrainer:
 
     # ---------------------------------------------------------------------------------------------------------
     def forward_backward(self, *, latents, noise, sigmas, image_embeddings, trajectories, motion_values, controlnet_bbox=None,
-                         camera_cond=None, ran_idx: int = 0, scaling_factor: float = 0.18215, noise_aug: float = 0.02) -> torch.Tensor:
+                         camera_cond=None, ran_idx: int = 0, scaling_factor: float = 0.18215, noise_aug: float = 0.02,
+                         random_p: Optional[torch.Tensor] = None, conditioning_dropout_prob: Optional[float] = None) -> torch.Tensor:
         """Loss and ControlNet gradients (into the gradient buckets; all-reduces launched).  Inputs as oracle/train.py
         `training_step`: latents [b, F, 4, h, w] (already x scaling_factor), noise like latents, sigmas [b],
         image_embeddings [b, 1, D], trajectories [b, F, 3, 8h, 8w], motion_values [b]; `camera_cond` [b, F, 12] for the
-        camera model (scripts/train_svd_traj_VIPSeg_14_cam_concat.py:1404-1412), `controlnet_bbox` like trajectories."""
+        camera model (scripts/train_svd_traj_VIPSeg_14_cam_concat.py:1404-1412), `controlnet_bbox` like trajectories;
+        `random_p` [b] in [0, 1) with `conditioning_dropout_prob`: the reference's conditioning dropout (:1365-1385 — the image
+        embedding is zeroed where random_p < 2p, the conditioning latent where p <= random_p < 3p)."""
         sp = _sp()
         b, Fr = latents.shape[:2]
         assert (b, Fr) == (self.B, self.F)
@@ -612,6 +615,15 @@ class ControlNetTrainer:
         inp = torch.cat([noisy / ((s ** 2 + 1) ** 0.5), cond.unsqueeze(1).repeat(1, Fr, 1, 1, 1)], dim=2)
         ids = torch.stack([torch.full((b,), 6.0, device=dev), torch.full((b,), noise_aug, device=dev), motion_values.to(dev, F32).reshape(b)], 1)
         ehs = image_embeddings.to(dev, F32)
+        if conditioning_dropout_prob is not None:
+            if random_p is None:
+                raise ValueError("conditioning_dropout_prob needs random_p (one uniform draw per sample)")
+            rp = random_p.to(dev, F32).reshape(b)
+            pd = float(conditioning_dropout_prob)
+            ehs = torch.where((rp < 2 * pd).reshape(b, 1, 1), torch.zeros_like(ehs), ehs)
+            image_mask = 1 - ((rp >= pd).to(F32) * (rp < 3 * pd).to(F32))
+            cond = image_mask.reshape(b, 1, 1, 1) * cond
+            inp = torch.cat([noisy / ((s ** 2 + 1) ** 0.5), cond.unsqueeze(1).repeat(1, Fr, 1, 1, 1)], dim=2)
         cp, up = self.cplan, self.uplan
         # ---- ControlNet
         self._stage(cp, inp, timesteps, ehs, ids)
@@ -735,5 +747,16 @@ class ControlNetTrainer:
         self.optimizer_step()
         return self.loss
 
+    def set_lr(self, lr: float) -> None:
+        """`lr_scheduler.step()` of the reference loop (:1474): the learning rate is a launch argument of the AdamW kernel."""
+        self.opt.lr = float(lr)
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {k: v.clone() for k, v in self.master.items()}
+
+    def save_pretrained(self, directory: str, variant: Optional[str] = None) -> str:
+        """The trained ControlNet in the diffusers layout (`config.json` + `diffusion_pytorch_model.safetensors`, fp32) —
+        what the reference writes with `controlnet.save_pretrained` at its checkpoints and what
+        `ControlNetSDVModel.from_pretrained` (and the reference's own loader) read back."""
+        from . import checkpoint
+        return checkpoint.save_pretrained(self.state_dict(), self.cfg, directory, "ControlNetSDVModel", variant)

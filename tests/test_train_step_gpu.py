@@ -95,6 +95,52 @@ def test_one_step_loss_and_all_gradients(cuda_dev, variant, h, w, b):
             assert e == 0, k
 
 
+def test_conditioning_dropout_and_checkpoint_round_trip(cuda_dev, tmp_path):
+    """The reference's conditioning dropout (train...cam_concat.py:1365-1385) and save_pretrained -> from_pretrained."""
+    from oracle.train import training_step
+    from posetraj_b200.models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+    from posetraj_b200.train_engine import ControlNetTrainer
+    cfg = small_cfg()
+    o_unet, o_cnet = oracle_pair(cfg, seed=23)
+    batch, _ = make_batch(cfg, seed=5)
+    rp = torch.tensor([0.15, 0.05])            # sample 0: conditioning latent AND embedding dropped (p <= r < 2p); sample 1: embedding
+    o_unet.to(cuda_dev).requires_grad_(False)
+    o_cnet.to(cuda_dev).requires_grad_(True)
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        out = training_step(o_unet, o_cnet, ran_idx=2, random_p=rp.to(cuda_dev), conditioning_dropout_prob=0.1,
+                            **{k: v.to(cuda_dev) for k, v in batch.items()})
+        out["loss"].backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    unet = UNetSpatioTemporalConditionControlNetModel(cfg, o_unet.state_dict(), cuda_dev)
+    cnet = ControlNetSDVModel(cfg, o_cnet.state_dict(), cuda_dev)
+    tr = ControlNetTrainer(unet, cnet, batch=2, frames=cfg.num_frames, height=16, width=24, lr=1e-4)
+    loss = tr.forward_backward(ran_idx=2, random_p=rp, conditioning_dropout_prob=0.1, **batch)
+    tr.buckets.finish()
+    assert abs(float(loss) - float(out["loss"].detach())) < 5e-3 * abs(float(out["loss"].detach()))
+    g = tr.gradients()
+    num = den = 0.0
+    for n, p in o_cnet.named_parameters():
+        og = p.grad if p.grad is not None else torch.zeros_like(p)
+        num += float((g[n].float() - og.float()).pow(2).sum())
+        den += float(og.float().pow(2).sum())
+    assert (num / den) ** 0.5 < 3e-2
+    with pytest.raises(ValueError):
+        tr.forward_backward(conditioning_dropout_prob=0.1, **batch)
+    # one optimizer step, save in the diffusers layout, load it back into the inference mirror
+    tr.set_lr(5e-5)
+    tr.optimizer_step()
+    path = tr.save_pretrained(str(tmp_path / "controlnet"))
+    assert os.path.exists(path)
+    again = ControlNetSDVModel.from_pretrained(str(tmp_path), subfolder="controlnet", device=cuda_dev)
+    sd, sd2 = tr.state_dict(), again.state_dict()
+    assert set(sd) == set(sd2)
+    assert all(torch.equal(sd[k].cpu().float(), sd2[k].cpu().float()) for k in sd)
+    assert any(not torch.equal(sd[k].cpu().float(), cnet.state_dict()[k].cpu().float()) for k in sd)   # it did move
+
+
 def test_adamw_step_follows_torch(cuda_dev):
     """Two steps on the same batch: the parameters after our fused AdamW match torch.optim.AdamW driven by the oracle's
     gradients, and the second loss is lower."""
