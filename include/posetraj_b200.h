@@ -583,6 +583,10 @@ typedef struct PtAttnSpatialBwdArgs {
   void* dqkv;               /* bf16 [n_img*S, dld] = (dQ | dK | dV) */
   int32_t dld;
   int32_t S, heads, C, n_img;
+  /* optional (both or neither): rank-3 tensor maps {3C | C, S, n_img}, box {64, 128, 1}, over qkv and dout.  With them and
+   * S >= 256 the dK / dV kernel runs on tcgen05 (S^T, dP^T, dV, dK in TMEM); without, on mma.sync. */
+  const PtTensorMap* tmap_qkv;
+  const PtTensorMap* tmap_dout;
 } PtAttnSpatialBwdArgs;
 int pt_attention_spatial_bwd(const PtAttnSpatialBwdArgs* a, void* stream);
 

@@ -190,7 +190,7 @@ PtWgradArgs = _st("PtWgradArgs", [
 
 PtAttnSpatialBwdArgs = _st("PtAttnSpatialBwdArgs", [
     ("qkv", vp), ("ld", i32), ("dout", vp), ("dout_ld", i32), ("lse", vp), ("delta", vp), ("dqkv", vp), ("dld", i32),
-    ("S", i32), ("heads", i32), ("C", i32), ("n_img", i32)])
+    ("S", i32), ("heads", i32), ("C", i32), ("n_img", i32), ("tmap_qkv", vp), ("tmap_dout", vp)])
 
 PtAttnTemporalBwdArgs = _st("PtAttnTemporalBwdArgs", [
     ("qkv", vp), ("ld", i32), ("dout", vp), ("dout_ld", i32), ("dqkv", vp), ("dld", i32),

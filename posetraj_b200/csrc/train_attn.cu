@@ -341,6 +341,240 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams p)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// dK, dV on tcgen05 (S >= 256): one CTA per (128-key block, head, image), looping over 128-query blocks.
+//   S^T  = K_j Q_i^T   and   dP^T = V_j dO_i^T          128 x 128 fp32 each, in TMEM (rows = keys = TMEM lanes)
+//   P^T  = exp2(scale S^T - lse[query]),  dS^T = P^T o (dP^T - delta[query])   -> bf16, SWIZZLE_128B smem tiles (K-major A)
+//   dV  += P^T dO_i,   dK += dS^T Q_i                    128 x 64 fp32 each, in TMEM; Q_i / dO_i are re-read MN-major
+// warp 0: TMA producer (K_j, V_j once; ring of {Q_i, dO_i}); warp 1: MMA issue; warps 2..9: two warps per TMEM lane quarter,
+// one per 64-query half of the tile — a thread owns one key row and 64 of its 128 score columns.
+// Same anatomy as the forward kernel (attn_spatial.cu); no atomics, dQ keeps its own kernel.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTcTile = 128;
+constexpr int kTcTileBytes = 128 * 64 * 2;   // 16 KiB: one [128 x 64] bf16 tile (K, V, Q, dO, each half of P^T / dS^T)
+constexpr uint32_t kTcTmemCols = 512;         // S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384)
+
+struct alignas(64) BwdTmap {
+  uint64_t opaque[16];
+};
+
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_constant__ BwdTmap tmap_do, const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* qd_full = kv_full + 1;      // [2]
+  uint64_t* qd_empty = qd_full + 2;     // [2]
+  uint64_t* s_full = qd_empty + 2;      // S^T(i), dP^T(i) complete
+  uint64_t* s_read = s_full + 1;        // all 8 softmax warps hold S^T(i), dP^T(i) in registers
+  uint64_t* p_full = s_read + 1;        // P^T(i), dS^T(i) staged in shared memory
+  uint64_t* pv_done = p_full + 1;       // dV / dK MMAs of iteration i retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint8_t* sK = smem + 1024;
+  uint8_t* sV = sK + kTcTileBytes;
+  uint8_t* sQD = sV + kTcTileBytes;                 // 2 stages x (Q 16 KiB | dO 16 KiB)
+  uint8_t* sP = sQD + 4 * kTcTileBytes;             // P^T: two 64-query halves
+  uint8_t* sDS = sP + 2 * kTcTileBytes;             // dS^T: two 64-query halves
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int key0 = blockIdx.x * kTcTile;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int n_q = (p.S + kTcTile - 1) / kTcTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qd_full[s], 1);
+      mbar_init(&qd_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_read, 8);
+    mbar_init(p_full, 8);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTcTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * kTcTileBytes);
+      tma_load_3d(sK, &tmap_qkv, kv_full, p.C + head * 64, key0, img);
+      tma_load_3d(sV, &tmap_qkv, kv_full, 2 * p.C + head * 64, key0, img);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i & 1;
+      mbar_wait(&qd_empty[st], (uint32_t)((i >> 1) & 1) ^ 1u);
+      uint8_t* sQ = sQD + (size_t)st * 2 * kTcTileBytes;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&qd_full[st], 2 * kTcTileBytes);
+        tma_load_3d(sQ, &tmap_qkv, &qd_full[st], head * 64, i * kTcTile, img);
+        tma_load_3d(sQ + kTcTileBytes, &tmap_do, &qd_full[st], head * 64, i * kTcTile, img);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // A (K-major) x B (K-major)
+    const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // A (K-major) x B (MN-major: head dim contiguous)
+    const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sK));
+    const uint64_t vdesc = make_desc_kmajor_sw128(smem_u32(sV));
+    auto issue_s = [&](int i) {
+      const int st = i & 1;
+      mbar_wait(&qd_full[st], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t sQ = smem_u32(sQD + (size_t)st * 2 * kTcTileBytes);
+      const uint64_t qdesc = make_desc_kmajor_sw128(sQ);
+      const uint64_t ddesc = make_desc_kmajor_sw128(sQ + kTcTileBytes);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_u, kdesc + (uint64_t)(2 * k), qdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_u + 128u, vdesc + (uint64_t)(2 * k), ddesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int i = 0; i < n_q; ++i) {
+      const uint32_t par = (uint32_t)i & 1u;
+      if (i + 1 < n_q) {
+        mbar_wait(s_read, par);          // S^T(i), dP^T(i) are in registers: their TMEM columns are free
+        tc_fence_after();
+        issue_s(i + 1);
+      }
+      mbar_wait(p_full, par);
+      tc_fence_after();
+      const int st = i & 1;
+      const uint32_t sQ = smem_u32(sQD + (size_t)st * 2 * kTcTileBytes);
+      const uint64_t qmn = make_smem_desc(sQ, 1024, 1024, 2);                 // Q_i as [K = queries][N = d], MN-major
+      const uint64_t dmn = make_smem_desc(sQ + kTcTileBytes, 1024, 1024, 2);  // dO_i likewise
+      const uint32_t sPa = smem_u32(sP), sDa = smem_u32(sDS);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t pdesc = make_desc_kmajor_sw128(sPa + (uint32_t)(k >> 2) * kTcTileBytes) + (uint64_t)(2 * (k & 3));
+          tc_mma_bf16(tmem_u + 256u, pdesc, dmn + (uint64_t)(k * 128), idesc_o, (i | k) != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t sdesc = make_desc_kmajor_sw128(sDa + (uint32_t)(k >> 2) * kTcTileBytes) + (uint64_t)(2 * (k & 3));
+          tc_mma_bf16(tmem_u + 320u, sdesc, qmn + (uint64_t)(k * 128), idesc_o, (i | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(pv_done);
+        tc_commit(&qd_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------ softmax warps ----------------------------
+    const int q = warp & 3;               // TMEM lane quarter
+    const int half = (warp - 2) >> 2;     // 64-query half of the tile
+    const int row = q * 32 + lane;        // key row inside the block == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float* lse_g = p.lse + ((size_t)img * p.heads + head) * p.S;
+    const float* delta_g = p.delta + ((size_t)img * p.heads + head) * p.S;
+    for (int i = 0; i < n_q; ++i) {
+      const uint32_t par = (uint32_t)i & 1u;
+      const int qbase = i * kTcTile + half * 64;            // first query of this warp's columns
+      mbar_wait(s_full, par);
+      tc_fence_after();
+      uint32_t sv[64], dv[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32(t_lane + (uint32_t)(half * 64 + c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+        tmem_ld_32x32(t_lane + 128u + (uint32_t)(half * 64 + c * 32), *reinterpret_cast<uint32_t(*)[32]>(&dv[c * 32]));
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_read);
+      if (i > 0) {                                           // the staging tiles are free once dV / dK of i-1 retired
+        mbar_wait(pv_done, (uint32_t)(i - 1) & 1u);
+        tc_fence_after();
+      }
+      uint8_t* prow = sP + (size_t)half * kTcTileBytes + (size_t)row * 128;
+      uint8_t* drow = sDS + (size_t)half * kTcTileBytes + (size_t)row * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {                       // 8 queries (16 bytes of bf16) per chunk
+        const int qi = qbase + ch * 8;
+        float l[8], dl[8];
+        if (qi + 8 <= p.S && (p.S & 3) == 0) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(lse_g + qi)), a1 = __ldg(reinterpret_cast<const float4*>(lse_g + qi) + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(delta_g + qi)), b1 = __ldg(reinterpret_cast<const float4*>(delta_g + qi) + 1);
+          l[0] = a0.x; l[1] = a0.y; l[2] = a0.z; l[3] = a0.w; l[4] = a1.x; l[5] = a1.y; l[6] = a1.z; l[7] = a1.w;
+          dl[0] = b0.x; dl[1] = b0.y; dl[2] = b0.z; dl[3] = b0.w; dl[4] = b1.x; dl[5] = b1.y; dl[6] = b1.z; dl[7] = b1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = qi + j < p.S;
+            l[j] = ok ? __ldg(lse_g + qi + j) : INFINITY;    // exp2(x - inf) = 0: padded queries contribute nothing
+            dl[j] = ok ? __ldg(delta_g + qi + j) : 0.f;
+          }
+        }
+        float pr[8], ds[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pr[j] = ex2_approx(fmaf(__uint_as_float(sv[ch * 8 + j]), p.scale_log2, -l[j]));
+          ds[j] = pr[j] * (__uint_as_float(dv[ch * 8 + j]) - dl[j]);
+        }
+        const int sw = (ch ^ (row & 7)) << 4;
+        *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]), pack_bf16x2(pr[4], pr[5]),
+                                                          pack_bf16x2(pr[6], pr[7]));
+        *reinterpret_cast<uint4*>(drow + sw) = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
+                                                          pack_bf16x2(ds[6], ds[7]));
+      }
+      fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // dV (half 1) / dK (half 0) of this key row once the last MMAs retired
+    mbar_wait(pv_done, (uint32_t)(n_q - 1) & 1u);
+    tc_fence_after();
+    const int krow = key0 + row;
+    const float osc = half == 0 ? p.scale : 1.0f;
+    bf16* dst = p.dqkv + ((size_t)img * p.S + krow) * p.dld + (half == 0 ? p.C : 2 * p.C) + head * 64;
+    const uint32_t t_o = t_lane + (half == 0 ? 320u : 256u);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_o + (uint32_t)c * 32u, o);
+      tmem_wait_ld();
+      if (krow < p.S) {
+#pragma unroll
+        for (int d = 0; d < 32; d += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[d]) * osc, __uint_as_float(o[d + 1]) * osc);
+          u.y = pack_bf16x2(__uint_as_float(o[d + 2]) * osc, __uint_as_float(o[d + 3]) * osc);
+          u.z = pack_bf16x2(__uint_as_float(o[d + 4]) * osc, __uint_as_float(o[d + 5]) * osc);
+          u.w = pack_bf16x2(__uint_as_float(o[d + 6]) * osc, __uint_as_float(o[d + 7]) * osc);
+          stg_u4(dst + c * 32 + d, u);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTcTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // temporal attention backward: one warp per (batch, pixel, head); rows (b*F + f)*HW + s
 // ------------------------------------------------------------------------------------------------------------
 struct TAttnBwdParams {
@@ -472,8 +706,30 @@ extern "C" int pt_attention_spatial_bwd(const PtAttnSpatialBwdArgs* a, void* str
     attr_set[dev_slot] = true;
   }
   dim3 grid((a->S + kBwdTile - 1) / kBwdTile, a->heads, a->n_img);
-  pt_launch(attn_bwd_dkv_kernel, grid, dim3(128), smem, stream, 1, p);
-  int rc = pt_launched("pt_attention_spatial_bwd (dK, dV)");
+  int rc;
+  static int env_tc = -2;   // PT_ATTN_BWD_TC=0 keeps the mma.sync dK / dV kernel at every size
+  if (env_tc == -2) {
+    const char* e = getenv("PT_ATTN_BWD_TC");
+    env_tc = e ? atoi(e) : 1;
+  }
+  if (env_tc != 0 && a->tmap_qkv != nullptr && a->tmap_dout != nullptr && a->S >= 256 && a->dld % 8 == 0) {
+    const size_t smem_tc = 1024 + (size_t)kTcTileBytes * (2 + 4 + 2 + 2) + 1024;
+    static bool attr_tc[PT_MAX_DEVICES] = {false};
+    if (!attr_tc[dev_slot]) {
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+      if (e != cudaSuccess) return pt_fail(e, "pt_attention_spatial_bwd: cudaFuncSetAttribute (tcgen05)");
+      attr_tc[dev_slot] = true;
+    }
+    BwdTmap tq, td;
+    memcpy(&tq, a->tmap_qkv, sizeof(tq));
+    memcpy(&td, a->tmap_dout, sizeof(td));
+    dim3 grid_tc((a->S + kTcTile - 1) / kTcTile, a->heads, a->n_img);
+    pt_launch(attn_bwd_dkv_tc_kernel, grid_tc, dim3(320), smem_tc, stream, 1, tq, td, p);
+    rc = pt_launched("pt_attention_spatial_bwd (dK, dV: tcgen05)");
+  } else {
+    pt_launch(attn_bwd_dkv_kernel, grid, dim3(128), smem, stream, 1, p);
+    rc = pt_launched("pt_attention_spatial_bwd (dK, dV)");
+  }
   if (rc != 0) return rc;
   pt_launch(attn_bwd_dq_kernel, grid, dim3(128), smem, stream, 1, p);
   return pt_launched("pt_attention_spatial_bwd (dQ)");

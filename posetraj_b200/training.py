@@ -578,6 +578,11 @@ def attention_spatial_backward(qkv: torch.Tensor, out: torch.Tensor, dout: torch
     a.qkv, a.ld, a.dout, a.dout_ld = qkv.data_ptr(), qkv.stride(0), dout.data_ptr(), dout.stride(0)
     a.lse, a.delta, a.dqkv, a.dld = lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), dqkv.stride(0)
     a.S, a.heads, a.C, a.n_img = S, heads, Cc, n_img
+    if S >= 256 and qkv.stride(0) % 8 == 0 and dout.stride(0) % 8 == 0:
+        # tcgen05 dK / dV kernel: TMA tiles of the operands (keep the descriptors alive until the call has been issued)
+        tm_q = _lib.encode_tensormap(qkv.data_ptr(), [c3, S, n_img], [qkv.stride(0) * 2, qkv.stride(0) * 2 * S], [64, 128, 1])
+        tm_d = _lib.encode_tensormap(dout.data_ptr(), [Cc, S, n_img], [dout.stride(0) * 2, dout.stride(0) * 2 * S], [64, 128, 1])
+        a.tmap_qkv, a.tmap_dout = C.addressof(tm_q), C.addressof(tm_d)
     _lib.check(_lib.lib().pt_attention_spatial_bwd(C.addressof(a), _sp()), "pt_attention_spatial_bwd")
     return dqkv
 
