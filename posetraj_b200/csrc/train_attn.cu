@@ -499,12 +499,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_read);
-      if (i > 0) {                                           // the staging tiles are free once dV / dK of i-1 retired
-        mbar_wait(pv_done, (uint32_t)(i - 1) & 1u);
-        tc_fence_after();
-      }
-      uint8_t* prow = sP + (size_t)half * kTcTileBytes + (size_t)row * 128;
-      uint8_t* drow = sDS + (size_t)half * kTcTileBytes + (size_t)row * 128;
+      // P^T and dS^T of this thread's 64 columns, packed to bf16 in registers: the exponentials run while the tensor
+      // core still works on dV / dK of the previous query block
+      uint4 pk[8], dk[8];
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {                       // 8 queries (16 bytes of bf16) per chunk
         const int qi = qbase + ch * 8;
@@ -528,11 +525,20 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_co
           pr[j] = ex2_approx(fmaf(__uint_as_float(sv[ch * 8 + j]), p.scale_log2, -l[j]));
           ds[j] = pr[j] * (__uint_as_float(dv[ch * 8 + j]) - dl[j]);
         }
+        pk[ch] = make_uint4(pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]), pack_bf16x2(pr[4], pr[5]), pack_bf16x2(pr[6], pr[7]));
+        dk[ch] = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+      }
+      if (i > 0) {                                           // the staging tiles are free once dV / dK of i-1 retired
+        mbar_wait(pv_done, (uint32_t)(i - 1) & 1u);
+        tc_fence_after();
+      }
+      uint8_t* prow = sP + (size_t)half * kTcTileBytes + (size_t)row * 128;
+      uint8_t* drow = sDS + (size_t)half * kTcTileBytes + (size_t)row * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
         const int sw = (ch ^ (row & 7)) << 4;
-        *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]), pack_bf16x2(pr[4], pr[5]),
-                                                          pack_bf16x2(pr[6], pr[7]));
-        *reinterpret_cast<uint4*>(drow + sw) = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
-                                                          pack_bf16x2(ds[6], ds[7]));
+        *reinterpret_cast<uint4*>(prow + sw) = pk[ch];
+        *reinterpret_cast<uint4*>(drow + sw) = dk[ch];
       }
       fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
@@ -561,6 +567,201 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_co
           u.w = pack_bf16x2(__uint_as_float(o[d + 6]) * osc, __uint_as_float(o[d + 7]) * osc);
           stg_u4(dst + c * 32 + d, u);
         }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTcTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dQ on tcgen05 (S >= 256): one CTA per (128-query block, head, image), looping over 128-key blocks.
+//   S = Q_i K_j^T,  dP = dO_i V_j^T   (rows = queries = TMEM lanes: lse / delta are per-thread scalars)
+//   dS = P o (dP - delta) -> bf16, SWIZZLE_128B smem tiles;   dQ += dS K_j   (K_j re-read MN-major), scaled at the end
+// Roles as in the dK / dV kernel; the ring carries {K_j, V_j}, Q_i / dO_i stay resident.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_constant__ BwdTmap tmap_do, const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* qd_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* kv_full = qd_full + 1;      // [2]
+  uint64_t* kv_empty = kv_full + 2;     // [2]
+  uint64_t* s_full = kv_empty + 2;
+  uint64_t* s_read = s_full + 1;
+  uint64_t* p_full = s_read + 1;
+  uint64_t* pv_done = p_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint8_t* sQ = smem + 1024;
+  uint8_t* sdO = sQ + kTcTileBytes;
+  uint8_t* sKV = sdO + kTcTileBytes;                // 2 stages x (K 16 KiB | V 16 KiB)
+  uint8_t* sDS = sKV + 4 * kTcTileBytes;            // dS: two 64-key halves
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTcTile;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int n_k = (p.S + kTcTile - 1) / kTcTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(qd_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_read, 8);
+    mbar_init(p_full, 8);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTcTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(qd_full, 2 * kTcTileBytes);
+      tma_load_3d(sQ, &tmap_qkv, qd_full, head * 64, q0, img);
+      tma_load_3d(sdO, &tmap_do, qd_full, head * 64, q0, img);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_k; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_empty[st], (uint32_t)((j >> 1) & 1) ^ 1u);
+      uint8_t* sK = sKV + (size_t)st * 2 * kTcTileBytes;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kTcTileBytes);
+        tma_load_3d(sK, &tmap_qkv, &kv_full[st], p.C + head * 64, j * kTcTile, img);
+        tma_load_3d(sK + kTcTileBytes, &tmap_qkv, &kv_full[st], 2 * p.C + head * 64, j * kTcTile, img);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+    const uint64_t qdesc = make_desc_kmajor_sw128(smem_u32(sQ));
+    const uint64_t ddesc = make_desc_kmajor_sw128(smem_u32(sdO));
+    auto issue_s = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&kv_full[st], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t sK = smem_u32(sKV + (size_t)st * 2 * kTcTileBytes);
+      const uint64_t kdesc = make_desc_kmajor_sw128(sK);
+      const uint64_t vdesc = make_desc_kmajor_sw128(sK + kTcTileBytes);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_u, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_u + 128u, ddesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(qd_full, 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < n_k; ++j) {
+      const uint32_t par = (uint32_t)j & 1u;
+      if (j + 1 < n_k) {
+        mbar_wait(s_read, par);
+        tc_fence_after();
+        issue_s(j + 1);
+      }
+      mbar_wait(p_full, par);
+      tc_fence_after();
+      const int st = j & 1;
+      const uint64_t kmn = make_smem_desc(smem_u32(sKV + (size_t)st * 2 * kTcTileBytes), 1024, 1024, 2);   // K_j as [K = keys][N = d]
+      const uint32_t sDa = smem_u32(sDS);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t sdesc = make_desc_kmajor_sw128(sDa + (uint32_t)(k >> 2) * kTcTileBytes) + (uint64_t)(2 * (k & 3));
+          tc_mma_bf16(tmem_u + 256u, sdesc, kmn + (uint64_t)(k * 128), idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(pv_done);
+        tc_commit(&kv_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;     // 64-key half of the tile
+    const int row = q * 32 + lane;        // query row inside the block == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int qrow = q0 + row;
+    const size_t sidx = ((size_t)img * p.heads + head) * p.S + (qrow < p.S ? qrow : 0);
+    const float l = qrow < p.S ? p.lse[sidx] : INFINITY;
+    const float dl = qrow < p.S ? p.delta[sidx] : 0.f;
+    for (int j = 0; j < n_k; ++j) {
+      const uint32_t par = (uint32_t)j & 1u;
+      const int kbase = j * kTcTile + half * 64;
+      mbar_wait(s_full, par);
+      tc_fence_after();
+      uint32_t sv[64], dv[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32(t_lane + (uint32_t)(half * 64 + c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+        tmem_ld_32x32(t_lane + 128u + (uint32_t)(half * 64 + c * 32), *reinterpret_cast<uint32_t(*)[32]>(&dv[c * 32]));
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_read);
+      const bool full = kbase + 64 <= p.S;
+      uint4 dk[8];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float ds[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float pr = ex2_approx(fmaf(__uint_as_float(sv[ch * 8 + jj]), p.scale_log2, -l));
+          if (!full && kbase + ch * 8 + jj >= p.S) pr = 0.f;     // keys beyond S are TMA zero-fill
+          ds[jj] = pr * (__uint_as_float(dv[ch * 8 + jj]) - dl);
+        }
+        dk[ch] = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+      }
+      if (j > 0) {                                           // the staging tile is free once dQ += dS K of j-1 retired
+        mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+      }
+      uint8_t* drow = sDS + (size_t)half * kTcTileBytes + (size_t)row * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(drow + ((ch ^ (row & 7)) << 4)) = dk[ch];
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (uint32_t)(n_k - 1) & 1u);
+    tc_fence_after();
+    // dQ: this warp writes 32 of the row's 64 head dims
+    uint32_t o[32];
+    tmem_ld_32x32(t_lane + 256u + (uint32_t)half * 32u, o);
+    tmem_wait_ld();
+    if (qrow < p.S) {
+      bf16* dst = p.dqkv + ((size_t)img * p.S + qrow) * p.dld + head * 64 + half * 32;
+#pragma unroll
+      for (int d = 0; d < 32; d += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o[d]) * p.scale, __uint_as_float(o[d + 1]) * p.scale);
+        u.y = pack_bf16x2(__uint_as_float(o[d + 2]) * p.scale, __uint_as_float(o[d + 3]) * p.scale);
+        u.z = pack_bf16x2(__uint_as_float(o[d + 4]) * p.scale, __uint_as_float(o[d + 5]) * p.scale);
+        u.w = pack_bf16x2(__uint_as_float(o[d + 6]) * p.scale, __uint_as_float(o[d + 7]) * p.scale);
+        stg_u4(dst + d, u);
       }
     }
   }
@@ -731,6 +932,21 @@ extern "C" int pt_attention_spatial_bwd(const PtAttnSpatialBwdArgs* a, void* str
     rc = pt_launched("pt_attention_spatial_bwd (dK, dV)");
   }
   if (rc != 0) return rc;
+  if (env_tc != 0 && a->tmap_qkv != nullptr && a->tmap_dout != nullptr && a->S >= 256 && a->dld % 8 == 0) {
+    const size_t smem_tc = 1024 + (size_t)kTcTileBytes * (2 + 4 + 2) + 1024;
+    static bool attr_tq[PT_MAX_DEVICES] = {false};
+    if (!attr_tq[dev_slot]) {
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+      if (e != cudaSuccess) return pt_fail(e, "pt_attention_spatial_bwd: cudaFuncSetAttribute (tcgen05 dQ)");
+      attr_tq[dev_slot] = true;
+    }
+    BwdTmap tq, td;
+    memcpy(&tq, a->tmap_qkv, sizeof(tq));
+    memcpy(&td, a->tmap_dout, sizeof(td));
+    dim3 grid_tc((a->S + kTcTile - 1) / kTcTile, a->heads, a->n_img);
+    pt_launch(attn_bwd_dq_tc_kernel, grid_tc, dim3(320), smem_tc, stream, 1, tq, td, p);
+    return pt_launched("pt_attention_spatial_bwd (dQ: tcgen05)");
+  }
   pt_launch(attn_bwd_dq_kernel, grid, dim3(128), smem, stream, 1, p);
   return pt_launched("pt_attention_spatial_bwd (dQ)");
 }
