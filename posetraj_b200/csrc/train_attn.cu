@@ -342,11 +342,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams p)
 
 // ------------------------------------------------------------------------------------------------------------
 // dK, dV on tcgen05 (S >= 256): one CTA per (128-key block, head, image), looping over 128-query blocks.
-//   S^T  = K_j Q_i^T   and   dP^T = V_j dO_i^T          128 x 128 fp32 each, in TMEM (rows = keys = TMEM lanes)
-//   P^T  = exp2(scale S^T - lse[query]),  dS^T = P^T o (dP^T - delta[query])   -> bf16, SWIZZLE_128B smem tiles (K-major A)
-//   dV  += P^T dO_i,   dK += dS^T Q_i                    128 x 64 fp32 each, in TMEM; Q_i / dO_i are re-read MN-major
+//   S  = Q_i K_j^T   and   dP = dO_i V_j^T              128 x 128 fp32 each, in TMEM (rows = queries = TMEM lanes, so the
+//                                                       softmax statistics lse / delta are per-thread scalars)
+//   P  = exp2(scale S - lse),  dS = P o (dP - delta)    -> bf16, SWIZZLE_128B smem tiles [queries x keys]
+//   dV += P^T dO_i,   dK += dS^T Q_i                    128 x 64 fp32 each, in TMEM (rows = keys): P / dS are read as the
+//                                                       MN-major A operand (= transposed for free), Q_i / dO_i as MN-major B
 // warp 0: TMA producer (K_j, V_j once; ring of {Q_i, dO_i}); warp 1: MMA issue; warps 2..9: two warps per TMEM lane quarter,
-// one per 64-query half of the tile — a thread owns one key row and 64 of its 128 score columns.
+// one per 64-key half of the tile — a thread owns one query row and 64 of its 128 score columns.
 // Same anatomy as the forward kernel (attn_spatial.cu); no atomics, dQ keeps its own kernel.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kTcTile = 128;
@@ -424,7 +426,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_co
   } else if (warp == 1) {
     const uint32_t tmem_u = uniform_u32(tmem_base);
     const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // A (K-major) x B (K-major)
-    const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // A (K-major) x B (MN-major: head dim contiguous)
+    const uint32_t idesc_o = make_idesc_bf16(128, 64, 1, 1);    // A = P^T / dS^T (MN-major: keys contiguous) x B (MN-major: head dim contiguous)
     const uint64_t kdesc = make_desc_kmajor_sw128(smem_u32(sK));
     const uint64_t vdesc = make_desc_kmajor_sw128(smem_u32(sV));
     auto issue_s = [&](int i) {
@@ -436,9 +438,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_co
       const uint64_t ddesc = make_desc_kmajor_sw128(sQ + kTcTileBytes);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_u, kdesc + (uint64_t)(2 * k), qdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_u, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_u + 128u, vdesc + (uint64_t)(2 * k), ddesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_u + 128u, ddesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
         tc_commit(s_full);
       }
       __syncwarp();
@@ -459,18 +461,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_co
       const uint32_t sQ = smem_u32(sQD + (size_t)st * 2 * kTcTileBytes);
       const uint64_t qmn = make_smem_desc(sQ, 1024, 1024, 2);                 // Q_i as [K = queries][N = d], MN-major
       const uint64_t dmn = make_smem_desc(sQ + kTcTileBytes, 1024, 1024, 2);  // dO_i likewise
-      const uint32_t sPa = smem_u32(sP), sDa = smem_u32(sDS);
+      // P / dS tiles: [128 queries (K) x 2 x 64 keys (M)], 128 B per row and half: M blocks 16 KiB apart (LBO), 8-row groups
+      // 1 KiB apart (SBO); a K step of 16 queries = 2 KiB
+      const uint64_t pmn = make_smem_desc(smem_u32(sP), kTcTileBytes, 1024, 2);
+      const uint64_t smn = make_smem_desc(smem_u32(sDS), kTcTileBytes, 1024, 2);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t pdesc = make_desc_kmajor_sw128(sPa + (uint32_t)(k >> 2) * kTcTileBytes) + (uint64_t)(2 * (k & 3));
-          tc_mma_bf16(tmem_u + 256u, pdesc, dmn + (uint64_t)(k * 128), idesc_o, (i | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 8; ++k) tc_mma_bf16(tmem_u + 256u, pmn + (uint64_t)(k * 128), dmn + (uint64_t)(k * 128), idesc_o, (i | k) != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t sdesc = make_desc_kmajor_sw128(sDa + (uint32_t)(k >> 2) * kTcTileBytes) + (uint64_t)(2 * (k & 3));
-          tc_mma_bf16(tmem_u + 320u, sdesc, qmn + (uint64_t)(k * 128), idesc_o, (i | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 8; ++k) tc_mma_bf16(tmem_u + 320u, smn + (uint64_t)(k * 128), qmn + (uint64_t)(k * 128), idesc_o, (i | k) != 0 ? 1u : 0u);
         tc_commit(pv_done);
         tc_commit(&qd_empty[st]);
       }
@@ -479,14 +478,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_co
   } else {
     // ------------------------------ softmax warps ----------------------------
     const int q = warp & 3;               // TMEM lane quarter
-    const int half = (warp - 2) >> 2;     // 64-query half of the tile
-    const int row = q * 32 + lane;        // key row inside the block == TMEM lane
+    const int half = (warp - 2) >> 2;     // 64-key half of the tile
+    const int row = q * 32 + lane;        // S / dP row (query of the current block) == TMEM lane; later: key row of dK / dV
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const float* lse_g = p.lse + ((size_t)img * p.heads + head) * p.S;
     const float* delta_g = p.delta + ((size_t)img * p.heads + head) * p.S;
+    const int kbase = key0 + half * 64;                      // first key of this warp's columns
+    const bool kfull = kbase + 64 <= p.S;
     for (int i = 0; i < n_q; ++i) {
       const uint32_t par = (uint32_t)i & 1u;
-      const int qbase = i * kTcTile + half * 64;            // first query of this warp's columns
+      const int qrow = i * kTcTile + row;
+      const float l = qrow < p.S ? __ldg(lse_g + qrow) : INFINITY;   // exp2(x - inf) = 0: padded queries contribute nothing
+      const float dl = qrow < p.S ? __ldg(delta_g + qrow) : 0.f;
       mbar_wait(s_full, par);
       tc_fence_after();
       uint32_t sv[64], dv[64];
@@ -499,31 +502,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ BwdTmap tmap_qkv, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_read);
-      // P^T and dS^T of this thread's 64 columns, packed to bf16 in registers: the exponentials run while the tensor
-      // core still works on dV / dK of the previous query block
+      // P and dS of this thread's 64 columns, packed to bf16 in registers: the exponentials run while the tensor core still
+      // works on dV / dK of the previous query block
       uint4 pk[8], dk[8];
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {                       // 8 queries (16 bytes of bf16) per chunk
-        const int qi = qbase + ch * 8;
-        float l[8], dl[8];
-        if (qi + 8 <= p.S && (p.S & 3) == 0) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(lse_g + qi)), a1 = __ldg(reinterpret_cast<const float4*>(lse_g + qi) + 1);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(delta_g + qi)), b1 = __ldg(reinterpret_cast<const float4*>(delta_g + qi) + 1);
-          l[0] = a0.x; l[1] = a0.y; l[2] = a0.z; l[3] = a0.w; l[4] = a1.x; l[5] = a1.y; l[6] = a1.z; l[7] = a1.w;
-          dl[0] = b0.x; dl[1] = b0.y; dl[2] = b0.z; dl[3] = b0.w; dl[4] = b1.x; dl[5] = b1.y; dl[6] = b1.z; dl[7] = b1.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const bool ok = qi + j < p.S;
-            l[j] = ok ? __ldg(lse_g + qi + j) : INFINITY;    // exp2(x - inf) = 0: padded queries contribute nothing
-            dl[j] = ok ? __ldg(delta_g + qi + j) : 0.f;
-          }
-        }
+      for (int ch = 0; ch < 8; ++ch) {
         float pr[8], ds[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          pr[j] = ex2_approx(fmaf(__uint_as_float(sv[ch * 8 + j]), p.scale_log2, -l[j]));
-          ds[j] = pr[j] * (__uint_as_float(dv[ch * 8 + j]) - dl[j]);
+          pr[j] = ex2_approx(fmaf(__uint_as_float(sv[ch * 8 + j]), p.scale_log2, -l));
+          if (!kfull && kbase + ch * 8 + j >= p.S) pr[j] = 0.f;      // keys beyond S are TMA zero-fill
+          ds[j] = pr[j] * (__uint_as_float(dv[ch * 8 + j]) - dl);
         }
         pk[ch] = make_uint4(pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]), pack_bf16x2(pr[4], pr[5]), pack_bf16x2(pr[6], pr[7]));
         dk[ch] = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
