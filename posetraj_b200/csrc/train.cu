@@ -173,7 +173,28 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColsumParams p) {
   }
 }
 
-// out[i] (+)= scale * sum_b partials[b][i]: 32 elements x 8 slices of b per CTA, slices folded in order (deterministic)
+// out[i] (+)= scale * sum_b partials[b][i], b in order.  Two shapes occur: (a) FEW partials of a LARGE array (wgrad: 2-20 row
+// slices of a whole weight matrix) -> one thread per 4 consecutive elements, 16-byte loads, the b loop in registers;
+// (b) MANY partials of a SMALL array (norm scale / shift gradients: hundreds of CTAs x 2C) -> 32 elements x 8 slices of b per
+// CTA, slices folded in order.  Both are deterministic.
+__global__ void __launch_bounds__(256) reduce_partials_vec4_kernel(const float* partials, int nb, long long n4, float scale, float* out,
+                                                                   int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b2 = 0; b2 < nb; ++b2) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partials + (size_t)b2 * n4 * 4) + i);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out) + i;
+    if (accumulate) {
+      const float4 c = *o;
+      *o = make_float4(c.x + scale * t.x, c.y + scale * t.y, c.z + scale * t.z, c.w + scale * t.w);
+    } else {
+      *o = make_float4(scale * t.x, scale * t.y, scale * t.z, scale * t.w);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* partials, int nb, long long n, float scale, float* out, int accumulate) {
   __shared__ float sm[8][33];
   const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
@@ -329,7 +350,12 @@ extern "C" int pt_colsum(const PtColsumArgs* a, void* stream) {
 
 extern "C" int pt_reduce_partials(const float* partials, int32_t nb, int64_t n, float scale, float* out, int32_t accumulate, void* stream) {
   PT_CHECK_ARG(partials && out && nb > 0 && n > 0, "pt_reduce_partials: bad argument");
-  pt_launch(reduce_partials_kernel, dim3(grid_for(n, 32, 148 * 8)), dim3(256), 0, stream, 1, partials, (int)nb, (long long)n, scale, out, (int)accumulate);
+  if (nb <= 32 && n % 4 == 0 && ((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0)
+    pt_launch(reduce_partials_vec4_kernel, dim3(grid_for(n / 4, 256, 148 * 16)), dim3(256), 0, stream, 1, partials, (int)nb, (long long)(n / 4), scale,
+              out, (int)accumulate);
+  else
+    pt_launch(reduce_partials_kernel, dim3(grid_for(n, 32, 148 * 8)), dim3(256), 0, stream, 1, partials, (int)nb, (long long)n, scale, out,
+              (int)accumulate);
   return pt_launched("pt_reduce_partials");
 }
 
