@@ -28,31 +28,59 @@ struct SmallLinearParams {
   int act_in_silu, act_out_silu, accumulate;
 };
 
+// kStage: the (activated) input rows are staged ONCE per CTA in shared memory.  Without it every warp re-evaluated
+// silu(x) for its own output row: 2 MUFU per element x N rows — for the batched time_emb_proj GEMV (N ~ 55 000, K = 1280)
+// that was 176 us per launch, 3x the time of streaming its 141 MB of weights (profiles/r2v_train_launches.md).
+template <bool kStage>
 __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearParams p) {
+  extern __shared__ __align__(16) float sl_x[];   // kStage: [rows of this pass (<= 8)][K]
   griddep_launch();
   griddep_wait();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (n >= p.N) return;
-  const bf16* wr = p.w + (size_t)n * p.w_ld;
+  const bool live = n < p.N;
+  if (!kStage && !live) return;
+  const bf16* wr = p.w + (size_t)(live ? n : 0) * p.w_ld;
   for (int m0 = 0; m0 < p.M; m0 += 8) {
+    const int mrows = min(8, p.M - m0);
+    if (kStage) {
+      if (m0 > 0) __syncthreads();
+      for (int idx = threadIdx.x; idx < mrows * p.K; idx += 256) {
+        const int i = idx / p.K, k = idx - i * p.K;
+        float x = p.in[(size_t)(m0 + i) * p.in_ld + k];
+        if (p.act_in_silu) x = silu_f(x);
+        sl_x[idx] = x;
+      }
+      __syncthreads();
+    }
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (!live) continue;
     if ((p.K & 7) == 0 && (p.w_ld & 7) == 0) {
+#pragma unroll 2
       for (int k = lane * 8; k < p.K; k += 256) {
         const uint4 u = ldg_u4(wr + k);
         const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
         const float wv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (m0 + i < p.M) {
-            const float* xr = p.in + (size_t)(m0 + i) * p.in_ld + k;
+          if (i < mrows) {
+            if (kStage) {
+              const float4 x0 = *reinterpret_cast<const float4*>(sl_x + (size_t)i * p.K + k);
+              const float4 x1 = *reinterpret_cast<const float4*>(sl_x + (size_t)i * p.K + k + 4);
+              acc[i] = fmaf(x0.x, wv[0], acc[i]); acc[i] = fmaf(x0.y, wv[1], acc[i]);
+              acc[i] = fmaf(x0.z, wv[2], acc[i]); acc[i] = fmaf(x0.w, wv[3], acc[i]);
+              acc[i] = fmaf(x1.x, wv[4], acc[i]); acc[i] = fmaf(x1.y, wv[5], acc[i]);
+              acc[i] = fmaf(x1.z, wv[6], acc[i]); acc[i] = fmaf(x1.w, wv[7], acc[i]);
+            } else {
+              const float* xr = p.in + (size_t)(m0 + i) * p.in_ld + k;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = xr[j];
-              if (p.act_in_silu) x = silu_f(x);
-              acc[i] = fmaf(x, wv[j], acc[i]);
+              for (int j = 0; j < 8; ++j) {
+                float x = xr[j];
+                if (p.act_in_silu) x = silu_f(x);
+                acc[i] = fmaf(x, wv[j], acc[i]);
+              }
             }
           }
         }
@@ -62,9 +90,14 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearPara
         const float wv = __bfloat162float(wr[k]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (m0 + i < p.M) {
-            float x = p.in[(size_t)(m0 + i) * p.in_ld + k];
-            if (p.act_in_silu) x = silu_f(x);
+          if (i < mrows) {
+            float x;
+            if (kStage) {
+              x = sl_x[(size_t)i * p.K + k];
+            } else {
+              x = p.in[(size_t)(m0 + i) * p.in_ld + k];
+              if (p.act_in_silu) x = silu_f(x);
+            }
             acc[i] = fmaf(x, wv, acc[i]);
           }
         }
@@ -75,7 +108,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearPara
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (m0 + i < p.M) {
+        if (i < mrows) {
           float v = acc[i] + (p.bias != nullptr ? p.bias[n] : 0.f);
           if (p.act_out_silu) v = silu_f(v);
           float* o = p.out + (size_t)(m0 + i) * p.out_ld + n;
@@ -404,7 +437,11 @@ extern "C" int pt_small_linear(const PtSmallLinearArgs* a, void* stream) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.act_in_silu = a->act_in_silu; p.act_out_silu = a->act_out_silu; p.accumulate = a->accumulate;
   const int blocks = (a->N + 7) / 8;
-  pt_launch(small_linear_kernel, dim3(blocks), dim3(256), 0, (void*)stream, 1, p);
+  const size_t stage_bytes = (size_t)(a->M < 8 ? a->M : 8) * a->K * sizeof(float);
+  if (stage_bytes <= 48 * 1024 && a->N >= 64)
+    pt_launch(small_linear_kernel<true>, dim3(blocks), dim3(256), stage_bytes, (void*)stream, 1, p);
+  else
+    pt_launch(small_linear_kernel<false>, dim3(blocks), dim3(256), 0, (void*)stream, 1, p);
   return pt_launched("pt_small_linear");
 }
 
