@@ -779,7 +779,8 @@ struct TAttnBwdParams {
   int warps_per_cta;
 };
 
-constexpr int kTStride = 65;  // fp32 row stride of the per-warp q/k/v/dO copies: conflict-free column walks
+constexpr int kTStride = 68;  // fp32 row stride of the per-warp q/k/v/dO copies: 16-byte aligned rows whose float4 reads of 8
+                              // consecutive rows cover all 32 banks
 
 __global__ void attn_temporal_bwd_kernel(const TAttnBwdParams p) {
   extern __shared__ __align__(16) float tsm[];
@@ -792,7 +793,7 @@ __global__ void attn_temporal_bwd_kernel(const TAttnBwdParams p) {
   const long long bs = w / p.heads;
   const int s = (int)(bs % p.HW);
   const int b = (int)(bs / p.HW);
-  float* base = tsm + (size_t)wl * (4 * F * kTStride + 2 * F * F);
+  float* base = tsm + (size_t)wl * (size_t)((4 * F * kTStride + 2 * F * F + 3) & ~3);   // 16-byte aligned per-warp slabs
   float* sq = base;
   float* sk = sq + F * kTStride;
   float* sv = sk + F * kTStride;
@@ -807,20 +808,22 @@ __global__ void attn_temporal_bwd_kernel(const TAttnBwdParams p) {
     const float2 k = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(r + p.C));
     const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(r + 2 * p.C));
     const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.dout + row * p.dout_ld + head * 64 + 2 * lane));
-    sq[f * kTStride + 2 * lane] = q.x; sq[f * kTStride + 2 * lane + 1] = q.y;
-    sk[f * kTStride + 2 * lane] = k.x; sk[f * kTStride + 2 * lane + 1] = k.y;
-    sv[f * kTStride + 2 * lane] = v.x; sv[f * kTStride + 2 * lane + 1] = v.y;
-    sdo[f * kTStride + 2 * lane] = d.x; sdo[f * kTStride + 2 * lane + 1] = d.y;
+    *reinterpret_cast<float2*>(sq + f * kTStride + 2 * lane) = q;
+    *reinterpret_cast<float2*>(sk + f * kTStride + 2 * lane) = k;
+    *reinterpret_cast<float2*>(sv + f * kTStride + 2 * lane) = v;
+    *reinterpret_cast<float2*>(sdo + f * kTStride + 2 * lane) = d;
   }
   __syncwarp();
   // S = Q K^T and dP = dO V^T
   for (int e = lane; e < F * F; e += 32) {
     const int i = e / F, j = e - i * F;
     float a = 0.f, c = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < 64; ++d) {
-      a = fmaf(sq[i * kTStride + d], sk[j * kTStride + d], a);
-      c = fmaf(sdo[i * kTStride + d], sv[j * kTStride + d], c);
+#pragma unroll 4
+    for (int d = 0; d < 64; d += 4) {
+      const float4 q4 = *reinterpret_cast<const float4*>(sq + i * kTStride + d), k4 = *reinterpret_cast<const float4*>(sk + j * kTStride + d);
+      const float4 o4 = *reinterpret_cast<const float4*>(sdo + i * kTStride + d), v4 = *reinterpret_cast<const float4*>(sv + j * kTStride + d);
+      a = fmaf(q4.x, k4.x, a); a = fmaf(q4.y, k4.y, a); a = fmaf(q4.z, k4.z, a); a = fmaf(q4.w, k4.w, a);
+      c = fmaf(o4.x, v4.x, c); c = fmaf(o4.y, v4.y, c); c = fmaf(o4.z, v4.z, c); c = fmaf(o4.w, v4.w, c);
     }
     sp[e] = a;
     sds[e] = c;
@@ -847,12 +850,15 @@ __global__ void attn_temporal_bwd_kernel(const TAttnBwdParams p) {
     float q0 = 0.f, q1 = 0.f, k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
     for (int j = 0; j < F; ++j) {
       const float ds_fj = sds[f * F + j], ds_jf = sds[j * F + f], p_jf = sp[j * F + f];
-      q0 = fmaf(ds_fj, sk[j * kTStride + c0], q0);
-      q1 = fmaf(ds_fj, sk[j * kTStride + c0 + 1], q1);
-      k0 = fmaf(ds_jf, sq[j * kTStride + c0], k0);
-      k1 = fmaf(ds_jf, sq[j * kTStride + c0 + 1], k1);
-      v0 = fmaf(p_jf, sdo[j * kTStride + c0], v0);
-      v1 = fmaf(p_jf, sdo[j * kTStride + c0 + 1], v1);
+      const float2 kk = *reinterpret_cast<const float2*>(sk + j * kTStride + c0);
+      const float2 qq = *reinterpret_cast<const float2*>(sq + j * kTStride + c0);
+      const float2 oo = *reinterpret_cast<const float2*>(sdo + j * kTStride + c0);
+      q0 = fmaf(ds_fj, kk.x, q0);
+      q1 = fmaf(ds_fj, kk.y, q1);
+      k0 = fmaf(ds_jf, qq.x, k0);
+      k1 = fmaf(ds_jf, qq.y, k1);
+      v0 = fmaf(p_jf, oo.x, v0);
+      v1 = fmaf(p_jf, oo.y, v1);
     }
     bf16* o = p.dqkv + (row0 + (size_t)f * p.HW) * p.dld + head * 64 + c0;
     *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(q0, q1);
@@ -951,7 +957,7 @@ extern "C" int pt_attention_temporal_bwd(const PtAttnTemporalBwdArgs* a, void* s
   p.dqkv = reinterpret_cast<bf16*>(a->dqkv); p.dld = a->dld;
   p.B = a->B; p.F = a->F; p.HW = a->HW; p.heads = a->heads; p.C = a->C;
   p.scale = 0.125f; p.scale_log2 = 0.125f * kLog2e;
-  const size_t per_warp = (size_t)(4 * a->F * kTStride + 2 * a->F * a->F) * sizeof(float);
+  const size_t per_warp = (size_t)((4 * a->F * kTStride + 2 * a->F * a->F + 3) & ~3) * sizeof(float);
   int wpc = (int)((size_t)96 * 1024 / per_warp);
   if (wpc > 8) wpc = 8;
   if (wpc < 1) wpc = 1;
