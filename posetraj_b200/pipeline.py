@@ -147,7 +147,7 @@ class DenoiseEngine:
         self.cplan: NetPlan = controlnet.plan_for(self.row_count, frames, h, w, cond_hw=cond_hw, **kw)
         # Two-stream step (PT_TWO_STREAM, default on): the UNet's encoder never reads the ControlNet's residuals before they are
         # added to its skips, so it runs CONCURRENTLY with the ControlNet on a second stream inside the captured graph (the
-        # kernels of levels 2-3 fill a fraction of the 148 SMs, and every persistent GEMM has a partial last wave); the 13
+        # kernels of levels 2-3 fill a fraction of the 148 SMs, and every persistent GEMM has a partial last wave); the 12
         # injections `skip_i += m_i * r_i` follow the join (models/unet_spatio_temporal_condition_controlnet.py:451-469).
         self.two_stream = os.environ.get("PT_TWO_STREAM", "1") != "0"
         ukw = dict(kw, defer_injection=True) if self.two_stream else kw
