@@ -26,7 +26,7 @@ def make_batch(cfg, b=2, h=16, w=24, seed=0):
                 trajectories=traj, motion_values=torch.tensor([127.0, 90.0, 10.0, 200.0][:b])), bbox
 
 
-def oracle_step(o_unet, o_cnet, batch, bbox_maps, ran_idx, dev, camera_cond=None):
+def oracle_step(o_unet, o_cnet, batch, bbox_maps, ran_idx, dev, camera_cond=None, use_spatial=True):
     from oracle.train import training_step
     o_unet.to(dev).requires_grad_(False)
     o_cnet.to(dev).requires_grad_(True)
@@ -42,7 +42,7 @@ def oracle_step(o_unet, o_cnet, batch, bbox_maps, ran_idx, dev, camera_cond=None
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
     try:
         kw = {} if camera_cond is None else {"camera_cond": camera_cond.to(dev)}
-        out = training_step(o_unet, cnet, ran_idx=ran_idx, **{k: v.to(dev) for k, v in batch.items()}, **kw)
+        out = training_step(o_unet, cnet, ran_idx=ran_idx, use_spatial=use_spatial, **{k: v.to(dev) for k, v in batch.items()}, **kw)
         out["loss"].backward()
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
@@ -50,22 +50,23 @@ def oracle_step(o_unet, o_cnet, batch, bbox_maps, ran_idx, dev, camera_cond=None
     return out, grads
 
 
-@pytest.mark.parametrize("variant,h,w,b", [("plain", 16, 24, 2), ("bbox", 16, 24, 2), ("cam", 16, 24, 2), ("plain", 24, 40, 1)])
+@pytest.mark.parametrize("variant,h,w,b", [("plain", 16, 24, 2), ("bbox", 16, 24, 2), ("cam", 16, 24, 2), ("plain", 24, 40, 1),
+                                           ("plain-nospatial", 16, 24, 2)])
 def test_one_step_loss_and_all_gradients(cuda_dev, variant, h, w, b):
     """plain / bbox (second tower through the shared conv_out) / cam (cc_projection) models; the last case has a 3 x 5
     bottom level (odd sizes, partial attention tiles) and batch 1."""
     from posetraj_b200.models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
     from posetraj_b200.train_engine import ControlNetTrainer
-    bbox, cam = variant == "bbox", variant == "cam"
+    bbox, cam, spatial = variant == "bbox", variant == "cam", not variant.endswith("nospatial")
     cfg = small_cfg()
     o_unet, o_cnet = oracle_pair(cfg, seed=21, bbox=bbox, cam=cam)
     batch, bbox_maps = make_batch(cfg, b=b, h=h, w=w)
     bbox_maps = bbox_maps if bbox else None
     camera = torch.randn(b, cfg.num_frames, 12, generator=torch.Generator().manual_seed(9)) * 0.3 if cam else None
-    out, og = oracle_step(o_unet, o_cnet, batch, bbox_maps, 1, cuda_dev, camera)
+    out, og = oracle_step(o_unet, o_cnet, batch, bbox_maps, 1, cuda_dev, camera, use_spatial=spatial)
     unet = UNetSpatioTemporalConditionControlNetModel(cfg, o_unet.state_dict(), cuda_dev)
     cnet = ControlNetSDVModel(cfg, o_cnet.state_dict(), cuda_dev, bbox=bbox, cam=cam)
-    tr = ControlNetTrainer(unet, cnet, batch=b, frames=cfg.num_frames, height=h, width=w)
+    tr = ControlNetTrainer(unet, cnet, batch=b, frames=cfg.num_frames, height=h, width=w, use_spatial=spatial)
     loss = tr.forward_backward(ran_idx=1, controlnet_bbox=bbox_maps, camera_cond=camera, **batch)
     tr.buckets.finish()
     torch.cuda.synchronize()
