@@ -6,3 +6,4 @@ from .pipeline import StableVideoDiffusionPipelineControlNet  # noqa: F401
 from .scheduler import EulerDiscreteScheduler  # noqa: F401
 from .vae import AutoencoderKLTemporalDecoder  # noqa: F401
 from .clip import CLIPVisionModelWithProjection, resize_with_antialiasing  # noqa: F401
+from .train_engine import ControlNetTrainer  # noqa: F401

@@ -22,7 +22,6 @@ the product path and raise without the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Dict, List, Optional, Sequence
 
 import torch
