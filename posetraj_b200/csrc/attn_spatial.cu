@@ -70,6 +70,9 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const int n_kv = (p.S + kKTile - 1) / kKTile;
+  // query groups of this CTA that hold at least one real query: the last CTA of a sequence whose length is not a multiple
+  // of NQ x 128 (2880 = 11 x 256 + 64) runs ONE group instead of spending a full group on TMA zero-fill
+  const int nq_act = (NQ == 2 && q0 + kQTile >= p.S) ? 1 : NQ;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
@@ -100,8 +103,8 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
   if (warp == 0) {
     {
       if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, NQ * kTileBytes);
-        for (int g = 0; g < NQ; ++g) tma_load_3d(sQ + g * kTileBytes, &tmap_qkv, q_full, head * kHd, q0 + g * kQTile, img);
+        mbar_arrive_expect_tx(q_full, nq_act * kTileBytes);
+        for (int g = 0; g < nq_act; ++g) tma_load_3d(sQ + g * kTileBytes, &tmap_qkv, q_full, head * kHd, q0 + g * kQTile, img);
       }
       __syncwarp();
       int stage = 0;
@@ -141,7 +144,7 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      for (int g = 0; g < NQ; ++g) issue_s(g, 0);
+      for (int g = 0; g < nq_act; ++g) issue_s(g, 0);
       int stage = 0;       // stage of K_j / V_j
       int stage_n = 1 % kKvStages;  // stage of K_{j+1}
       uint32_t phase_n = (kKvStages == 1) ? 1u : 0u;
@@ -157,8 +160,8 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
         const uint64_t vdesc = make_smem_desc(sV, 1024, 1024, 2);
         // Event-driven issue: S_g(j+1) goes out as soon as the softmax warps hold S_g(j) in registers (its latency
         // hides behind their exponentials), PV_g(j) as soon as P_g(j) is in shared memory — whichever comes first.
-        uint32_t pend_s = has_next ? ((1u << NQ) - 1u) : 0u;
-        uint32_t pend_pv = (1u << NQ) - 1u;
+        uint32_t pend_s = has_next ? ((1u << nq_act) - 1u) : 0u;
+        uint32_t pend_pv = (1u << nq_act) - 1u;
         const uint32_t par = (uint32_t)j & 1u;
         uint32_t spins = 0;
         while (pend_s | pend_pv) {
@@ -211,7 +214,8 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
     uint8_t* sPg = sP + (size_t)g * 2 * kTileBytes;
     float m_ref = -INFINITY;  // the max the exponent offsets currently refer to (raw score units)
     float l_run = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
+    const bool active = g < nq_act;   // (an inactive group's warps go straight to the final barrier)
+    for (int j = 0; active && j < n_kv; ++j) {
       mbar_wait(&s_full[g], (uint32_t)j & 1u);
       tc_fence_after();
       const int kvalid = min(kKTile, p.S - j * kKTile);  // keys beyond S are TMA zero-fill: mask them
@@ -311,6 +315,7 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
       if (lane == 0) mbar_arrive(&p_full[g]);
     }
     // O_g = sum_j P_g(j) V_j is complete once the last PV retired
+    if (active) {
     mbar_wait(&o_done[g], (uint32_t)(n_kv - 1) & 1u);
     tc_fence_after();
     const int qrow = q0 + g * kQTile + row;
@@ -334,6 +339,7 @@ attn_spatial_kernel(const __grid_constant__ AttnTmap tmap_qkv, const __grid_cons
           stg_u4(dst + c * 32 + d, u);
         }
       }
+    }
     }
   }
 
