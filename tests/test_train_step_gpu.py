@@ -96,6 +96,37 @@ def test_one_step_loss_and_all_gradients(cuda_dev, variant, h, w, b):
             assert e == 0, k
 
 
+def test_full_width_step(cuda_dev):
+    """The real channel plan (320 / 640 / 1280 / 1280, heads 5 / 10 / 20 / 20, 682 M trained parameters) on a small clip: the
+    tuned tile table, CTA-pair GEMMs, 256-wide wgrad tiles and the tcgen05 attention backward as the full-size step runs
+    them, against the fp32 oracle."""
+    from posetraj_b200.config import SVDConfig
+    from posetraj_b200.models import ControlNetSDVModel, UNetSpatioTemporalConditionControlNetModel
+    from posetraj_b200.train_engine import ControlNetTrainer
+    cfg = SVDConfig(num_frames=2)
+    o_unet, o_cnet = oracle_pair(cfg, seed=31)
+    batch, _ = make_batch(cfg, b=1, h=16, w=24, seed=8)
+    out, og = oracle_step(o_unet, o_cnet, batch, None, 1, cuda_dev)
+    unet = UNetSpatioTemporalConditionControlNetModel(cfg, o_unet.state_dict(), cuda_dev)
+    cnet = ControlNetSDVModel(cfg, o_cnet.state_dict(), cuda_dev)
+    del o_unet
+    tr = ControlNetTrainer(unet, cnet, batch=1, frames=cfg.num_frames, height=16, width=24)
+    loss = tr.forward_backward(ran_idx=1, **batch)
+    tr.buckets.finish()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(out["loss"].detach())) < 5e-3 * abs(float(out["loss"].detach()))
+    g = tr.gradients()
+    num = den = 0.0
+    for k in og:
+        num += float((g[k].float() - og[k].float()).pow(2).sum())
+        den += float(og[k].float().pow(2).sum())
+    total = (num / den) ** 0.5
+    with open(os.path.join(OUT, "train_step_parity.jsonl"), "a") as f:
+        f.write(json.dumps(dict(variant="plain, full width (320-1280 ch), 2 frames", hw=[16, 24], batch=1, loss=float(loss),
+                                oracle_loss=float(out["loss"].detach()), total_rel_l2=total, worst=[])) + "\n")
+    assert total < 3e-2, total
+
+
 def test_conditioning_dropout_and_checkpoint_round_trip(cuda_dev, tmp_path):
     """The reference's conditioning dropout (train...cam_concat.py:1365-1385) and save_pretrained -> from_pretrained."""
     from oracle.train import training_step
