@@ -405,6 +405,11 @@ struct LnParams {
   bf16* sum_out;        // optional: x + addvec (bf16), same ld as out
 };
 
+PT_DEVICE void unpack_row8(uint4 u, float* f) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
 constexpr int kLnMaxVec = 8;  // vectors per lane: 8 x 8 channels x 32 lanes = 2048 channels at G = 32
 
 // V = 16-byte vectors per lane (compile-time so that the row really lives in V*8 registers, not kLnMaxVec*8)
@@ -517,6 +522,164 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
           float o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gg[j], bb[j]);
+          uint4 u;
+          u.x = pack_bf16x2(o[0], o[1]);
+          u.y = pack_bf16x2(o[2], o[3]);
+          u.z = pack_bf16x2(o[4], o[5]);
+          u.w = pack_bf16x2(o[6], o[7]);
+          stg_u4(p.out + (size_t)row * p.out_ld + vi * 8, u);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm, packed variant: the row stays in registers as the bf16 it was loaded as (V x 16 bytes per lane instead of
+// V x 8 floats) and is unpacked once per pass.  LayerNorm at these widths is ISSUE-bound, not HBM-bound: ~75 instructions
+// per 16-byte vector (unpack, sum, centred squares, normalise, pack, affine loads) is ~80 % of the four schedulers at
+// 5 TB/s, which is why deeper prefetch (a cp.async ring with 120 KB in flight per SM) measured SLOWER than this kernel and
+// why what helps is occupancy (80 registers: 3 resident CTAs per SM instead of 2) and fewer instructions:
+//   kOnePass = false: mean, then centred squares — same arithmetic and reduction order as layernorm_kernel, bit-identical;
+//   kOnePass = true : sum and sum of squares in ONE pass over the registers (var = E[x^2] - mean^2 in fp32, clamped at 0):
+//                     one unpack pass and one subtraction per element less.
+// Handles the plain form and addvec + sum_out (the temporal norm_in: the row is re-packed after the add, exactly the
+// bf16 rounding the consumer of sum_out sees); addvec without sum_out keeps the fp32 kernel above.
+// ---------------------------------------------------------------------------------------------------------
+// kFull: C == 8 * G * V exactly (every width of this model), so no lane has a vector slot to predicate off
+template <int G, int V, bool kOnePass, bool kFull>
+__global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel(const LnParams p) {
+  constexpr int kRowsPerWarp = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int l = lane % G;
+  const int nvec = p.C >> 3;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int n_groups = (p.rows + kRowsPerWarp - 1) / kRowsPerWarp;
+  int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  griddep_launch();
+  griddep_wait();
+  if (grp >= n_groups) return;
+  auto row_of = [&](int g) {
+    const int r = g * kRowsPerWarp + lane / G;
+    return r < p.rows ? r : p.rows - 1;
+  };
+  uint4 nxt[V];
+  {
+    const bf16* src = p.x + (size_t)row_of(grp) * p.ld;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int vi = l + i * G;
+      nxt[i] = (kFull || vi < nvec) ? ldg_nc_u4(src + vi * 8) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (; grp < n_groups; grp += warps_total) {
+    const int row = row_of(grp);
+    const bool live = grp * kRowsPerWarp + lane / G < p.rows;
+    uint4 cur[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) cur[i] = nxt[i];
+    if (grp + warps_total < n_groups) {
+      const bf16* nsrc = p.x + (size_t)row_of(grp + warps_total) * p.ld;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int vi = l + i * G;
+        nxt[i] = (kFull || vi < nvec) ? ldg_nc_u4(nsrc + vi * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    float s = 0.f;
+    if (p.addvec != nullptr) {
+      const float* av = p.addvec + (size_t)((row / p.hw) % p.F) * p.C;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int vi = l + i * G;
+        if (kFull || vi < nvec) {
+          float v[8];
+          unpack_row8(cur[i], v);
+          const float4 e0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
+          const float4 e1 = __ldg(reinterpret_cast<const float4*>(av + vi * 8) + 1);
+          v[0] += e0.x; v[1] += e0.y; v[2] += e0.z; v[3] += e0.w;
+          v[4] += e1.x; v[5] += e1.y; v[6] += e1.z; v[7] += e1.w;
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]);
+          o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]);
+          o.w = pack_bf16x2(v[6], v[7]);
+          if (live) stg_u4(p.sum_out + (size_t)row * p.out_ld + vi * 8, o);
+          cur[i] = o;
+        }
+      }
+    }
+    float mean, rstd;
+    if (kOnePass) {
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int vi = l + i * G;
+        if (kFull || vi < nvec) {
+          float v[8];
+          unpack_row8(cur[i], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s += v[j];
+            sq = fmaf(v[j], v[j], sq);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      mean = s / (float)p.C;
+      rstd = rsqrtf(fmaxf(sq / (float)p.C - mean * mean, 0.f) + p.eps);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int vi = l + i * G;
+        if (kFull || vi < nvec) {
+          float v[8];
+          unpack_row8(cur[i], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += v[j];
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mean = s / (float)p.C;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int vi = l + i * G;
+        if (kFull || vi < nvec) {
+          float v[8];
+          unpack_row8(cur[i], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = v[j] - mean;
+            sq = fmaf(d, d, sq);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      rstd = rsqrtf(sq / (float)p.C + p.eps);
+    }
+    const float nmr = -mean * rstd;  // (v - mean) * rstd as one FMA
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int vi = l + i * G;
+        if (kFull || vi < nvec) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8) + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8) + 1);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float v[8], o[8];
+          unpack_row8(cur[i], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[j], rstd, nmr), gg[j], bb[j]);
           uint4 u;
           u.x = pack_bf16x2(o[0], o[1]);
           u.y = pack_bf16x2(o[2], o[3]);
@@ -722,10 +885,39 @@ extern "C" int pt_layernorm(const PtLayerNormArgs* a, void* stream) {
   const int V = (nvec + G - 1) / G;
   const int rows_per_block = 8 * (32 / G);
   int blocks = (a->rows + rows_per_block - 1) / rows_per_block;
-  const int max_blocks = pt_num_sms() * 2;  // persistent: 2 resident CTAs per SM (117 registers), each warp strides over row groups
-  if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t st = (cudaStream_t)stream;
-#define PT_LN_LAUNCH(GG, VV) pt_launch(layernorm_kernel<GG, VV>, dim3(blocks), dim3(256), 0, (void*)st, 1, p)
+  // packed variant (3 resident CTAs per SM at V <= 5) unless PT_LN_PACKED=0 or the fp32-add form (addvec without sum_out)
+  static int packed_env = -1;
+  if (packed_env < 0) {
+    const char* e = getenv("PT_LN_PACKED");
+    packed_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool packed = packed_env != 0 && (a->addvec == nullptr || a->sum_out != nullptr);
+  // persistent grid: as many CTAs as are co-resident (2 per SM for the fp32-row kernel at 117 registers, 3 for the
+  // packed one at V <= 5); each warp strides over row groups with the next group's loads in flight
+  static int onepass_env = -1;  // PT_LN_ONEPASS=1: single-pass statistics (E[x^2] - mean^2)
+  if (onepass_env < 0) {
+    const char* e = getenv("PT_LN_ONEPASS");
+    onepass_env = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  const bool onepass = onepass_env != 0;
+  static int full_env = -1;  // PT_LN_FULL=0: keep the per-vector predicates even when C == 8 * G * V
+  if (full_env < 0) {
+    const char* e = getenv("PT_LN_FULL");
+    full_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool full = full_env != 0 && nvec == G * V;
+  const int per_sm = packed ? (V <= 5 ? 3 : 2) : 2;
+  const int max_blocks = pt_num_sms() * per_sm;
+  if (blocks > max_blocks) blocks = max_blocks;
+#define PT_LN_LAUNCH(GG, VV)                                                                        \
+  do {                                                                                              \
+    if (packed && onepass && full) pt_launch(layernorm_packed_kernel<GG, VV, true, true>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
+    else if (packed && onepass) pt_launch(layernorm_packed_kernel<GG, VV, true, false>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
+    else if (packed && full) pt_launch(layernorm_packed_kernel<GG, VV, false, true>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
+    else if (packed) pt_launch(layernorm_packed_kernel<GG, VV, false, false>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
+    else pt_launch(layernorm_kernel<GG, VV>, dim3(blocks), dim3(256), 0, (void*)st, 1, p);          \
+  } while (0)
 #define PT_LN_G(GG)                                   \
   switch (V) {                                        \
     case 1: PT_LN_LAUNCH(GG, 1); break;               \
