@@ -536,18 +536,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
 
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm, packed variant: the row stays in registers as the bf16 it was loaded as (V x 16 bytes per lane instead of
-// V x 8 floats) and is unpacked once per pass.  LayerNorm at these widths is ISSUE-bound, not HBM-bound: ~75 instructions
-// per 16-byte vector (unpack, sum, centred squares, normalise, pack, affine loads) is ~80 % of the four schedulers at
-// 5 TB/s, which is why deeper prefetch (a cp.async ring with 120 KB in flight per SM) measured SLOWER than this kernel and
-// why what helps is occupancy (80 registers: 3 resident CTAs per SM instead of 2) and fewer instructions:
-//   kOnePass = false: mean, then centred squares — same arithmetic and reduction order as layernorm_kernel, bit-identical;
-//   kOnePass = true : sum and sum of squares in ONE pass over the registers (var = E[x^2] - mean^2 in fp32, clamped at 0):
-//                     one unpack pass and one subtraction per element less.
+// V x 8 floats) and is unpacked once per pass (sum, centred squares, output).  Same arithmetic and the same order of every
+// reduction as layernorm_kernel, so the two are bit-identical; what changes is the register budget: 80 instead of 117,
+// i.e. 3 resident CTAs per SM instead of 2 (level-0 launches 28.7 -> 27.6 us, with the position add 46.2 -> 43.0 us,
+// class 2.49 -> 2.35 ms per step).  Measured and NOT kept (profiles/r3_glue_kernels.md): a cp.async prefetch ring with
+// 120 KB in flight per SM (slower: 32.8 us), 4 CTAs per SM at 64 registers (slower), one-pass statistics (26.7 us, not
+// worth a second set of numerics), predicate-free instantiations (spills at the 80-register cap: 34.8 us).
 // Handles the plain form and addvec + sum_out (the temporal norm_in: the row is re-packed after the add, exactly the
 // bf16 rounding the consumer of sum_out sees); addvec without sum_out keeps the fp32 kernel above.
 // ---------------------------------------------------------------------------------------------------------
-// kFull: C == 8 * G * V exactly (every width of this model), so no lane has a vector slot to predicate off
-template <int G, int V, bool kOnePass, bool kFull>
+template <int G, int V>
 __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel(const LnParams p) {
   constexpr int kRowsPerWarp = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -569,7 +567,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int vi = l + i * G;
-      nxt[i] = (kFull || vi < nvec) ? ldg_nc_u4(src + vi * 8) : make_uint4(0, 0, 0, 0);
+      nxt[i] = (vi < nvec) ? ldg_nc_u4(src + vi * 8) : make_uint4(0, 0, 0, 0);
     }
   }
   for (; grp < n_groups; grp += warps_total) {
@@ -583,7 +581,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int vi = l + i * G;
-        nxt[i] = (kFull || vi < nvec) ? ldg_nc_u4(nsrc + vi * 8) : make_uint4(0, 0, 0, 0);
+        nxt[i] = (vi < nvec) ? ldg_nc_u4(nsrc + vi * 8) : make_uint4(0, 0, 0, 0);
       }
     }
     float s = 0.f;
@@ -592,7 +590,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int vi = l + i * G;
-        if (kFull || vi < nvec) {
+        if (vi < nvec) {
           float v[8];
           unpack_row8(cur[i], v);
           const float4 e0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
@@ -609,67 +607,41 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
         }
       }
     }
-    float mean, rstd;
-    if (kOnePass) {
-      float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const int vi = l + i * G;
-        if (kFull || vi < nvec) {
-          float v[8];
-          unpack_row8(cur[i], v);
+    for (int i = 0; i < V; ++i) {
+      const int vi = l + i * G;
+      if (vi < nvec) {
+        float v[8];
+        unpack_row8(cur[i], v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s += v[j];
-            sq = fmaf(v[j], v[j], sq);
-          }
-        }
+        for (int j = 0; j < 8; ++j) s += v[j];
       }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      }
-      mean = s / (float)p.C;
-      rstd = rsqrtf(fmaxf(sq / (float)p.C - mean * mean, 0.f) + p.eps);
-    } else {
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const int vi = l + i * G;
-        if (kFull || vi < nvec) {
-          float v[8];
-          unpack_row8(cur[i], v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) s += v[j];
-        }
-      }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      mean = s / (float)p.C;
-      float sq = 0.f;
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const int vi = l + i * G;
-        if (kFull || vi < nvec) {
-          float v[8];
-          unpack_row8(cur[i], v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float d = v[j] - mean;
-            sq = fmaf(d, d, sq);
-          }
-        }
-      }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      rstd = rsqrtf(sq / (float)p.C + p.eps);
     }
-    const float nmr = -mean * rstd;  // (v - mean) * rstd as one FMA
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)p.C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int vi = l + i * G;
+      if (vi < nvec) {
+        float v[8];
+        unpack_row8(cur[i], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[j] - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)p.C + p.eps);
     if (live) {
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int vi = l + i * G;
-        if (kFull || vi < nvec) {
+        if (vi < nvec) {
           const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
           const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8) + 1);
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8));
@@ -679,7 +651,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
           float v[8], o[8];
           unpack_row8(cur[i], v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[j], rstd, nmr), gg[j], bb[j]);
+          for (int j = 0; j < 8; ++j) o[j] = fmaf((v[j] - mean) * rstd, gg[j], bb[j]);
           uint4 u;
           u.x = pack_bf16x2(o[0], o[1]);
           u.y = pack_bf16x2(o[2], o[3]);
@@ -895,27 +867,12 @@ extern "C" int pt_layernorm(const PtLayerNormArgs* a, void* stream) {
   const bool packed = packed_env != 0 && (a->addvec == nullptr || a->sum_out != nullptr);
   // persistent grid: as many CTAs as are co-resident (2 per SM for the fp32-row kernel at 117 registers, 3 for the
   // packed one at V <= 5); each warp strides over row groups with the next group's loads in flight
-  static int onepass_env = -1;  // PT_LN_ONEPASS=1: single-pass statistics (E[x^2] - mean^2)
-  if (onepass_env < 0) {
-    const char* e = getenv("PT_LN_ONEPASS");
-    onepass_env = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  const bool onepass = onepass_env != 0;
-  static int full_env = -1;  // PT_LN_FULL=0: keep the per-vector predicates even when C == 8 * G * V
-  if (full_env < 0) {
-    const char* e = getenv("PT_LN_FULL");
-    full_env = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  const bool full = full_env != 0 && nvec == G * V;
   const int per_sm = packed ? (V <= 5 ? 3 : 2) : 2;
   const int max_blocks = pt_num_sms() * per_sm;
   if (blocks > max_blocks) blocks = max_blocks;
 #define PT_LN_LAUNCH(GG, VV)                                                                        \
   do {                                                                                              \
-    if (packed && onepass && full) pt_launch(layernorm_packed_kernel<GG, VV, true, true>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
-    else if (packed && onepass) pt_launch(layernorm_packed_kernel<GG, VV, true, false>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
-    else if (packed && full) pt_launch(layernorm_packed_kernel<GG, VV, false, true>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
-    else if (packed) pt_launch(layernorm_packed_kernel<GG, VV, false, false>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
+    if (packed) pt_launch(layernorm_packed_kernel<GG, VV>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
     else pt_launch(layernorm_kernel<GG, VV>, dim3(blocks), dim3(256), 0, (void*)st, 1, p);          \
   } while (0)
 #define PT_LN_G(GG)                                   \

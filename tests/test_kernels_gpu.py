@@ -191,3 +191,48 @@ def test_conv_direct(cuda_dev, cin, cout, stride, nchw):
     o = out.view(n, oH + 1, oW + 1, 64)
     assert rel_l2(o[:, :oH, :oW, :cout], ref) < 4e-3
     assert o[..., cout:].abs().max() == 0 and o[:, oH].abs().max() == 0
+
+
+_VARIANT_SCRIPT = r"""
+import hashlib, sys, torch
+sys.path.insert(0, ".")
+from posetraj_b200.ops import AttnTemporal, LayerNorm
+sp = torch.cuda.current_stream().cuda_stream
+torch.manual_seed(11)
+h = hashlib.sha256()
+for rows, C, hw, fr in [(1260, 320, 45, 14), (700, 640, 25, 14), (333, 1280, 111, 3), (64, 1024, 64, 1)]:
+    x = (torch.randn(rows, C, device="cuda") + 0.3).to(torch.bfloat16)
+    g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    out = torch.empty_like(x)
+    LayerNorm(x, out, g, b).launch(sp)
+    h.update(out.cpu().view(torch.int16).numpy().tobytes())
+    emb = torch.randn(fr, C, device="cuda")
+    mix = torch.empty_like(x)
+    LayerNorm(x, out, g, b, addvec=emb, hw=hw, frames=fr, sum_out=mix).launch(sp)
+    h.update(out.cpu().view(torch.int16).numpy().tobytes())
+    h.update(mix.cpu().view(torch.int16).numpy().tobytes())
+for B, Fr, HW, heads in [(2, 14, 45, 20), (1, 25, 50, 10), (2, 16, 33, 5)]:
+    C = heads * 64
+    qkv = torch.randn(B * Fr * HW, 3 * C, device="cuda").to(torch.bfloat16)
+    out = torch.zeros(B * Fr * HW, C, device="cuda", dtype=torch.bfloat16)
+    AttnTemporal(qkv, out, batch=B, frames=Fr, hw=HW, heads=heads).launch(sp)
+    h.update(out.cpu().view(torch.int16).numpy().tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_layernorm_and_temporal_attention_variants_are_bit_identical(cuda_dev):
+    """The packed LayerNorm (3 CTAs per SM) and the staged temporal attention (16-byte cp.async + ldmatrix) do the same
+    arithmetic in the same order as the kernels they replace (PT_LN_PACKED=0, PT_TATTN_STAGED=0): identical bits.  The
+    switches are read once per process, so each variant runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for packed, staged in (("1", "1"), ("0", "0")):
+        env = dict(os.environ, PT_LN_PACKED=packed, PT_TATTN_STAGED=staged)
+        r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1], digests

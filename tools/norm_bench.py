@@ -36,6 +36,7 @@ for n_img, H, W, C, per_stat_frames, halo in [(28, 40, 72, 320, 1, True), (28, 4
     rows_out = n_img * (H + 1) * (W + 1) if halo else n_img * H * W
     out = torch.empty(rows_out, C, device="cuda", dtype=torch.bfloat16)
     g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
-    op = GroupNorm(x, out, g, b, stats, rows_per_stat=per_stat_frames * H * W, eps=1e-5, silu=True, halo=(H, W) if halo else None)
-    us = bench(lambda: op.launch(sp))
-    print(f"groupnorm {n_img}x{H}x{W}x{C} frames/stat={per_stat_frames} halo={halo}: {us:.1f} us  {2 * x.numel() * 2 / us / 1e3:.0f} GB/s (algorithmic)")
+    for silu in (True, False):
+        op = GroupNorm(x, out, g, b, stats, rows_per_stat=per_stat_frames * H * W, eps=1e-5, silu=silu, halo=(H, W) if halo else None)
+        us = bench(lambda: op.launch(sp))
+        print(f"groupnorm {n_img}x{H}x{W}x{C} frames/stat={per_stat_frames} halo={halo} silu={silu}: {us:.1f} us  {2 * x.numel() * 2 / us / 1e3:.0f} GB/s (algorithmic)")
