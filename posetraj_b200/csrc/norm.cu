@@ -56,6 +56,7 @@ struct GnParams {
   const double* sums_peers[8];
   int res_slots;  // rows per thread kept resident in shared memory between the two passes
   int res_off;    // byte offset of the resident area in dynamic shared memory
+  unsigned int mW, mH;  // 2^32 / W + 1, 2^32 / H + 1: row -> (image row, image) of the haloed output by multiply-high
 };
 
 PT_DEVICE void cp_async_16(uint32_t smem_dst, const void* gsrc) {
@@ -68,6 +69,67 @@ PT_DEVICE uint4 lds_u4(uint32_t addr) {
   uint4 u;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
   return u;
+}
+
+// Phase 2 of gn_fused_kernel for one thread: normalise (+SiLU) its rows and write the output layout.  Slot i of the thread
+// is row r0 + i * rpar of the statistics group; the first n_res slots are read back from shared memory, the rest from
+// global memory (L2 hits).  Four rows per iteration without predicates, then a one-row tail.  The haloed output row of
+// group row rk is rk + yg + img * (W + 1) with yg = rk / W, img = yg / H (one extra column per image row, one extra row
+// per image), the two divisions as multiply-high by 2^32 / W, 2^32 / H (exact for rk * W < 2^32, checked by the host).
+// The first version of this phase walked (x, y, img) with `while` loops and carried live / resident predicates per row:
+// 157 instructions per 16-byte vector where the arithmetic needs ~60, on a kernel with 3.75 warps per scheduler
+// (ncu: 61 % of the level-0 launch's samples, spread thin over fixed-latency stalls; profiles/r3_glue_kernels.md).
+template <bool kSilu, bool kHalo>
+PT_DEVICE void gn_apply_rows(const GnParams& p, const float (&sc)[8], const float (&sh)[8], const bf16* base, int ld,
+                             bf16* out_base, int r0, int rpar, int n_my, int n_res, uint32_t res_u32, uint32_t res_stride) {
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const int W1 = p.W + 1;
+  auto emit = [&](const uint4 u, const int rk) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = fmaf(v[j], sc[j], sh[j]);
+      if (kSilu) v[j] = silu_f(v[j]);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    if (kHalo) {
+      const int yg = p.W > 1 ? (int)__umulhi((unsigned)rk, p.mW) : rk;
+      const int img = p.H > 1 ? (int)__umulhi((unsigned)yg, p.mH) : yg;
+      bf16* dst = out_base + (size_t)(rk + yg + img * W1) * p.out_ld;
+      stg_u4(dst, o);
+      // the zero halo: one extra column right of every image row, one extra row below every image
+      const bool last_x = rk - yg * p.W == p.W - 1;
+      if (last_x) stg_u4(dst + p.out_ld, zero4);
+      if (yg - img * p.H == p.H - 1) {
+        stg_u4(dst + (size_t)W1 * p.out_ld, zero4);
+        if (last_x) stg_u4(dst + (size_t)(W1 + 1) * p.out_ld, zero4);
+      }
+    } else {
+      stg_u4(out_base + (size_t)rk * p.out_ld, o);
+    }
+  };
+  int i = 0;
+  for (; i + 4 <= n_res; i += 4) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = lds_u4(res_u32 + (uint32_t)(i + k) * res_stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(u[k], r0 + (i + k) * rpar);
+  }
+  for (; i < n_res; ++i) emit(lds_u4(res_u32 + (uint32_t)i * res_stride), r0 + i * rpar);
+  for (; i + 4 <= n_my; i += 4) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = ldg_u4(base + (size_t)(r0 + (i + k) * rpar) * ld);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(u[k], r0 + (i + k) * rpar);
+  }
+  for (; i < n_my; ++i) emit(ldg_u4(base + (size_t)(r0 + i * rpar) * ld), r0 + i * rpar);
 }
 
 // kCluster: the CTAs of one statistics group form ONE thread-block cluster (<= 16 CTAs, every row resident in shared
@@ -322,69 +384,16 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
       sh[j] = be[j] - s_mean[g] * sc[j];
     }
   }
-  const int HW = p.H * p.W;
-  const int W1 = p.W + 1;
-  const int P = (p.H + 1) * W1;
-  const int imgs_per_stat = p.halo ? p.rows_per_stat / HW : 1;
-  const size_t out_rows_per_stat = p.halo ? (size_t)imgs_per_stat * P : (size_t)p.rows_per_stat;
+  const size_t out_rows_per_stat =
+      p.halo ? (size_t)(p.rows_per_stat / (p.H * p.W)) * (size_t)((p.H + 1) * (p.W + 1)) : (size_t)p.rows_per_stat;
   bf16* out_base = p.out + (size_t)stat * out_rows_per_stat * p.out_ld + c;
-  int r = r_begin + tr;
-  int img = 0, y = 0, x = 0;
+  const int r0 = r_begin + tr;
   if (p.halo) {
-    img = r / HW;
-    const int rem = r - img * HW;
-    y = rem / p.W;
-    x = rem - y * p.W;
-  }
-  const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  int slot = 0;  // index of row r among this thread's rows
-  for (; r < r_end; r += 4 * rpar, slot += 4) {
-    uint4 u[4];
-    bool live[4];
-    size_t orow[4];
-    int px[4], py[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int rk = r + k * rpar;
-      live[k] = rk < r_end;
-      orow[k] = (size_t)rk;
-      px[k] = py[k] = -1;
-      if (p.halo) {
-        orow[k] = (size_t)img * P + (size_t)y * W1 + x;
-        px[k] = x;
-        py[k] = y;
-        x += rpar;
-        while (x >= p.W) { x -= p.W; ++y; }
-        while (y >= p.H) { y -= p.H; ++img; }
-      }
-      u[k] = !live[k] ? zero4 : (slot + k < n_res ? lds_u4(res_u32 + (uint32_t)(slot + k) * res_stride) : ldg_u4(base + (size_t)rk * ld));
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!live[k]) continue;
-      const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), cc = unpack_bf16x2(u[k].z), d = unpack_bf16x2(u[k].w);
-      float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = fmaf(v[j], sc[j], sh[j]);
-        if (p.silu) v[j] = silu_f(v[j]);
-      }
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]);
-      o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]);
-      o.w = pack_bf16x2(v[6], v[7]);
-      bf16* dst = out_base + orow[k] * p.out_ld;
-      stg_u4(dst, o);
-      if (p.halo) {
-        // the zero halo: one extra column right of every image row, one extra row below every image
-        if (px[k] == p.W - 1) stg_u4(dst + p.out_ld, zero4);
-        if (py[k] == p.H - 1) {
-          stg_u4(dst + (size_t)W1 * p.out_ld, zero4);
-          if (px[k] == p.W - 1) stg_u4(dst + (size_t)(W1 + 1) * p.out_ld, zero4);
-        }
-      }
-    }
+    if (p.silu) gn_apply_rows<true, true>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride);
+    else gn_apply_rows<false, true>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride);
+  } else {
+    if (p.silu) gn_apply_rows<true, false>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride);
+    else gn_apply_rows<false, false>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride);
   }
 }
 
@@ -766,6 +775,9 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   p.out = reinterpret_cast<bf16*>(a->out);
   p.out_ld = a->out_ld;
   p.halo = a->halo; p.H = a->H > 0 ? a->H : 1; p.W = a->W > 0 ? a->W : 1;
+  p.mW = p.W > 1 ? 0xFFFFFFFFu / (unsigned)p.W + 1u : 0u;
+  p.mH = p.H > 1 ? 0xFFFFFFFFu / (unsigned)p.H + 1u : 0u;
+  PT_CHECK_ARG(!a->halo || (long long)a->rows_per_stat * p.W < (1ll << 32), "pt_groupnorm: rows_per_stat * W must stay below 2^32");
   p.mode = a->mode; p.sums = a->sums; p.count = a->count;
   p.n_peers = a->mode == 2 ? a->n_peers : 0;
   PT_CHECK_ARG(p.n_peers >= 0 && p.n_peers <= 8, "pt_groupnorm: at most 8 peers");
