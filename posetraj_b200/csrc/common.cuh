@@ -78,6 +78,17 @@ PT_DEVICE float rcp_approx(float x) {
 // instructions and the GroupNorm+SiLU pass is issue-bound with it (profiles/r1g_groupnorm.md)
 PT_DEVICE float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
+// SiLU of x = 2h as h + h tanh(h) with ONE MUFU (tanh.approx.f32, max relative error 2^-11 on the tanh).  Relative error
+// of the result <= 2.5e-4 for x >= -1 and below the bf16 rounding (2^-9) down to x = -3; further out in the negative tail
+// (0.13 % of a unit normal) the cancellation in 1 + tanh(h) leaves an ABSOLUTE error <= |h| 4.9e-4 ~ 1e-3 on values
+// |silu| < 0.14, i.e. the size of the bf16 rounding of an ordinary O(0.5) activation.  For the GroupNorm + SiLU apply phase,
+// which is MUFU-queue bound with ex2 + rcp per element (ncu stall_mio on the MUFU instructions, profiles/r3_glue_kernels.md).
+PT_DEVICE float silu_half_tanh(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 // GEGLU gate  value * gelu_erf(g)  = value * g * Phi(g)  for the tensor-core epilogues (gemm.cu, mlp.cu), where it is
 // evaluated 128 x 64 times per hidden chunk and bounds the kernel (profiles/r1b, r2).  Phi(g) is evaluated as
 //     sigmoid(2 g (c0 + c1 s + c2 s^2)),  s = min(g^2, 81)

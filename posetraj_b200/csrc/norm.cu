@@ -79,7 +79,8 @@ PT_DEVICE uint4 lds_u4(uint32_t addr) {
 // The first version of this phase walked (x, y, img) with `while` loops and carried live / resident predicates per row:
 // 157 instructions per 16-byte vector where the arithmetic needs ~60, on a kernel with 3.75 warps per scheduler
 // (ncu: 61 % of the level-0 launch's samples, spread thin over fixed-latency stalls; profiles/r3_glue_kernels.md).
-template <bool kSilu, bool kHalo>
+// kSilu: 0 none, 1 x * sigmoid(x) with ex2 + rcp, 2 h + h tanh(h) (sc / sh then carry the factor 1/2: h = x / 2)
+template <int kSilu, bool kHalo>
 PT_DEVICE void gn_apply_rows(const GnParams& p, const float (&sc)[8], const float (&sh)[8], const bf16* base, int ld,
                              bf16* out_base, int r0, int rpar, int n_my, int n_res, uint32_t res_u32, uint32_t res_stride) {
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
@@ -90,7 +91,8 @@ PT_DEVICE void gn_apply_rows(const GnParams& p, const float (&sc)[8], const floa
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[j] = fmaf(v[j], sc[j], sh[j]);
-      if (kSilu) v[j] = silu_f(v[j]);
+      if (kSilu == 1) v[j] = silu_f(v[j]);
+      if (kSilu == 2) v[j] = silu_half_tanh(v[j]);
     }
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]);
@@ -388,13 +390,24 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnParams p) {
       p.halo ? (size_t)(p.rows_per_stat / (p.H * p.W)) * (size_t)((p.H + 1) * (p.W + 1)) : (size_t)p.rows_per_stat;
   bf16* out_base = p.out + (size_t)stat * out_rows_per_stat * p.out_ld + c;
   const int r0 = r_begin + tr;
-  if (p.halo) {
-    if (p.silu) gn_apply_rows<true, true>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride);
-    else gn_apply_rows<false, true>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride);
-  } else {
-    if (p.silu) gn_apply_rows<true, false>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride);
-    else gn_apply_rows<false, false>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride);
+  if (p.silu == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] *= 0.5f;
+      sh[j] *= 0.5f;
+    }
   }
+#define PT_GN_APPLY(SILU, HALO) gn_apply_rows<SILU, HALO>(p, sc, sh, base, ld, out_base, r0, rpar, n_my, n_res, res_u32, res_stride)
+  if (p.halo) {
+    if (p.silu == 2) PT_GN_APPLY(2, true);
+    else if (p.silu) PT_GN_APPLY(1, true);
+    else PT_GN_APPLY(0, true);
+  } else {
+    if (p.silu == 2) PT_GN_APPLY(2, false);
+    else if (p.silu) PT_GN_APPLY(1, false);
+    else PT_GN_APPLY(0, false);
+  }
+#undef PT_GN_APPLY
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -772,6 +785,14 @@ extern "C" int pt_groupnorm(const PtGroupNormArgs* a, void* stream) {
   p.depart = reinterpret_cast<unsigned int*>(ws + 4096);
   p.partials = reinterpret_cast<double*>(ws + 8192);
   p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
+  {
+    static int silu_tanh_env = -1;  // PT_GN_SILU_TANH=0: x * sigmoid(x) with ex2 + rcp (two MUFU per element) instead of h + h tanh(h)
+    if (silu_tanh_env < 0) {
+      const char* e = getenv("PT_GN_SILU_TANH");
+      silu_tanh_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (p.silu != 0 && silu_tanh_env != 0) p.silu = 2;
+  }
   p.out = reinterpret_cast<bf16*>(a->out);
   p.out_ld = a->out_ld;
   p.halo = a->halo; p.H = a->H > 0 ? a->H : 1; p.W = a->W > 0 ? a->W : 1;

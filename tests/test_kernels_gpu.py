@@ -54,6 +54,30 @@ def test_groupnorm(cuda_dev, n_img, H, W, c0, c1, frames_per_stat, halo, silu):
     assert rel_l2(got, ref) < 6e-3
 
 
+def test_groupnorm_silu_negative_tail(cuda_dev):
+    """The apply phase evaluates SiLU as h + h tanh(h), h = x / 2, with ONE tanh.approx (common.cuh silu_half_tanh).  Its
+    weak spot is the cancellation 1 + tanh(h) for very negative x; a shifted affine (beta = -3, gamma = 1.5) puts most
+    of the tensor there.  Bound: the bf16 rounding of the result plus 1.5e-3 absolute (|h| * 2^-11 at x = -6)."""
+    from posetraj_b200.ops import GroupNorm
+    torch.manual_seed(21)
+    n_img, H, W, Cc = 4, 10, 18, 320
+    x = rnd(n_img * H * W, Cc)
+    gamma = torch.full((Cc,), 1.5, device="cuda")
+    beta = torch.full((Cc,), -3.0, device="cuda")
+    stats = torch.zeros((2 * n_img + 4 * 148 + 64) * 64 + 1024, device="cuda", dtype=torch.float64)
+    out = torch.empty(n_img * H * W, Cc, device="cuda", dtype=torch.bfloat16)
+    GroupNorm(x, out, gamma, beta, stats, rows_per_stat=H * W, eps=1e-5, silu=True).launch(sp())
+    torch.cuda.synchronize()
+    xr = x.float().view(n_img, H * W, Cc).permute(0, 2, 1)
+    pre = F.group_norm(xr, 32, gamma, beta, eps=1e-5)
+    ref = F.silu(pre).permute(0, 2, 1).reshape(n_img * H * W, Cc)
+    assert float(pre.min()) < -7.0 and float((pre < -3).float().mean()) > 0.4       # the tail is really exercised
+    err = (out.float() - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + 1.5e-3
+    assert bool((err <= bound).all()), float((err - bound).max())
+    assert rel_l2(out, ref) < 6e-3
+
+
 @pytest.mark.parametrize("rows,Cc", [(1000, 320), (333, 640), (77, 1280)])
 def test_layernorm(cuda_dev, rows, Cc):
     from posetraj_b200.ops import LayerNorm
