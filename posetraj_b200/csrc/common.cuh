@@ -104,6 +104,22 @@ PT_DEVICE float geglu_gate_fast(float value, float g) {
   return value * g * rcp_approx(1.0f + e);       // g * sigmoid(2u); e = +inf for very negative g gives exactly 0
 }
 
+// The same gate with ONE MUFU: sigmoid(2u) = (1 + tanh(u)) / 2, so value * g * Phi(g) = hv + hv tanh(u) with
+// hv = value * g / 2 and u = g (c0 + c1 s + c2 s^2) (the same re-fitted quintic, without the exponential's -2 log2(e)).
+// tanh.approx.f32 is good to 2^-11 relative: the result is within 2.5e-4 relative for g >= -1; in the negative tail the
+// cancellation 1 + tanh(u) leaves an absolute error <= |hv| 4.9e-4, below the bf16 rounding of an ordinary gated value
+// (same argument as silu_half_tanh).  11.5 issue slots and one MUFU per gate instead of 12.5 and two: the gate evaluation
+// bounds the fused feed-forward (mlp.cu) and its MUFU queue is what the gate warps stall on.
+PT_DEVICE float geglu_gate_tanh(float value, float g) {
+  const float s = fminf(g * g, 81.0f);
+  float poly = fmaf(-3.53110710e-04f, s, 3.70155061e-02f);
+  poly = fmaf(poly, s, 7.97496957e-01f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(poly * g));
+  const float hv = (0.5f * value) * g;
+  return fmaf(hv, t, hv);
+}
+
 // exact (erf) GELU, as diffusers' GEGLU uses F.gelu(gate) with approximate="none"
 PT_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

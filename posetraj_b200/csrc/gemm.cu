@@ -109,7 +109,7 @@ PT_DEVICE uint4 pack8(const float* v) {
 }
 
 // GEGLU gate: see geglu_gate_fast in common.cuh (value * g * Phi(g), Phi re-fitted to the exact erf GELU, 2.6e-5 abs).
-PT_DEVICE float geglu_gate(float value, float g) { return geglu_gate_fast(value, g); }
+PT_DEVICE float geglu_gate(float value, float g) { return geglu_gate_tanh(value, g); }
 
 // activation codes of PtGemmArgs.act_silu: 1 SiLU, 2 GELU (exact erf), 3 quick-GELU x*sigmoid(1.702 x)
 PT_DEVICE float apply_act(int act, float v) {

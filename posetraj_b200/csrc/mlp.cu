@@ -50,7 +50,7 @@ struct alignas(64) MlpTmap {
   uint64_t opaque[16];
 };
 
-PT_DEVICE float mlp_gate(float value, float g) { return geglu_gate_fast(value, g); }
+PT_DEVICE float mlp_gate(float value, float g) { return geglu_gate_tanh(value, g); }
 
 // debug trace: slot = event id, up to 64 chunks per role
 PT_DEVICE void mlp_stamp(long long* trace, int role, int ev, uint32_t chunk) {

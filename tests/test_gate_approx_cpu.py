@@ -46,3 +46,24 @@ def test_gate_is_much_closer_than_the_textbook_tanh_form():
     exact = np.array([x * 0.5 * (1.0 + math.erf(x / math.sqrt(2.0))) for x in g])
     tanh_form = 0.5 * g * (1 + np.tanh(math.sqrt(2 / math.pi) * (g + 0.044715 * g ** 3)))
     assert np.abs(gate_np(g) - exact).max() * 10 < np.abs(tanh_form - exact).max()
+
+
+def test_tanh_form_is_the_same_function():
+    """`geglu_gate_tanh` (one MUFU: hv + hv tanh(u)) is `geglu_gate_fast` rewritten with sigmoid(2u) = (1 + tanh(u)) / 2: the
+    same three constants, and with an exact tanh the same 3e-5 bound against the erf GELU; what the hardware tanh.approx
+    (2^-11 relative) adds is bounded on the GPU in tests/test_gemm_gpu.py."""
+    src = (Path(__file__).resolve().parents[1] / "posetraj_b200" / "csrc" / "common.cuh").read_text()
+    body = src[src.index("PT_DEVICE float geglu_gate_tanh"):]
+    body = body[: body.index("}")]
+    c = [float(x) for x in re.findall(r"(-?\d\.\d+e[+-]\d+)f", body)]
+    assert (c[2], c[1], c[0]) == _constants()
+    c0, c1, c2 = _constants()
+    g = np.concatenate([np.linspace(-30, 30, 600001), np.linspace(-1e3, 1e3, 2001)]).astype(np.float32)
+    s = np.minimum(g * g, np.float32(81.0))
+    poly = (np.float32(c2) * s + np.float32(c1)).astype(np.float32)
+    poly = (poly * s + np.float32(c0)).astype(np.float32)
+    u = (poly * g).astype(np.float32)
+    hv = (np.float32(0.5) * g).astype(np.float32)
+    got = (hv * np.tanh(u.astype(np.float64)).astype(np.float32) + hv).astype(np.float64)
+    exact = np.array([x * 0.5 * (1.0 + math.erf(x / math.sqrt(2.0))) for x in g.astype(np.float64)])
+    assert np.abs(got - exact).max() < 3e-5

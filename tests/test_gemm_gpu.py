@@ -116,6 +116,29 @@ def test_geglu(cuda_dev, pair, M, C, bn):
     assert rel_l2(out, ref) < TOL
 
 
+def test_geglu_gate_pointwise_incl_negative_tail(cuda_dev):
+    """The epilogue's gate is value * g * Phi(g) as hv + hv tanh(u) with ONE tanh.approx (common.cuh geglu_gate_tanh).  With a
+    one-hot weight matrix the GEMM is a copy, so every output is the gate of a known (value, g) pair: gates from -9 to +9,
+    element-wise bound = bf16 rounding of the result + |value g| * 3e-4 (tanh.approx is good to 2^-11 relative; the
+    cancellation 1 + tanh(u) in the negative tail turns that into an absolute error of that size)."""
+    from posetraj_b200.ops import Gemm
+    torch.manual_seed(14)
+    M, C = 1024, 128
+    a = torch.zeros(M, C, device="cuda")
+    a[:, :64] = torch.randn(M, 64, device="cuda") * 2.0                       # values
+    a[:, 64:] = torch.linspace(-9.0, 9.0, M * 64, device="cuda").view(M, 64)   # gates
+    a = a.to(torch.bfloat16)
+    w = torch.eye(C, device="cuda")                 # rows 0..63 -> x (values), rows 64..127 -> g (gates)
+    out = torch.empty(M, 64, device="cuda", dtype=torch.bfloat16)
+    Gemm(a, w.to(torch.bfloat16), out, geglu=True).launch(sp())
+    torch.cuda.synchronize()
+    x, g = a.float()[:, :64], a.float()[:, 64:]
+    ref = x * F.gelu(g)
+    err = (out.float() - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + (x * g).abs() * 3e-4 + 1e-6
+    assert bool((err <= bound).all()), float((err - bound).max())
+
+
 @pytest.mark.parametrize("pair", [False, True])
 def test_two_k_sources(cuda_dev, pair):
     from posetraj_b200.ops import Gemm
