@@ -567,7 +567,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
 // Handles the plain form and addvec + sum_out (the temporal norm_in: the row is re-packed after the add, exactly the
 // bf16 rounding the consumer of sum_out sees); addvec without sum_out keeps the fp32 kernel above.
 // ---------------------------------------------------------------------------------------------------------
-template <int G, int V>
+// kFull (needs C == 8 * G * V, every width of this model): no lane has a vector slot to predicate off (-24 % instructions)
+// and gamma | beta are staged in shared memory once per CTA.  Pays on the position-add form (45.1 -> 36.9 us at level 0);
+// on the plain form it changes nothing at level 0 and its prologue costs 2 us on the small tensors, so the host uses it
+// for the position-add launches only.
+template <int G, int V, bool kFull>
 __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel(const LnParams p) {
   constexpr int kRowsPerWarp = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -576,6 +580,16 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int n_groups = (p.rows + kRowsPerWarp - 1) / kRowsPerWarp;
   int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // gamma | beta staged once per CTA: as global loads in the output pass they sat behind the statistics in program order
+  // (no registers left to hoist them) and their latency was exposed once per vector (ncu: 44 % long-scoreboard stalls)
+  extern __shared__ __align__(16) float s_gb[];
+  if (kFull) {
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+      s_gb[i] = __ldg(p.gamma + i);
+      s_gb[p.C + i] = __ldg(p.beta + i);
+    }
+    __syncthreads();
+  }
   griddep_launch();
   griddep_wait();
   if (grp >= n_groups) return;
@@ -589,7 +603,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int vi = l + i * G;
-      nxt[i] = (vi < nvec) ? ldg_nc_u4(src + vi * 8) : make_uint4(0, 0, 0, 0);
+      nxt[i] = (kFull || vi < nvec) ? ldg_nc_u4(src + vi * 8) : make_uint4(0, 0, 0, 0);
     }
   }
   for (; grp < n_groups; grp += warps_total) {
@@ -603,7 +617,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int vi = l + i * G;
-        nxt[i] = (vi < nvec) ? ldg_nc_u4(nsrc + vi * 8) : make_uint4(0, 0, 0, 0);
+        nxt[i] = (kFull || vi < nvec) ? ldg_nc_u4(nsrc + vi * 8) : make_uint4(0, 0, 0, 0);
       }
     }
     float s = 0.f;
@@ -612,7 +626,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int vi = l + i * G;
-        if (vi < nvec) {
+        if (kFull || vi < nvec) {
           float v[8];
           unpack_row8(cur[i], v);
           const float4 e0 = __ldg(reinterpret_cast<const float4*>(av + vi * 8));
@@ -632,7 +646,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int vi = l + i * G;
-      if (vi < nvec) {
+      if (kFull || vi < nvec) {
         float v[8];
         unpack_row8(cur[i], v);
 #pragma unroll
@@ -646,7 +660,7 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int vi = l + i * G;
-      if (vi < nvec) {
+      if (kFull || vi < nvec) {
         float v[8];
         unpack_row8(cur[i], v);
 #pragma unroll
@@ -663,11 +677,19 @@ __global__ void __launch_bounds__(256, (V <= 5 ? 3 : 2)) layernorm_packed_kernel
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int vi = l + i * G;
-        if (vi < nvec) {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8) + 1);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8) + 1);
+        if (kFull || vi < nvec) {
+          float4 g0, g1, b0, b1;
+          if (kFull) {
+            g0 = *reinterpret_cast<const float4*>(s_gb + vi * 8);
+            g1 = *reinterpret_cast<const float4*>(s_gb + vi * 8 + 4);
+            b0 = *reinterpret_cast<const float4*>(s_gb + p.C + vi * 8);
+            b1 = *reinterpret_cast<const float4*>(s_gb + p.C + vi * 8 + 4);
+          } else {
+            g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
+            g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8) + 1);
+            b0 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8));
+            b1 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8) + 1);
+          }
           const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float v[8], o[8];
@@ -900,12 +922,19 @@ extern "C" int pt_layernorm(const PtLayerNormArgs* a, void* stream) {
   const bool packed = packed_env != 0 && (a->addvec == nullptr || a->sum_out != nullptr);
   // persistent grid: as many CTAs as are co-resident (2 per SM for the fp32-row kernel at 117 registers, 3 for the
   // packed one at V <= 5); each warp strides over row groups with the next group's loads in flight
+  static int full_env = -1;  // PT_LN_FULL=0: keep the per-vector predicates even when C == 8 * G * V
+  if (full_env < 0) {
+    const char* e = getenv("PT_LN_FULL");
+    full_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool full = full_env != 0 && nvec == G * V && a->addvec != nullptr && a->rows >= 16384;  // levels 0 / 1
   const int per_sm = packed ? (V <= 5 ? 3 : 2) : 2;
   const int max_blocks = pt_num_sms() * per_sm;
   if (blocks > max_blocks) blocks = max_blocks;
 #define PT_LN_LAUNCH(GG, VV)                                                                        \
   do {                                                                                              \
-    if (packed) pt_launch(layernorm_packed_kernel<GG, VV>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
+    if (packed && full) pt_launch(layernorm_packed_kernel<GG, VV, true>, dim3(blocks), dim3(256), (size_t)a->C * 8, (void*)st, 1, p); \
+    else if (packed) pt_launch(layernorm_packed_kernel<GG, VV, false>, dim3(blocks), dim3(256), 0, (void*)st, 1, p); \
     else pt_launch(layernorm_kernel<GG, VV>, dim3(blocks), dim3(256), 0, (void*)st, 1, p);          \
   } while (0)
 #define PT_LN_G(GG)                                   \
