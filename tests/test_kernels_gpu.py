@@ -224,7 +224,7 @@ from posetraj_b200.ops import AttnTemporal, LayerNorm
 sp = torch.cuda.current_stream().cuda_stream
 torch.manual_seed(11)
 h = hashlib.sha256()
-for rows, C, hw, fr in [(1260, 320, 45, 14), (700, 640, 25, 14), (333, 1280, 111, 3), (64, 1024, 64, 1)]:
+for rows, C, hw, fr in [(1260, 320, 45, 14), (700, 640, 25, 14), (333, 1280, 111, 3), (64, 1024, 64, 1), (16800, 320, 600, 14), (16390, 640, 1639, 5)]:
     x = (torch.randn(rows, C, device="cuda") + 0.3).to(torch.bfloat16)
     g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
     out = torch.empty_like(x)
