@@ -158,27 +158,34 @@ struct UpsampleParams {
   int n, H, W, C, halo, scale;
 };
 
+// One thread per INPUT vector (16 bytes): one load, scale x scale stores plus the zero halo it is responsible for (the
+// column right of the last pixel of a row, the row below the last row of an image).  blockIdx.y walks the input image
+// rows, so the only integer division is x = i / cvec.  (The first version ran one thread per OUTPUT vector with six 64-bit
+// divisions each: ~300 instructions per 16 bytes, 0.40 of the HBM copy rate.)
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p) {
   griddep_launch();
   griddep_wait();
   const int cvec = p.C >> 3;
   const int sc = p.scale;
   const int oW = sc * p.W + (p.halo ? 1 : 0), oH = sc * p.H + (p.halo ? 1 : 0);
-  const long long total = (long long)p.n * oH * oW * cvec;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % cvec);
-    const long long orow = idx / cvec;
-    const int ox = (int)(orow % oW);
-    const long long t2 = orow / oW;
-    const int oy = (int)(t2 % oH);
-    const int img = (int)(t2 / oH);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (oy < sc * p.H && ox < sc * p.W) {
-      const size_t irow = ((size_t)img * p.H + (oy / sc)) * p.W + (ox / sc);
-      v = ldg_u4(p.x + irow * p.ld + cv * 8);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.W * cvec) return;
+  const int x = i / cvec, cv = i - x * cvec;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int yrow = blockIdx.y; yrow < p.n * p.H; yrow += gridDim.y) {
+    const int img = yrow / p.H, y = yrow - img * p.H;
+    const uint4 v = ldg_u4(p.x + ((size_t)yrow * p.W + x) * p.ld + cv * 8);
+    bf16* o = p.out + (((size_t)img * oH + (size_t)(sc * y)) * oW + (size_t)(sc * x)) * p.out_ld + cv * 8;
+    for (int dy = 0; dy < sc; ++dy)
+      for (int dx = 0; dx < sc; ++dx) stg_u4(o + ((size_t)dy * oW + dx) * p.out_ld, v);
+    if (p.halo) {
+      if (x == p.W - 1)
+        for (int dy = 0; dy < sc; ++dy) stg_u4(o + ((size_t)dy * oW + sc) * p.out_ld, zero4);
+      if (y == p.H - 1) {
+        for (int dx = 0; dx < sc; ++dx) stg_u4(o + ((size_t)sc * oW + dx) * p.out_ld, zero4);
+        if (x == p.W - 1) stg_u4(o + ((size_t)sc * oW + sc) * p.out_ld, zero4);
+      }
     }
-    stg_u4(p.out + (size_t)orow * p.out_ld + cv * 8, v);
   }
 }
 
@@ -465,11 +472,10 @@ extern "C" int pt_upsample2x(const PtUpsampleArgs* a, void* stream) {
   p.out = reinterpret_cast<bf16*>(a->out); p.out_ld = a->out_ld;
   p.n = a->n; p.H = a->H; p.W = a->W; p.C = a->C; p.halo = a->halo;
   p.scale = (a->scale == 1) ? 1 : 2;
-  const long long total = (long long)a->n * (2 * a->H + 1) * (2 * a->W + 1) * (a->C / 8);
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)pt_num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  pt_launch(upsample2x_kernel, dim3((int)blocks), dim3(256), 0, (void*)stream, 1, p);
+  const int wc = a->W * (a->C / 8);
+  long long rows = (long long)a->n * a->H;
+  if (rows > 65535) rows = 65535;   // the kernel strides over the remaining image rows
+  pt_launch(upsample2x_kernel, dim3((unsigned)((wc + 255) / 256), (unsigned)rows), dim3(256), 0, (void*)stream, 1, p);
   return pt_launched("pt_upsample2x");
 }
 

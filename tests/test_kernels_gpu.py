@@ -178,6 +178,19 @@ def test_upsample_and_layout(cuda_dev):
     ref = F.interpolate(x.float().view(n, H, W, Cc).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
     assert torch.equal(o[:, :2 * H, :2 * W].float(), ref)
     assert o[:, 2 * H].abs().max() == 0 and o[:, :, 2 * W].abs().max() == 0
+    # compact output, and scale 1 (a copy into the haloed layout), at a width that is not a multiple of the block
+    n, H, W, Cc = 2, 7, 36, 640
+    x = rnd(n * H * W, Cc)
+    xi = x.float().view(n, H, W, Cc)
+    out = torch.full((n * 2 * H * 2 * W, Cc), 3.0, device="cuda", dtype=torch.bfloat16)
+    Upsample2x(x, out, n=n, H=H, W=W, halo=False).launch(sp())
+    torch.cuda.synchronize()
+    assert torch.equal(out.float().view(n, 2 * H, 2 * W, Cc), xi.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    out = torch.full((n * (H + 1) * (W + 1), Cc), 3.0, device="cuda", dtype=torch.bfloat16)
+    Upsample2x(x, out, n=n, H=H, W=W, halo=True, scale=1).launch(sp())
+    torch.cuda.synchronize()
+    o = out.float().view(n, H + 1, W + 1, Cc)
+    assert torch.equal(o[:, :H, :W], xi) and o[:, H].abs().max() == 0 and o[:, :, W].abs().max() == 0
     for dt in (torch.float32, torch.bfloat16):
         for halo in (False, True):
             src = torch.randn(4, 40, 7, 11, device="cuda").to(dt).contiguous()
