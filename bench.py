@@ -51,7 +51,7 @@ def _peaks():
 
 def _ncu_traffic(kind):
     """Per-launch DRAM traffic of a kernel class from the committed ncu capture (None if the file is absent)."""
-    path = os.path.join(ROOT, "profiles", "r2z_dram_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r3z_dram_traffic.json")
     try:
         with open(path) as f:
             return json.load(f)["classes"][kind]["traffic_bytes_per_launch"]
@@ -794,7 +794,7 @@ def run_own(args):
                     "launches_per_step": int(round(gem["launches"])), "avg_launch_ms": gem["ms"] / gem["launches"],
                     "share_of_step": gem["ms"] / total_ms, "traffic": _ncu_traffic("gemm"),
                     "algorithmic_bytes_per_launch": gem["bytes"] / gem["launches"],
-                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the pt_gemm launches of one step, from the committed ncu capture profiles/r2z_dram_traffic.json (bytes); algorithmic_bytes_per_launch = A rows once + weights + epilogue operands + outputs"}
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the pt_gemm launches of one step, from the committed ncu capture profiles/r3z_dram_traffic.json (bytes); algorithmic_bytes_per_launch = A rows once + weights + epilogue operands + outputs"}
         per_class = {}
         for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
             e = {"ms": round(c["ms"], 4), "launches": int(round(c["launches"])), "share": round(c["ms"] / total_ms, 4)}
