@@ -1,6 +1,6 @@
 """Micro-benchmark of LayerNorm and temporal attention at the shapes of one denoise step (CUDA events, L2 flushed).
 The kernel variants are chosen by environment variables read once per process (PT_LN_PACKED, PT_LN_RING, PT_TATTN_STAGED),
-so tools/r2_glue_ab.sh runs this once per variant."""
+so tools/r3_ln.sh runs this once per variant."""
 import os
 import sys
 import torch
@@ -9,7 +9,7 @@ from posetraj_b200.ops import AttnTemporal, LayerNorm
 
 sp = torch.cuda.current_stream().cuda_stream
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-print({k: os.environ.get(k) for k in ("PT_LN_PACKED", "PT_LN_RING", "PT_TATTN_STAGED")})
+print({k: os.environ.get(k) for k in ("PT_LN_PACKED", "PT_LN_FULL", "PT_TATTN_STAGED")})
 
 
 def bench(fn, iters=11):
