@@ -1,5 +1,5 @@
 """Micro-benchmark of LayerNorm and temporal attention at the shapes of one denoise step (CUDA events, L2 flushed).
-The kernel variants are chosen by environment variables read once per process (PT_LN_PACKED, PT_LN_RING, PT_TATTN_STAGED),
+The kernel variants are chosen by environment variables read once per process (PT_LN_PACKED, PT_LN_FULL, PT_TATTN_STAGED),
 so tools/r3_ln.sh runs this once per variant."""
 import os
 import sys
